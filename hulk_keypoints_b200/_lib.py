@@ -1,0 +1,114 @@
+"""ctypes binding of libhulk_sm100.so (C ABI declared in include/hulk_sm100.h).
+
+There is NO fallback: if the shared library is missing, or a call fails, a RuntimeError is raised.
+The library is built in-tree by `python -m hulk_keypoints_b200.build` (or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libhulk_sm100.so")
+
+# enums of include/hulk_sm100.h
+HK_F32, HK_BF16, HK_F64 = 0, 1, 2
+HK_CONV_TCGEN05, HK_CONV_FFMA = 0, 1
+ABI_VERSION = 1
+
+EXPORTS = (
+    "hk_version", "hk_last_error", "hk_check_device", "hk_pack_conv_weights", "hk_conv_bn_act_fwd",
+    "hk_maxpool3x3s2_fwd", "hk_head_fwd", "hk_argmax_workspace_bytes", "hk_argmax_decode",
+    "hk_gauss_targets", "hk_bce_workspace_bytes", "hk_bce_fwd_bwd",
+)
+
+
+class HkConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "batch", "in_h", "in_w", "in_c", "out_h", "out_w", "out_c", "kh", "kw", "stride", "pad", "dil",
+        "relu", "in_dtype", "out_dtype", "in_is_nchw", "algo")]
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _declare(lib):
+    vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    lib.hk_version.restype = i
+    lib.hk_version.argtypes = []
+    lib.hk_last_error.restype = C.c_char_p
+    lib.hk_last_error.argtypes = []
+    lib.hk_check_device.restype = i
+    lib.hk_check_device.argtypes = []
+    lib.hk_pack_conv_weights.restype = i
+    lib.hk_pack_conv_weights.argtypes = [vp, vp, vp, vp, vp, f, i, i, i, i, i, vp, vp, vp, vp]
+    lib.hk_conv_bn_act_fwd.restype = i
+    lib.hk_conv_bn_act_fwd.argtypes = [C.POINTER(HkConvDesc), vp, vp, vp, vp, vp, vp, vp]
+    lib.hk_maxpool3x3s2_fwd.restype = i
+    lib.hk_maxpool3x3s2_fwd.argtypes = [vp, vp, i, i, i, i, i, i, i, vp]
+    lib.hk_head_fwd.restype = i
+    lib.hk_head_fwd.argtypes = [vp, i, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
+    lib.hk_argmax_workspace_bytes.restype = sz
+    lib.hk_argmax_workspace_bytes.argtypes = [i, i, i, i]
+    lib.hk_argmax_decode.restype = i
+    lib.hk_argmax_decode.argtypes = [vp, i, i, i, i, vp, vp, vp, sz, vp]
+    lib.hk_gauss_targets.restype = i
+    lib.hk_gauss_targets.argtypes = [vp, i, i, i, i, f, vp, i, vp]
+    lib.hk_bce_workspace_bytes.restype = sz
+    lib.hk_bce_workspace_bytes.argtypes = [C.c_longlong]
+    lib.hk_bce_fwd_bwd.restype = i
+    lib.hk_bce_fwd_bwd.argtypes = [vp, i, vp, i, vp, i, i, i, i, f, vp, vp, vp, sz, vp]
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises RuntimeError when the library is absent."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: the CUDA extension has not been built "
+                        "(run `python -m hulk_keypoints_b200.build`). There is no CPU or PyTorch fallback.")
+                handle = C.CDLL(LIB_PATH)
+                _declare(handle)
+                v = handle.hk_version()
+                if v != ABI_VERSION:
+                    raise RuntimeError(f"libhulk_sm100.so ABI version {v} != expected {ABI_VERSION}; rebuild")
+                _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().hk_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed with status {rc}: {msg}")
+
+
+def require_device() -> None:
+    """Fail loudly unless the current CUDA device is a B200 (sm_100)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("hulk_keypoints_b200 needs a CUDA device (B200, sm_100a); no CPU path exists")
+    check(lib().hk_check_device(), "hk_check_device")
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return HK_F32
+    if dt == torch.bfloat16:
+        return HK_BF16
+    if dt == torch.float64:
+        return HK_F64
+    raise ValueError(f"unsupported dtype {dt}")

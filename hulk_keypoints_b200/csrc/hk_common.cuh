@@ -1,0 +1,59 @@
+// Shared host/device helpers for libhulk_sm100.so.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/hulk_sm100.h"
+
+namespace hk {
+
+// Thread-local last-error text (hk_last_error()).
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+// Check the launch that was just enqueued; returns HK_OK or records the CUDA error text.
+int check_launch(const char* what);
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// Number of SMs of the current device (cached).
+int sm_count();
+
+#define HK_REQUIRE(cond, ...)                                  \
+  do {                                                         \
+    if (!(cond)) return ::hk::fail(HK_ERR_BAD_ARG, __VA_ARGS__); \
+  } while (0)
+
+// ---- device helpers ----
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t v) { return __uint_as_float(((uint32_t)v) << 16); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void unpack_bf16x2(uint32_t v, float& lo, float& hi) {
+  lo = __uint_as_float(v << 16);
+  hi = __uint_as_float(v & 0xffff0000u);
+}
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return bf16_bits_to_float(__ldg(reinterpret_cast<const unsigned short*>(p)));
+}
+template <typename T>
+__device__ __forceinline__ void store_from_float(T* p, float v);
+template <>
+__device__ __forceinline__ void store_from_float<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+}  // namespace hk

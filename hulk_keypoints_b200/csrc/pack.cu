@@ -1,0 +1,68 @@
+// Weight repack: OIHW fp32 state_dict tensor -> O(HW)I ("KRSC") fp32/bf16 GEMM-B operand, and
+// BatchNorm(eval) -> per-channel (scale, bias) applied in the conv epilogue.
+//
+// The reference keeps nn.Conv2d weights as (cout, cin, kh, kw) and applies nn.BatchNorm2d as a separate
+// op (src/resnet.py:46,49,139,187).  In eval() that op is y = (x - mean) / sqrt(var + eps) * gamma + beta,
+// i.e. y = x * scale + bias with scale = gamma / sqrt(var + eps), bias = beta - mean * scale.  The scale is
+// kept OUT of the weights (applied to the fp32 accumulator) so bf16 weight rounding is not perturbed.
+#include "hk_common.cuh"
+
+namespace hk {
+
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const float* __restrict__ w_oihw, OutT* __restrict__ w_out, int cout, int cin, int khw) {
+  const long long total = (long long)cout * cin * khw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // destination index: ((o * khw + t) * cin + c)
+    const int c = (int)(i % cin);
+    const long long r = i / cin;
+    const int t = (int)(r % khw);
+    const int o = (int)(r / khw);
+    const float v = __ldg(w_oihw + ((size_t)o * cin + c) * khw + t);
+    store_from_float<OutT>(w_out + i, v);
+  }
+}
+
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                               const float* __restrict__ var, float eps, int cout, float* __restrict__ scale,
+                               float* __restrict__ bias) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout) return;
+  if (gamma) {
+    // same op order as ATen's eval batch_norm: invstd = 1/sqrt(var+eps); w*invstd; b - mean*w*invstd
+    const float invstd = 1.0f / sqrtf(var[i] + eps);
+    const float s = gamma[i] * invstd;
+    scale[i] = s;
+    bias[i] = beta[i] - mean[i] * s;
+  } else {
+    scale[i] = 1.0f;
+    bias[i] = 0.0f;
+  }
+}
+
+}  // namespace hk
+
+extern "C" int hk_pack_conv_weights(const float* w_oihw, const float* bn_gamma, const float* bn_beta, const float* bn_mean,
+                                    const float* bn_var, float bn_eps, int cout, int cin, int kh, int kw, int w_dtype,
+                                    void* w_out, float* scale_out, float* bias_out, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(w_oihw && w_out && scale_out && bias_out, "hk_pack_conv_weights: null pointer");
+  HK_REQUIRE(cout > 0 && cin > 0 && kh > 0 && kw > 0, "hk_pack_conv_weights: bad shape");
+  const bool all = bn_gamma && bn_beta && bn_mean && bn_var;
+  const bool none = !bn_gamma && !bn_beta && !bn_mean && !bn_var;
+  HK_REQUIRE(all || none, "hk_pack_conv_weights: pass all four BatchNorm vectors or none");
+  HK_REQUIRE(w_dtype == HK_BF16 || w_dtype == HK_F32, "hk_pack_conv_weights: w_dtype must be bf16 or f32");
+  cudaStream_t s = as_stream(stream);
+  const long long total = (long long)cout * cin * kh * kw;
+  int blocks = (int)ceil_div_ll(total, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (w_dtype == HK_BF16)
+    pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(w_oihw, static_cast<__nv_bfloat16*>(w_out), cout, cin, kh * kw);
+  else
+    pack_weights_kernel<float><<<blocks, 256, 0, s>>>(w_oihw, static_cast<float*>(w_out), cout, cin, kh * kw);
+  int rc = check_launch("pack_weights_kernel");
+  if (rc) return rc;
+  bn_fold_kernel<<<ceil_div(cout, 128), 128, 0, s>>>(bn_gamma, bn_beta, bn_mean, bn_var, bn_eps, cout, scale_out, bias_out);
+  return check_launch("bn_fold_kernel");
+}

@@ -1,0 +1,164 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/hulk_sm100.h).
+
+torch is used here for device memory and streams only; every computation is a kernel of
+libhulk_sm100.so enqueued on torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import HK_BF16, HK_CONV_FFMA, HK_CONV_TCGEN05, HK_F32, HK_F64, HkConvDesc, check, dtype_code, lib, ptr, stream_ptr
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("hulk_keypoints_b200 kernels take CUDA tensors only (no CPU fallback)")
+
+
+def conv_out_hw(h: int, w: int, k: int, stride: int, pad: int, dil: int) -> Tuple[int, int]:
+    eff = dil * (k - 1) + 1
+    return (h + 2 * pad - eff) // stride + 1, (w + 2 * pad - eff) // stride + 1
+
+
+def pack_conv_weights(w_oihw: torch.Tensor, bn: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]],
+                      eps: float, w_dtype: torch.dtype):
+    """OIHW fp32 (+ BatchNorm vectors) -> ((cout, kh, kw, cin) w_dtype, scale f32, bias f32)."""
+    _need_cuda(w_oihw)
+    w = w_oihw.detach().contiguous().float()
+    cout, cin, kh, kw = w.shape
+    w_out = torch.empty((cout, kh, kw, cin), device=w.device, dtype=w_dtype)
+    scale = torch.empty(cout, device=w.device, dtype=torch.float32)
+    bias = torch.empty(cout, device=w.device, dtype=torch.float32)
+    if bn is not None:
+        g, b, m, v = (t.detach().contiguous().float() for t in bn)
+    else:
+        g = b = m = v = None
+    check(lib().hk_pack_conv_weights(ptr(w), ptr(g), ptr(b), ptr(m), ptr(v), C.c_float(eps), cout, cin, kh, kw,
+                                     dtype_code(w_dtype), ptr(w_out), ptr(scale), ptr(bias), stream_ptr()),
+          "hk_pack_conv_weights")
+    return w_out, scale, bias
+
+
+def conv_bn_act(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, *,
+                stride: int, pad: int, dil: int, relu: bool, residual: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+                algo: int = HK_CONV_TCGEN05, in_is_nchw: bool = False) -> torch.Tensor:
+    """Fused conv + affine (+ residual) (+ ReLU).  x is NHWC (B,H,W,C) unless in_is_nchw (B,C,H,W)."""
+    _need_cuda(x, w_packed, scale, bias, residual, out)
+    if in_is_nchw:
+        B, Cin, H, W = x.shape
+    else:
+        B, H, W, Cin = x.shape
+    cout, kh, kw, cin_w = w_packed.shape
+    if cin_w != Cin:
+        raise ValueError(f"weight cin {cin_w} != input channels {Cin}")
+    Ho, Wo = conv_out_hw(H, W, kh, stride, pad, dil)
+    if out is None:
+        out = torch.empty((B, Ho, Wo, cout), device=x.device, dtype=out_dtype or (torch.bfloat16 if algo == HK_CONV_TCGEN05 else x.dtype))
+    elif tuple(out.shape) != (B, Ho, Wo, cout):
+        raise ValueError(f"out shape {tuple(out.shape)} != {(B, Ho, Wo, cout)}")
+    if residual is not None and (tuple(residual.shape) != tuple(out.shape) or residual.dtype != out.dtype):
+        raise ValueError("residual must match the output shape and dtype")
+    if not (x.is_contiguous() and w_packed.is_contiguous() and out.is_contiguous() and (residual is None or residual.is_contiguous())):
+        raise ValueError("conv_bn_act needs contiguous tensors")
+    d = HkConvDesc(B, H, W, Cin, Ho, Wo, cout, kh, kw, stride, pad, dil, int(relu), dtype_code(x.dtype),
+                   dtype_code(out.dtype), int(in_is_nchw), algo)
+    check(lib().hk_conv_bn_act_fwd(C.byref(d), ptr(x), ptr(w_packed), ptr(scale), ptr(bias), ptr(residual), ptr(out),
+                                   stream_ptr()), "hk_conv_bn_act_fwd")
+    return out
+
+
+def maxpool3x3s2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, out)
+    B, H, W, Cc = x.shape
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cc), device=x.device, dtype=x.dtype)
+    check(lib().hk_maxpool3x3s2_fwd(ptr(x), ptr(out), dtype_code(x.dtype), B, H, W, Cc, Ho, Wo, stream_ptr()),
+          "hk_maxpool3x3s2_fwd")
+    return out
+
+
+def head(feat: torch.Tensor, w_fc: torch.Tensor, b_fc: torch.Tensor, H: int, W: int,
+         heat: Optional[torch.Tensor] = None, logits_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B,h,w,C) NHWC features -> (B,K,H,W) fp32 heatmaps.  w_fc (K,C) fp32, b_fc (K) fp32."""
+    _need_cuda(feat, w_fc, b_fc, heat, logits_ws)
+    B, h, w, Cc = feat.shape
+    K = w_fc.shape[0]
+    if heat is None:
+        heat = torch.empty((B, K, H, W), device=feat.device, dtype=torch.float32)
+    if logits_ws is None:
+        logits_ws = torch.empty((B, K, h, w), device=feat.device, dtype=torch.float32)
+    check(lib().hk_head_fwd(ptr(feat), dtype_code(feat.dtype), ptr(w_fc), ptr(b_fc), ptr(logits_ws), ptr(heat),
+                            B, K, Cc, h, w, H, W, stream_ptr()), "hk_head_fwd")
+    return heat
+
+
+def argmax_workspace_bytes(B: int, K: int, H: int, W: int) -> int:
+    return int(lib().hk_argmax_workspace_bytes(B, K, H, W))
+
+
+def argmax_decode(heat: torch.Tensor, yx: Optional[torch.Tensor] = None, maxval: Optional[torch.Tensor] = None,
+                  ws: Optional[torch.Tensor] = None, want_max: bool = False):
+    """(B,K,H,W) fp32 -> (B,K,2) int32 (row, col) with numpy's first-index tie-break."""
+    _need_cuda(heat, yx, maxval, ws)
+    if heat.dtype != torch.float32 or not heat.is_contiguous():
+        raise ValueError("argmax_decode needs a contiguous fp32 heatmap")
+    B, K, H, W = heat.shape
+    if yx is None:
+        yx = torch.empty((B, K, 2), device=heat.device, dtype=torch.int32)
+    if maxval is None and want_max:
+        maxval = torch.empty((B, K), device=heat.device, dtype=torch.float32)
+    nbytes = argmax_workspace_bytes(B, K, H, W)
+    if ws is None:
+        ws = torch.empty(nbytes, device=heat.device, dtype=torch.uint8)
+    check(lib().hk_argmax_decode(ptr(heat), B, K, H, W, ptr(yx), ptr(maxval), ptr(ws), ws.numel() * ws.element_size(),
+                                 stream_ptr()), "hk_argmax_decode")
+    return (yx, maxval) if want_max else yx
+
+
+def gauss_targets(uv: torch.Tensor, H: int, W: int, sigma: float, out_dtype: torch.dtype = torch.float64,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uv (B,K,2) = (x, y) -> (B,K,H,W) Gaussian targets (fp32 math, stored as out_dtype)."""
+    _need_cuda(uv, out)
+    uv32 = uv.detach().to(torch.float32).contiguous()
+    B, K, _ = uv32.shape
+    if out is None:
+        out = torch.empty((B, K, H, W), device=uv.device, dtype=out_dtype)
+    check(lib().hk_gauss_targets(ptr(uv32), B, K, H, W, C.c_float(float(sigma)), ptr(out), dtype_code(out.dtype),
+                                 stream_ptr()), "hk_gauss_targets")
+    return out
+
+
+def bce_fwd_bwd(pred: torch.Tensor, target: Optional[torch.Tensor] = None, uv: Optional[torch.Tensor] = None,
+                sigma: float = 8.0, want_grad: bool = True, pred_is_logits: bool = False):
+    """Mean BCE of fp32 heatmaps against fp64/fp32 targets (or Gaussians generated from uv on the fly).
+
+    `pred_is_logits=True`: `pred` holds the upsampled logits and the sigmoid is fused into the kernel.
+    Returns (loss f64 0-dim CUDA tensor, grad wrt LOGITS fp32 or None)."""
+    _need_cuda(pred, target, uv)
+    if pred.dtype != torch.float32 or not pred.is_contiguous() or pred.dim() != 4:
+        raise ValueError("bce_fwd_bwd needs a contiguous (B,K,H,W) fp32 prediction")
+    B, K, H, W = pred.shape
+    n = pred.numel()
+    loss = torch.empty((), device=pred.device, dtype=torch.float64)
+    grad = torch.empty_like(pred) if want_grad else None
+    ws = torch.empty(int(lib().hk_bce_workspace_bytes(n)), device=pred.device, dtype=torch.uint8)
+    tcode = 0
+    uv32 = None
+    if target is not None:
+        if tuple(target.shape) != tuple(pred.shape) or not target.is_contiguous():
+            raise ValueError("target must be contiguous and shaped like pred")
+        tcode = dtype_code(target.dtype)
+    else:
+        uv32 = uv.detach().to(torch.float32).contiguous()
+        if tuple(uv32.shape) != (B, K, 2):
+            raise ValueError("uv must be (B,K,2)")
+    check(lib().hk_bce_fwd_bwd(ptr(pred), int(pred_is_logits), ptr(target), tcode, ptr(uv32), B, K, H, W, C.c_float(float(sigma)), ptr(loss),
+                               ptr(grad), ptr(ws), ws.numel(), stream_ptr()), "hk_bce_fwd_bwd")
+    return loss, grad

@@ -1,0 +1,83 @@
+"""Prediction -- host-side mirror of reference src/prediction.py:8-66.
+
+`predict` keeps the reference's contract (3-D input gains a batch axis, the model's forward output is
+returned on the model's device).  Deliberate, documented deviation: constructing a
+Prediction puts the model in eval() mode -- the reference scripts never call .eval(), so as written
+they normalise each image with its own batch statistics; the B200 inference path folds the running
+statistics instead ("BN folded at inference").  Pass bn_mode="as_written" to keep train-mode BN.
+
+Additive API: `decode(heatmap)` runs the argmax of reference prediction.py:46 on the GPU for EVERY batch
+element (the reference's `plot` decodes element 0 only, on the host).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+class Prediction:
+    def __init__(self, model, num_keypoints, img_height, img_width, use_cuda, bn_mode: str = "eval"):
+        self.model = model
+        self.num_keypoints = num_keypoints
+        self.img_height = img_height
+        self.img_width = img_width
+        self.use_cuda = use_cuda
+        if bn_mode not in ("eval", "as_written"):
+            raise ValueError("bn_mode must be 'eval' or 'as_written'")
+        if bn_mode == "eval":
+            self.model.eval()
+
+    def predict(self, imgs):
+        # imgs: torch.Tensor (3, H, W) or (B, 3, H, W)
+        if imgs.dim() == 3:
+            imgs = imgs.unsqueeze(0)
+        elif imgs.dim() != 4:
+            raise ValueError(f"expected a 3-D or 4-D image tensor, got {tuple(imgs.shape)}")
+        return self.model.forward(imgs)
+
+    def decode(self, heatmap):
+        """(B,K,H,W) heatmap (CUDA tensor or numpy) -> (B,K,2) int64 numpy array of (y, x) peaks."""
+        if isinstance(heatmap, np.ndarray):
+            heatmap = torch.from_numpy(np.ascontiguousarray(heatmap, dtype=np.float32)).cuda()
+        heat = heatmap.detach().float().contiguous()
+        return ops.argmax_decode(heat).cpu().numpy().astype(np.int64)
+
+    # ---- kept callable for API parity; host-side helpers of the reference (prediction.py:26-38) ----
+    def softmax(self, x):
+        e_x = np.exp(x - np.max(x))
+        return e_x / e_x.sum()
+
+    def expectation(self, d):
+        """Soft-argmax (x, y) of one (H, W) map, truncated to int like the reference."""
+        d = np.asarray(d)
+        height, width = d.shape
+        p = self.softmax(d.ravel())
+        flat = np.arange(height * width)
+        return [int(np.dot(p, flat % width)), int(np.dot(p, flat // width))]
+
+    def plot(self, img, heatmap, image_id=0, cls=None, classes=None):
+        """Overlay visualisation (reference prediction.py:40-66): host-side cv2 drawing, out of the hot
+        path.  Peaks come from `decode` (GPU) instead of a host argmax."""
+        import cv2
+
+        print("Running inferences on image: %d" % image_id)
+        heatmap = np.asarray(heatmap)
+        peaks = self.decode(heatmap[:1])[0]
+        overlays = []
+        for i in range(self.num_keypoints):
+            h = heatmap[0][i]
+            pred_y, pred_x = int(peaks[i][0]), int(peaks[i][1])
+            vis = cv2.normalize(h, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
+            vis = cv2.applyColorMap(vis, cv2.COLORMAP_JET)
+            overlay = cv2.addWeighted(img, 0.65, vis, 0.35, 0)
+            overlay = cv2.circle(overlay, (pred_x, pred_y), 4, (0, 0, 0), -1)
+            overlays.append(overlay)
+        half = self.num_keypoints // 2
+        left = cv2.vconcat(overlays[:half]) if half else None
+        right = cv2.vconcat(overlays[half:])
+        result = cv2.hconcat((left, right)) if left is not None else right
+        if cls is not None:
+            cv2.putText(result, classes[cls], (10, 55), cv2.FONT_HERSHEY_SIMPLEX, 0.7, (255, 255, 255), 2)
+        cv2.imwrite('preds/out%04d.png' % image_id, result)

@@ -1,0 +1,59 @@
+"""Training-side pieces: the fused sigmoid+BCE loss as an autograd function and a fused train step.
+
+Reference train.py:18-26 computes `nn.BCELoss()(model.forward(img).double(), gt_gauss)`: three full passes at
+8 bytes/element (cast, loss, reduce) and, in backward, a 1000-channel upsample gradient.  Here the autograd
+boundary is moved to the upsampled LOGITS of the K live channels: one pass of hk_bce_fwd_bwd evaluates the
+sigmoid (model.py:21), the fp64 loss and the fp32 gradient w.r.t. the logits -- bit-identical to what autograd
+produces for sigmoid -> .double() -> BCELoss -- optionally generating the Gaussian target on the fly from the
+(B,K,2) labels so neither the heatmap nor the fp64 target tensor is ever written to HBM.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+class _FusedSigmoidBCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, uv, sigma):
+        z = logits.detach().contiguous()
+        loss, grad_logits = ops.bce_fwd_bwd(z, target=target, uv=uv, sigma=sigma, want_grad=True, pred_is_logits=True)
+        ctx.save_for_backward(grad_logits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad_logits,) = ctx.saved_tensors
+        return grad_logits * grad_out.to(grad_logits.dtype), None, None, None
+
+
+def sigmoid_bce_loss(logits: torch.Tensor, target: Optional[torch.Tensor] = None, uv: Optional[torch.Tensor] = None,
+                     sigma: float = 8.0) -> torch.Tensor:
+    """mean BCE(sigmoid(logits), target) as a 0-dim float64 tensor, differentiable w.r.t. `logits` (fp32).
+    Pass either a (B,K,H,W) fp64/fp32 `target` or the (B,K,2) labels `uv` (+ `sigma`)."""
+    if (target is None) == (uv is None):
+        raise ValueError("pass exactly one of target / uv")
+    return _FusedSigmoidBCE.apply(logits, target, uv, float(sigma))
+
+
+def loss_from_batch(sample_batched, model, use_cuda: bool = True) -> torch.Tensor:
+    """Drop-in for reference train.py:18-26 `forward(sample_batched, model)`: (img, gt_gauss) -> float64 loss."""
+    img, gt_gauss = sample_batched
+    if use_cuda:
+        img, gt_gauss = img.cuda(), gt_gauss.cuda()
+    return sigmoid_bce_loss(model.forward_logits(img), target=gt_gauss.contiguous())
+
+
+def train_step(model, optimizer, img: torch.Tensor, uv: torch.Tensor, sigma: float = 8.0, allreduce=None) -> torch.Tensor:
+    """One step of reference train.py:33-36 (zero_grad, forward, backward, step) with targets generated from
+    labels on the fly.  `allreduce(params)` is called between backward and step (data-parallel exchange)."""
+    optimizer.zero_grad(set_to_none=True)
+    loss = sigmoid_bce_loss(model.forward_logits(img), uv=uv, sigma=sigma)
+    loss.backward()
+    if allreduce is not None:
+        allreduce(model.parameters())
+    optimizer.step()
+    return loss.detach()

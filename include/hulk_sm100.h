@@ -1,0 +1,150 @@
+/*
+ * hulk_sm100.h -- C ABI of libhulk_sm100.so, the B200 (sm_100a) implementation of the
+ * hulk-keypoints KeypointsGauss hot path.
+ *
+ * This is the drop-in boundary.  The reference (vainaviv/hulk-keypoints) is pure
+ * Python on torch and has no FFI of its own: every entry point below replaces one torch call site
+ * of the reference, cited as <file>:<line> relative to the reference root.  The Python host
+ * package (hulk_keypoints_b200/) binds these with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - One call == one (or a few) kernel enqueue(s) on the cudaStream_t passed in.  The library never
+ *     allocates or frees device memory on the call path, never synchronises the device, and never
+ *     falls back to the CPU.
+ *   - All device buffers are owned by the caller.  Pointers are plain device pointers.
+ *   - Return value: HK_OK (0) or a negative HkStatus; hk_last_error() returns a thread-local
+ *     human-readable message for the last failing call on this thread.
+ *   - Activations between kernels are NHWC ("channels last"); NCHW fp32 only at the API edge
+ *     (network input, heatmap output), which is what the reference's tensors are.
+ *   - `stream` is passed as void* (a cudaStream_t) so the header needs no CUDA include.
+ */
+#ifndef HULK_SM100_H_
+#define HULK_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HK_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define HK_API __attribute__((visibility("default")))
+#else
+#define HK_API
+#endif
+
+typedef enum HkStatus {
+  HK_OK = 0,
+  HK_ERR_BAD_ARG = -1,     /* null pointer, bad shape, misaligned buffer, unsupported combination */
+  HK_ERR_UNSUPPORTED_ARCH = -2, /* device is not sm_100 */
+  HK_ERR_CUDA = -3         /* CUDA runtime / launch error; text in hk_last_error() */
+} HkStatus;
+
+typedef enum HkDType { HK_F32 = 0, HK_BF16 = 1, HK_F64 = 2 } HkDType;
+
+/* Which kernel family executes a convolution. */
+typedef enum HkConvAlgo {
+  HK_CONV_TCGEN05 = 0, /* bf16 operands, fp32 accumulate in TMEM, TMA-fed implicit GEMM            */
+  HK_CONV_FFMA = 1     /* fp32 CUDA-core implicit GEMM: the fp32 correctness mode */
+} HkConvAlgo;
+
+/*
+ * One fused conv + per-channel affine (+ residual) (+ ReLU).
+ * Replaces  nn.Conv2d -> nn.BatchNorm2d(eval) -> [+= residual] -> nn.ReLU
+ *   src/resnet.py:56-67 (BasicBlock.forward), src/resnet.py:184-188 (downsample), src/resnet.py:199-201 (stem).
+ *   y[b,oy,ox,n] = act( scale[n] * sum_{r,s,c} x[b, oy*stride-pad+r*dil, ox*stride-pad+s*dil, c] * w[n,r,s,c]
+ *                       + bias[n] + residual[b,oy,ox,n] )
+ */
+typedef struct HkConvDesc {
+  int32_t batch;
+  int32_t in_h, in_w, in_c;
+  int32_t out_h, out_w, out_c;
+  int32_t kh, kw;
+  int32_t stride, pad, dil;
+  int32_t relu;          /* 0/1 */
+  int32_t in_dtype;      /* HkDType of x (HK_F32 or HK_BF16)                       */
+  int32_t out_dtype;     /* HkDType of y and residual                              */
+  int32_t in_is_nchw;    /* 1: x is NCHW (network input, FFMA algo only); 0: NHWC  */
+  int32_t algo;          /* HkConvAlgo                                             */
+} HkConvDesc;
+
+/* ---- library ---- */
+HK_API int hk_version(void);
+HK_API const char* hk_last_error(void);
+/* 0 if the current device is sm_100 (B200), HK_ERR_UNSUPPORTED_ARCH otherwise. */
+HK_API int hk_check_device(void);
+
+/* ---- weights ----
+ * Repack one conv + its BatchNorm for the kernels above.
+ * Replaces the implicit parameter layout of nn.Conv2d/nn.BatchNorm2d (src/resnet.py:36,46,137,139,185,187).
+ *   w_oihw : (cout, cin, kh, kw) fp32, the state_dict tensor
+ *   bn_*   : (cout) fp32 gamma, beta, running_mean, running_var; all four NULL => scale=1, bias=conv_bias_or_0
+ *   w_out  : (cout, kh, kw, cin) in `w_dtype` (HK_BF16 for TCGEN05, HK_F32 for FFMA)
+ *   scale/bias_out : (cout) fp32:  scale = gamma / sqrt(var + eps),  bias = beta - mean * scale
+ */
+HK_API int hk_pack_conv_weights(const float* w_oihw, const float* bn_gamma, const float* bn_beta,
+                         const float* bn_mean, const float* bn_var, float bn_eps,
+                         int cout, int cin, int kh, int kw, int w_dtype,
+                         void* w_out, float* scale_out, float* bias_out, void* stream);
+
+/* ---- backbone ---- */
+HK_API int hk_conv_bn_act_fwd(const HkConvDesc* desc, const void* x, const void* w_packed,
+                       const float* scale, const float* bias, const void* residual_or_null,
+                       void* y, void* stream);
+
+/* MaxPool2d(kernel 3, stride 2, pad 1) on NHWC.  Replaces src/resnet.py:141,202. */
+HK_API int hk_maxpool3x3s2_fwd(const void* x, void* y, int dtype, int batch, int in_h, int in_w, int c,
+                        int out_h, int out_w, void* stream);
+
+/* ---- head ----
+ * Scoring conv restricted to the K live rows + bilinear upsample (align_corners=True) + sigmoid.
+ * Replaces src/resnet.py:215 (fc as 1x1 conv), src/resnet_dilated.py:27 (upsample_bilinear),
+ *          src/model.py:21 (slice [:, :K] and sigmoid).
+ *   feat      : (B, h, w, C) NHWC, feat_dtype
+ *   w_fc      : (K, C) fp32  -- rows [0,K) of fc.weight ; b_fc : (K) fp32
+ *   logits_ws : (B, K, h, w) fp32 scratch owned by the caller
+ *   heat      : (B, K, H, W) fp32 NCHW
+ */
+HK_API int hk_head_fwd(const void* feat, int feat_dtype, const float* w_fc, const float* b_fc,
+                float* logits_ws, float* heat, int B, int K, int C, int h, int w, int H, int W,
+                void* stream);
+
+/* ---- decode ----
+ * Per-keypoint argmax with first-index tie-break.  Replaces src/prediction.py:46
+ * (np.unravel_index(h.argmax(), h.shape)), for every batch element instead of [0] only.
+ *   heat (B,K,H,W) fp32 ; yx (B,K,2) int32 = (row, col) ; maxval (B,K) fp32 or NULL
+ *   ws : hk_argmax_workspace_bytes(B,K,H,W) bytes of scratch
+ */
+HK_API size_t hk_argmax_workspace_bytes(int B, int K, int H, int W);
+HK_API int hk_argmax_decode(const float* heat, int B, int K, int H, int W, int32_t* yx, float* maxval_or_null,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ---- training-side elementwise / reduction kernels ----
+ * Gaussian heatmap targets.  Replaces gauss_2d_batch, src/dataset.py:36-44 (fp32 math, widened to f64).
+ *   uv (B,K,2) fp32 = (x, y) ; out (B,K,H,W) in out_dtype (HK_F64 drop-in, HK_F32 compact)
+ */
+HK_API int hk_gauss_targets(const float* uv, int B, int K, int H, int W, float sigma, void* out, int out_dtype,
+                     void* stream);
+
+/* BCE(mean) forward + backward through the sigmoid.  Replaces train.py:21,25 (pred.double(), nn.BCELoss)
+ * and the autograd of train.py:35 down to the logits (model.py:21).
+ *   pred   : (N) fp32 heatmap values (post-sigmoid), or the upsampled LOGITS when pred_is_logits != 0
+ *            (the sigmoid of model.py:21 is then evaluated in-kernel and no heatmap is materialised)
+ *   target : (N) fp64 or fp32 (target_dtype), or NULL with uv != NULL to generate the Gaussian on the fly
+ *   uv     : (B,K,2) fp32 labels when target == NULL (then N must equal B*K*H*W)
+ *   loss   : (1) fp64 mean loss ; grad_logits : (N) fp32 or NULL (forward only)
+ *   ws     : hk_bce_workspace_bytes(N) bytes
+ */
+HK_API size_t hk_bce_workspace_bytes(long long n);
+HK_API int hk_bce_fwd_bwd(const float* pred, int pred_is_logits, const void* target_or_null, int target_dtype,
+                   const float* uv_or_null, int B, int K, int H, int W, float sigma,
+                   double* loss, float* grad_logits_or_null, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HULK_SM100_H_ */
