@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- KeypointsGauss heatmap inference images/s on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 64] [--precision bf16]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of synthetic images: stem -> 16 BasicBlocks -> head ->
+argmax decode for `--batch` (64) images of 480x640 (BASELINE.json configs[1]).  Rank 0 prints ONE JSON line.
+
+  value      images/s, all ranks, inputs resident in HBM (CUDA-graph replay of the whole step), CUDA events,
+             barrier + synchronize on both sides, max over ranks.
+  e2e        same metric through the public API with HOST buffers: pinned-host fp32 images are copied to the
+             device, Prediction-equivalent forward + decode runs, keypoints (B,K,2) + peak values come back to the
+             host -- every step, inside the timed region (copies double-buffered against compute).
+  roofline   the dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOPs of its launches in one step /
+             their CUDA-event time, against MEASURED_PEAKS.json's dense bf16 peak.
+  cpu_baseline / --impl reference: the oracle port (torch CPU restatement of the reference) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+import torch  # noqa: E402
+
+METRIC = "heatmap_inference_images_per_sec"
+UNIT = "images/s"
+K_KEYPOINTS = 4
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-images", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", default="", help="write the per-launch timing table to this JSON file")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_tflops": d.get("bf16_tflops", 1590.0), "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0),
+                "hbm_gbs": d.get("hbm_gbs", 6650.0), "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+def conv_flops_per_image(h, w, k):
+    from oracle.keypoints_oracle import conv_flops_per_image as f  # checker-side arithmetic only
+    return f(h, w, k)
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_throughput(n_images: int, height: int, width: int, warm: int = 1):
+    """Oracle port (torch CPU restatement of the reference's eval forward + numpy argmax decode), B=1 per call as
+    analysis.py does, all host threads.  Returns (images/s, cores, seconds)."""
+    from oracle import keypoints_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.init_state_dict(0)
+    g = torch.Generator().manual_seed(1000)
+    imgs = [torch.rand(1, 3, height, width, generator=g) for _ in range(2)]
+    for i in range(warm):
+        O.argmax_decode(O.forward(sd, imgs[i % 2], K_KEYPOINTS).numpy())
+    t0 = time.perf_counter()
+    for i in range(n_images):
+        O.argmax_decode(O.forward(sd, imgs[i % 2], K_KEYPOINTS).numpy())
+    dt = time.perf_counter() - t0
+    return n_images / dt, cores, dt
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    n_per_step = 2
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_throughput(1, args.height, args.width, warm=0)
+    t0 = time.perf_counter()
+    total = 0
+    cores = os.cpu_count() or 1
+    for _ in range(args.steps):
+        _, cores, _ = cpu_reference_throughput(n_per_step, args.height, args.width, warm=0)
+        total += n_per_step
+    dt = time.perf_counter() - t0
+    value = total / dt
+    sample = f"{n_per_step} images of {args.height}x{args.width} per step, B=1 per call (analysis.py style), {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"KeypointsGauss eval forward + argmax decode, {args.height}x{args.width}, K={K_KEYPOINTS}, "
+                               f"oracle port of the reference on host CPU (bounded sample)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def per_launch_breakdown(engine, plan, decode=True):
+    """Eager (no graph) pass with a CUDA event pair around every launch group; returns [(name, ms, flops)]."""
+    from hulk_keypoints_b200 import ops
+
+    net = engine.model.resnet.resnet34_8s
+    P = engine._packed
+    rows = []
+    stream = torch.cuda.current_stream()
+
+    def timed(name, flops, fn, reps=3):
+        fn()
+        best = None
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); fn(); b.record(stream); b.synchronize()
+            t = a.elapsed_time(b)
+            best = t if best is None else min(best, t)
+        rows.append({"name": name, "ms": best, "flops": flops, "algo": None})
+
+    B = plan.B
+    timed("stem", 2.0 * B * plan.h2 * plan.w2 * 64 * 147,
+          lambda: engine._conv(P["stem"], plan.x, plan.stem, relu=True, in_is_nchw=True))
+    cur = 0
+    x = plan.view(cur, plan.h4, plan.w4, 64)
+    timed("maxpool", 0.0, lambda: ops.maxpool3x3s2(plan.stem, out=x))
+    h, w = plan.h4, plan.w4
+    for i, blk in enumerate(net.blocks()):
+        c1, c2 = P[f"b{i}.c1"], P[f"b{i}.c2"]
+        planes, cin = c1.w.shape[0], c1.w.shape[3]
+        ho, wo = ops.conv_out_hw(h, w, 3, c1.stride, c1.pad, c1.dil)
+        free = [j for j in range(4) if j != cur]
+        t = plan.view(free[0], ho, wo, planes)
+        xin = x
+        timed(f"b{i}.c1", 2.0 * B * ho * wo * planes * cin * 9, lambda: engine._conv(c1, xin, t, relu=True))
+        rows[-1]["algo"] = c1.algo
+        if blk.downsample is not None:
+            sc = plan.view(free[1], ho, wo, planes)
+            timed(f"b{i}.ds", 2.0 * B * ho * wo * planes * cin, lambda: engine._conv(P[f"b{i}.ds"], xin, sc, relu=False))
+            rows[-1]["algo"] = P[f"b{i}.ds"].algo
+        else:
+            sc = x
+        y = plan.view(free[2], ho, wo, planes)
+        timed(f"b{i}.c2", 2.0 * B * ho * wo * planes * planes * 9, lambda: engine._conv(c2, t, y, relu=True, residual=sc))
+        rows[-1]["algo"] = c2.algo
+        x, cur, h, w = y, free[2], ho, wo
+    xf = x
+    timed("head", 2.0 * B * h * w * engine.K * 512,
+          lambda: ops.head(xf, engine._fc_w, engine._fc_b, plan.H, plan.W, heat=plan.heat, logits_ws=plan.logits))
+    if decode:
+        timed("decode", 0.0, lambda: ops.argmax_decode(plan.heat, yx=plan.yx, maxval=plan.maxval, ws=plan.argmax_ws, want_max=True))
+    return rows
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    import hulk_keypoints_b200 as hk
+    from hulk_keypoints_b200._lib import HK_CONV_TCGEN05
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B, H, W = args.batch, args.height, args.width
+    torch.manual_seed(0)
+    model = hk.KeypointsGauss(K_KEYPOINTS, img_height=H, img_width=W, precision=args.precision).to(dev).eval()
+    engine = model.engine()
+    gen = torch.Generator().manual_seed(1000 + rank)
+    host_imgs = [torch.rand(B, 3, H, W, generator=gen).pin_memory() for _ in range(2)]
+    x_dev = host_imgs[0].to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput (value) ----------------
+    engine._ensure_packed()
+    plan = engine.plan_for(B, H, W)
+    plan.x.copy_(x_dev)
+    for _ in range(max(args.warmup, 3)):
+        engine.run_plan(plan, decode=True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for _ in range(args.steps):
+        engine.run_plan(plan, decode=True)
+    stop.record()
+    stop.synchronize()
+    barrier()
+    dev_ms = max_over_ranks(start.elapsed_time(stop))
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (dev_ms * 1e-3)
+    launches_per_step = plan.launches
+
+    # ---------------- end to end through the public API, host buffers ----------------
+    copy_stream = torch.cuda.Stream(device=dev)
+    compute = torch.cuda.current_stream()
+    dev_in = [torch.empty((B, 3, H, W), device=dev, dtype=torch.float32) for _ in range(2)]
+    host_yx = [torch.empty((B, K_KEYPOINTS, 2), dtype=torch.int32).pin_memory() for _ in range(2)]
+    host_mv = [torch.empty((B, K_KEYPOINTS), dtype=torch.float32).pin_memory() for _ in range(2)]
+    in_ready = [torch.cuda.Event() for _ in range(2)]
+    in_free = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_loop(steps):
+        for j in range(2):
+            in_free[j].record(compute)
+        for i in range(steps):
+            j = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(in_free[j])
+                dev_in[j].copy_(host_imgs[j], non_blocking=True)     # H2D of this step's images
+                in_ready[j].record(copy_stream)
+            compute.wait_event(in_ready[j])
+            heat, yx = model.heatmaps_and_keypoints(dev_in[j])        # public API (engine forward + decode)
+            in_free[j].record(compute)
+            host_yx[j].copy_(yx, non_blocking=True)                   # D2H of the step's result
+            host_mv[j].copy_(plan.maxval, non_blocking=True)
+        compute.synchronize()
+
+    e2e_loop(max(2, args.warmup))
+    barrier()
+    t0 = time.perf_counter()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    e2e_loop(args.steps)
+    e2.record()
+    e2.synchronize()
+    barrier()
+    e2e_ms = max_over_ranks(max(s2.elapsed_time(e2), 0.0))
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    h2d = B * 3 * H * W * 4
+    d2h = B * K_KEYPOINTS * 2 * 4 + B * K_KEYPOINTS * 4
+
+    # ---------------- roofline of the dominant kernel (live CUDA-event timing per launch) ----------------
+    rows = per_launch_breakdown(engine, plan)
+    tc = [r for r in rows if r["algo"] == HK_CONV_TCGEN05]
+    peaks = load_peaks()
+    if tc:
+        tc_flops, tc_ms = sum(r["flops"] for r in tc), sum(r["ms"] for r in tc)
+        achieved = tc_flops / (tc_ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops"]
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all launches of one step)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": f"{peaks['source']} burst bf16 ({peak}); sustained {peaks['bf16_tflops_sustained']}",
+                "launches": len(tc), "ms_in_step": tc_ms, "share_of_step": tc_ms / sum(r["ms"] for r in rows)}
+    else:
+        ff = [r for r in rows if r["flops"] > 0]
+        f, ms = sum(r["flops"] for r in ff), sum(r["ms"] for r in ff)
+        roof = {"bound": "tensor", "kernel": "conv_ffma_kernel (fp32 correctness mode, CUDA cores)", "achieved": f / (ms * 1e-3) / 1e12,
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": f / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "traffic": None}
+    if args.breakdown and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(args.breakdown)), exist_ok=True)
+        with open(args.breakdown, "w") as f:
+            json.dump({"batch": B, "rows": rows}, f, indent=1)
+
+    if rank != 0:
+        return
+    gf_img = conv_flops_per_image(H, W, K_KEYPOINTS) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"KeypointsGauss (ResnetDilated-34, OS8) eval forward + argmax decode, batch {B} per GPU, "
+                               f"{H}x{W}, K={K_KEYPOINTS}, random-init weights (BASELINE.json configs[1])",
+                   "batch_per_gpu": B, "height": H, "width": W, "precision": args.precision,
+                   "l2": f"per-step activations {B * 4.9:.0f}+ MB exceed the 126 MB L2 (no explicit flush)",
+                   "parallelism": f"batch-sharded x{world}, no collective", "cuda_graph": True},
+        "algorithmic_gflop_per_image": gf_img,
+        "achieved_tflops_whole_step": gf_img * value / world / 1e3,
+        "frac_of_bf16_peak_whole_step": gf_img * value / world / 1e3 / peaks["bf16_tflops"],
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
+                "note": "pinned-host fp32 images -> device, forward + decode, keypoints + peak values -> host; "
+                        "H2D double-buffered on a copy stream"},
+        "gpu_launches": launches_per_step * args.steps * 2,  # device-resident loop + e2e loop
+        "gpu_launches_per_step": launches_per_step,
+        "roofline": roof,
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world >= 1:
+        n = args.cpu_images or 12
+        v, cores, secs = cpu_reference_throughput(n, H, W, warm=1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{n} images {H}x{W}, B=1 per call, oracle port (torch CPU), {secs:.1f} s"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,296 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (hulk_keypoints_b200.ops -> libhulk_sm100.so).
+Every expected value comes from the CPU oracle (oracle/keypoints_oracle.py) or the committed goldens."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from hulk_keypoints_b200 import _lib, ops
+from oracle import keypoints_oracle as O
+
+warnings.filterwarnings("ignore")
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_device_is_b200():
+    _lib.require_device()
+    assert torch.cuda.get_device_capability(0) == (10, 0)
+
+
+# ------------------------------------------------------------------ argmax decode (bit-exact)
+def test_argmax_decode_matches_numpy():
+    g = torch.Generator().manual_seed(0)
+    for shape in [(2, 4, 48, 64), (1, 3, 37, 53), (3, 1, 480, 640), (1, 2, 5, 3)]:
+        h = torch.rand(shape, generator=g)
+        yx = ops.argmax_decode(h.to(dev())).cpu().numpy()
+        assert np.array_equal(yx.astype(np.int64), O.argmax_decode(h.numpy())), shape
+
+
+def test_argmax_decode_ties_constant_nan():
+    h = torch.zeros(2, 3, 40, 56)
+    h[0, 1, 20, 30] = h[0, 1, 39, 1] = h[0, 1, 20, 31] = 2.0
+    h[1, 0] = 1.0                      # saturated map (sigmoid == 1.0f everywhere) -> (0, 0)
+    h[1, 2, 33, 7] = float("nan")
+    h[0, 2] = -3.0
+    h[0, 2, 39, 55] = -0.0 - 2.5       # max at the very last element
+    yx, mv = ops.argmax_decode(h.to(dev()), want_max=True)
+    assert np.array_equal(yx.cpu().numpy().astype(np.int64), O.argmax_decode(h.numpy()))
+    assert mv[0, 1].item() == 2.0 and np.isnan(mv[1, 2].item())
+
+
+def test_argmax_decode_full_size_planted_peaks():
+    # BASELINE config 2 size: 64 x 4 maps of 480x640; property: a planted unique maximum is always found
+    B, K, H, W = 64, 4, 480, 640
+    h = torch.rand(B, K, H, W, device=dev()) * 0.5
+    rs = np.random.RandomState(1)
+    ys, xs = rs.randint(0, H, (B, K)), rs.randint(0, W, (B, K))
+    bi, ki = np.meshgrid(np.arange(B), np.arange(K), indexing="ij")
+    h[torch.from_numpy(bi), torch.from_numpy(ki), torch.from_numpy(ys), torch.from_numpy(xs)] = 0.75
+    yx = ops.argmax_decode(h).cpu().numpy()
+    assert np.array_equal(yx[..., 0], ys) and np.array_equal(yx[..., 1], xs)
+
+
+# ------------------------------------------------------------------ Gaussian targets
+def _ulp_close(a, b, ulps=4):
+    a32, b32 = a.astype(np.float32), b.astype(np.float32)
+    tol = ulps * np.spacing(np.maximum(np.abs(a32), np.abs(b32))).astype(np.float64) + 1e-38
+    return np.all(np.abs(a.astype(np.float64) - b.astype(np.float64)) <= tol)
+
+
+def test_gauss_targets_vs_oracle_and_golden(golden):
+    arrays, _ = golden
+    uv = torch.from_numpy(arrays["gauss_small_labels"]).float()[None].to(dev())
+    g = ops.gauss_targets(uv, 48, 64, 3.0)
+    assert g.dtype == torch.float64 and g.shape == (1, 4, 48, 64)
+    assert _ulp_close(g.cpu().numpy()[0], arrays["gauss_small"])
+    uvf = torch.from_numpy(arrays["gauss_labels"]).float()[None].to(dev())
+    gf = ops.gauss_targets(uvf, 480, 640, 8.0).cpu().numpy()[0]
+    assert _ulp_close(gf[:, ::4, ::4], arrays["gauss_full_sub4"])
+    assert _ulp_close(gf[:, [0, 20, 240, 479], :], arrays["gauss_full_rows"])
+    assert gf[0, 20, 10] == 1.0 and gf[2, 0, 0] == 1.0 and gf[3, 479, 639] == 1.0
+    assert np.allclose(gf.sum(axis=(1, 2)), arrays["gauss_full_sum"], rtol=1e-6)
+    g32 = ops.gauss_targets(uvf, 480, 640, 8.0, torch.float32).cpu().numpy()[0]
+    assert np.array_equal(g32.astype(np.float64), gf)  # f64 output is the widened f32 value
+
+
+def test_gauss_targets_batched_ragged_width():
+    uv = torch.tensor([[[3.0, 2.0], [0.0, 0.0]], [[8.5, 4.25], [10.0, 6.0]]])
+    g = ops.gauss_targets(uv.to(dev()), 7, 11, 2.0).cpu().numpy()   # W not a multiple of 4
+    assert _ulp_close(g, O.gauss_targets(uv.numpy(), 7, 11, 2.0))
+
+
+def test_dropin_gauss_2d_batch(golden):
+    import hulk_keypoints_b200 as hk
+    arrays, _ = golden
+    lab = arrays["gauss_small_labels"]
+    g = hk.gauss_2d_batch(64, 48, 3, torch.from_numpy(lab[:, 0].copy()), torch.from_numpy(lab[:, 1].copy()))
+    assert g.is_cuda and g.dtype == torch.float64 and g.shape == (4, 48, 64)
+    assert _ulp_close(g.cpu().numpy(), arrays["gauss_small"])
+
+
+# ------------------------------------------------------------------ BCE
+def test_bce_vs_golden_bit_exact_grad(golden):
+    arrays, _ = golden
+    p = torch.from_numpy(arrays["bce_pred"]).to(dev())
+    t = torch.from_numpy(arrays["bce_target"]).to(dev())
+    loss, grad = ops.bce_fwd_bwd(p, target=t)
+    ref = float(arrays["bce_loss"])
+    assert abs(loss.item() - ref) <= 1e-12 * abs(ref)
+    assert np.array_equal(grad.cpu().numpy(), arrays["bce_grad_logits"])
+    loss32, _ = ops.bce_fwd_bwd(p, target=t.float(), want_grad=False)
+    assert abs(loss32.item() - O.bce_loss(arrays["bce_pred"], arrays["bce_target"].astype(np.float32).astype(np.float64))) < 1e-12
+
+
+def test_bce_from_labels_and_logits(golden):
+    arrays, _ = golden
+    B, K, H, W = 2, 4, 48, 64
+    uv = torch.from_numpy(np.stack([arrays["gauss_small_labels"], arrays["gauss_small_labels"][::-1].copy()])).float()
+    z = torch.from_numpy(arrays["bce_logits"])
+    t = O.gauss_targets(uv.numpy(), H, W, 3.0)
+    p = torch.sigmoid(z)
+    loss, grad = ops.bce_fwd_bwd(z.to(dev()), uv=uv.to(dev()), sigma=3.0, pred_is_logits=True)
+    ref = O.bce_loss(p.numpy(), t)
+    assert abs(loss.item() - ref) <= 1e-6 * abs(ref)
+    gref = O.bce_grad_logits(p.numpy(), t)
+    assert np.abs(grad.cpu().numpy() - gref).max() <= 1e-6 * np.abs(gref).max()
+    # saturated elements: exact zeros, like the reference autograd
+    assert grad[0, 0, 0, 0].item() == 0.0
+
+
+def test_bce_known_answers():
+    p = torch.tensor([1.0, 0.5, 0.0, 0.25] * 4).view(1, 1, 4, 4).to(dev())
+    t = torch.tensor([0.25, 0.5, 0.0, 1.0] * 4, dtype=torch.float64).view(1, 1, 4, 4).to(dev())
+    loss, g = ops.bce_fwd_bwd(p, target=t)
+    expect = (100 * 0.75 + np.log(2.0) + 0.0 - np.log(0.25)) / 4
+    assert abs(loss.item() - expect) < 1e-12
+    gc = g.cpu().view(-1)
+    assert gc[0] == 0 and gc[1] == 0 and gc[2] == 0
+
+
+def test_fused_loss_autograd_matches_torch():
+    from hulk_keypoints_b200 import train_ops
+    torch.manual_seed(0)
+    z = (torch.randn(2, 4, 32, 48, device=dev()) * 3).requires_grad_(True)
+    uv = torch.tensor([[[5., 6.], [40., 20.], [0., 0.], [47., 31.]]] * 2, device=dev())
+    loss = train_ops.sigmoid_bce_loss(z, uv=uv, sigma=4.0)
+    loss.backward()
+    z2 = z.detach().clone().requires_grad_(True)
+    t = ops.gauss_targets(uv, 32, 48, 4.0)
+    ref = torch.nn.BCELoss()(torch.sigmoid(z2).double(), t)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-9
+    assert (z.grad - z2.grad).abs().max().item() <= 1e-6 * z2.grad.abs().max().item()
+
+
+# ------------------------------------------------------------------ head
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_head_vs_oracle(dtype):
+    g = torch.Generator().manual_seed(2)
+    B, h, w, C, K, H, W = 2, 8, 12, 512, 4, 64, 96
+    feat = (torch.randn(B, C, h, w, generator=g) * 2).to(dtype).float()
+    wfc = torch.randn(K, C, generator=g) * 0.05
+    bfc = torch.randn(K, generator=g) * 0.1
+    logits = F.conv2d(feat, wfc.view(K, C, 1, 1), bfc)
+    ref = O.heatmaps_from_logits(logits, (H, W)).numpy()
+    got = ops.head(feat.permute(0, 2, 3, 1).contiguous().to(dtype).to(dev()), wfc.to(dev()), bfc.to(dev()), H, W).cpu().numpy()
+    assert got.shape == (B, K, H, W)
+    assert np.abs(got - ref).max() < 2e-5
+    # corners of align_corners=True map exactly to the low-res logits
+    assert abs(got[0, 0, 0, 0] - torch.sigmoid(logits[0, 0, 0, 0]).item()) < 2e-6
+    assert abs(got[1, 3, H - 1, W - 1] - torch.sigmoid(logits[1, 3, h - 1, w - 1]).item()) < 2e-6
+
+
+def test_head_more_keypoints_and_saturation():
+    g = torch.Generator().manual_seed(3)
+    B, h, w, C, K, H, W = 1, 15, 20, 512, 16, 120, 160
+    feat = torch.randn(B, C, h, w, generator=g) * 30     # logits of +-60: sigmoid saturates to exactly 1.0f / ~0
+    wfc = torch.randn(K, C, generator=g) * 0.1
+    bfc = torch.zeros(K)
+    ref = O.heatmaps_from_logits(F.conv2d(feat, wfc.view(K, C, 1, 1), bfc), (H, W)).numpy()
+    got = ops.head(feat.permute(0, 2, 3, 1).contiguous().to(dev()), wfc.to(dev()), bfc.to(dev()), H, W).cpu().numpy()
+    assert np.abs(got - ref).max() < 1e-4
+    assert (got == 1.0).sum() > 0 and got.min() >= 0.0
+
+
+# ------------------------------------------------------------------ maxpool / pack
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_maxpool_exact(dtype):
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 64, 31, 46, generator=g).to(dtype)
+    ref = F.max_pool2d(x.float(), 3, 2, 1)
+    got = ops.maxpool3x3s2(x.permute(0, 2, 3, 1).contiguous().to(dev())).float().cpu().permute(0, 3, 1, 2)
+    assert torch.equal(got, ref)
+
+
+def test_pack_weights_and_bn_fold():
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(128, 64, 3, 3, generator=g)
+    gamma, beta = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g)
+    mean, var = torch.randn(128, generator=g), torch.rand(128, generator=g) + 0.1
+    wp, s, b = ops.pack_conv_weights(w.to(dev()), tuple(t.to(dev()) for t in (gamma, beta, mean, var)), 1e-5, torch.bfloat16)
+    assert torch.equal(wp.cpu(), w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+    s_ref = gamma / torch.sqrt(var + 1e-5)
+    assert torch.allclose(s.cpu(), s_ref, rtol=1e-6) and torch.allclose(b.cpu(), beta - mean * s_ref, rtol=1e-5, atol=1e-6)
+    wp32, s1, b0 = ops.pack_conv_weights(w.to(dev()), None, 1e-5, torch.float32)
+    assert torch.equal(wp32.cpu(), w.permute(0, 2, 3, 1).contiguous()) and (s1 == 1).all() and (b0 == 0).all()
+
+
+# ------------------------------------------------------------------ convolutions
+def _conv_case(B, H, W, cin, cout, k, stride, dil, residual, relu, seed, scale_in=1.0):
+    g = torch.Generator().manual_seed(seed)
+    pad = dil * (k - 1) // 2
+    x = torch.randn(B, cin, H, W, generator=g) * scale_in
+    w = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (k * k * cin)) ** 0.5
+    s = torch.rand(cout, generator=g) + 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    Ho, Wo = ops.conv_out_hw(H, W, k, stride, pad, dil)
+    res = torch.randn(B, cout, Ho, Wo, generator=g) if residual else None
+    return x, w, s, b, res, pad
+
+
+def _conv_ref(x, w, s, b, res, stride, pad, dil, relu):
+    y = F.conv2d(x.double(), w.double(), None, stride, pad, dil) * s.double().view(1, -1, 1, 1) + b.double().view(1, -1, 1, 1)
+    if res is not None:
+        y = y + res.double()
+    return (F.relu(y) if relu else y)
+
+
+FFMA_CASES = [
+    # B, H, W, cin, cout, k, stride, dil, residual, relu
+    (1, 20, 28, 64, 64, 3, 1, 1, True, True),
+    (2, 15, 20, 64, 128, 3, 2, 1, False, True),
+    (2, 15, 20, 64, 128, 1, 2, 1, False, False),
+    (1, 15, 20, 128, 256, 3, 1, 2, True, True),
+    (1, 15, 20, 256, 512, 3, 1, 4, False, True),
+    (3, 9, 7, 64, 68, 3, 1, 1, True, False),   # ragged M and N tiles
+]
+
+
+@pytest.mark.parametrize("case", FFMA_CASES)
+def test_conv_ffma_fp32_vs_oracle(case):
+    B, H, W, cin, cout, k, stride, dil, residual, relu = case
+    x, w, s, b, res, pad = _conv_case(*case, seed=11)
+    ref = _conv_ref(x, w, s, b, res, stride, pad, dil, relu)
+    wp, _, _ = ops.pack_conv_weights(w.to(dev()), None, 1e-5, torch.float32)
+    y = ops.conv_bn_act(x.permute(0, 2, 3, 1).contiguous().to(dev()), wp, s.to(dev()), b.to(dev()), stride=stride, pad=pad,
+                        dil=dil, relu=relu, residual=None if res is None else res.permute(0, 2, 3, 1).contiguous().to(dev()),
+                        algo=_lib.HK_CONV_FFMA)
+    got = y.cpu().permute(0, 3, 1, 2).double()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_conv_ffma_stem_nchw_input():
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(2, 3, 64, 96, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.05
+    s, b = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
+    ref = _conv_ref(x, w, s, b, None, 2, 3, 1, True)
+    wp, _, _ = ops.pack_conv_weights(w.to(dev()), None, 1e-5, torch.float32)
+    for odt, tol in ((torch.float32, 2e-6), (torch.bfloat16, 8e-3)):
+        y = ops.conv_bn_act(x.to(dev()), wp, s.to(dev()), b.to(dev()), stride=2, pad=3, dil=1, relu=True, out_dtype=odt,
+                            algo=_lib.HK_CONV_FFMA, in_is_nchw=True)
+        got = y.float().cpu().permute(0, 3, 1, 2).double()
+        assert (got - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+
+
+TC_CASES = [
+    # B, H, W, cin, cout, k, stride, dil, residual, relu
+    (1, 4, 16, 64, 64, 1, 1, 1, False, False),     # one box, one K block: the bare GEMM
+    (1, 8, 16, 64, 64, 1, 1, 1, False, False),     # one full M tile
+    (2, 8, 32, 128, 128, 1, 1, 1, False, True),    # two K blocks
+    (1, 12, 20, 64, 64, 3, 1, 1, True, True),      # ragged spatial tiles, 9 taps, halo zero fill
+    (2, 15, 20, 128, 256, 3, 1, 2, True, True),    # dilation 2, N=256
+    (1, 60, 80, 256, 512, 3, 1, 4, True, True),    # layer4 shape: dilation 4, 2 N tiles, 36+ K blocks
+    (4, 60, 80, 64, 128, 1, 1, 1, False, False),   # 150 M tiles > 148 SMs: persistence + TMEM double buffer
+    (2, 30, 40, 64, 128, 3, 2, 1, False, True),    # stride 2 via TMA element strides
+    (2, 30, 40, 64, 128, 1, 2, 1, False, False),   # 1x1 stride-2 downsample
+    (3, 15, 20, 512, 512, 3, 1, 4, True, True),    # odd number of boxes -> padding box
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_vs_oracle(case):
+    B, H, W, cin, cout, k, stride, dil, residual, relu = case
+    x, w, s, b, res, pad = _conv_case(*case, seed=21)
+    xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+    resb = None if res is None else res.to(torch.bfloat16)
+    # oracle: same bf16-rounded operands, exact (f64) accumulation
+    ref = _conv_ref(xb.float(), wb.float(), s, b, None if resb is None else resb.float(), stride, pad, dil, relu)
+    wp, _, _ = ops.pack_conv_weights(w.to(dev()), None, 1e-5, torch.bfloat16)
+    y = ops.conv_bn_act(xb.permute(0, 2, 3, 1).contiguous().to(dev()), wp, s.to(dev()), b.to(dev()), stride=stride, pad=pad,
+                        dil=dil, relu=relu, residual=None if resb is None else resb.permute(0, 2, 3, 1).contiguous().to(dev()),
+                        algo=_lib.HK_CONV_TCGEN05)
+    torch.cuda.synchronize()
+    got = y.float().cpu().permute(0, 3, 1, 2).double()
+    assert got.shape == ref.shape
+    err = (got - ref).abs()
+    tol = 2.0 ** -8 * ref.abs() + 1e-3 * max(1.0, ref.abs().max().item())   # one bf16 rounding of the output
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{bad} / {err.numel()} outputs off; max err {err.max().item():.4g}, ref max {ref.abs().max().item():.4g}"
