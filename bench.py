@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default="", help="write the per-launch timing table to this JSON file")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay (profiling)")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="device-resident loop only: no e2e loop, no per-launch breakdown, no CPU baseline (for ncu runs)")
     return ap.parse_args()
 
 
@@ -193,8 +196,12 @@ def per_launch_breakdown(engine, plan, decode=True):
         rows.append({"name": name, "ms": best, "flops": flops, "algo": None})
 
     B = plan.B
-    timed("stem", 2.0 * B * plan.h2 * plan.w2 * 64 * 147,
-          lambda: engine._conv(P["stem"], plan.x, plan.stem, relu=True, in_is_nchw=True))
+    if engine._stem_w_tc is not None:
+        timed("stem", 2.0 * B * plan.h2 * plan.w2 * 64 * 147,
+              lambda: ops.stem(plan.x, engine._stem_w_tc, P["stem"].scale, P["stem"].bias, out=plan.stem))
+    else:
+        timed("stem", 2.0 * B * plan.h2 * plan.w2 * 64 * 147,
+              lambda: engine._conv(P["stem"], plan.x, plan.stem, relu=True, in_is_nchw=True))
     cur = 0
     x = plan.view(cur, plan.h4, plan.w4, 64)
     timed("maxpool", 0.0, lambda: ops.maxpool3x3s2(plan.stem, out=x))
@@ -238,6 +245,7 @@ def run_ours(args, rank, world, local_rank):
     torch.manual_seed(0)
     model = hk.KeypointsGauss(K_KEYPOINTS, img_height=H, img_width=W, precision=args.precision).to(dev).eval()
     engine = model.engine()
+    engine.use_cuda_graph = not args.no_graph
     gen = torch.Generator().manual_seed(1000 + rank)
     host_imgs = [torch.rand(B, 3, H, W, generator=gen).pin_memory() for _ in range(2)]
     x_dev = host_imgs[0].to(dev)
@@ -276,6 +284,12 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (dev_ms * 1e-3)
     launches_per_step = plan.launches
+    if args.profile_mode:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "ms_per_step": dev_ms / args.steps, "profile_mode": True, "clocks": clocks,
+                              "gpu_launches_per_step": launches_per_step}), flush=True)
+        return
 
     # ---------------- end to end through the public API, host buffers ----------------
     copy_stream = torch.cuda.Stream(device=dev)
@@ -350,7 +364,7 @@ def run_ours(args, rank, world, local_rank):
                                f"{H}x{W}, K={K_KEYPOINTS}, random-init weights (BASELINE.json configs[1])",
                    "batch_per_gpu": B, "height": H, "width": W, "precision": args.precision,
                    "l2": f"per-step activations {B * 4.9:.0f}+ MB exceed the 126 MB L2 (no explicit flush)",
-                   "parallelism": f"batch-sharded x{world}, no collective", "cuda_graph": True},
+                   "parallelism": f"batch-sharded x{world}, no collective", "cuda_graph": not args.no_graph},
         "algorithmic_gflop_per_image": gf_img,
         "achieved_tflops_whole_step": gf_img * value / world / 1e3,
         "frac_of_bf16_peak_whole_step": gf_img * value / world / 1e3 / peaks["bf16_tflops"],

@@ -241,7 +241,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn get_encode_fn() {
+EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
   if (!tried) {

@@ -1,0 +1,267 @@
+// tcgen05 stem: conv 7x7 stride 2 pad 3 (3 -> 64) + folded BN + ReLU  (SURVEY.md k1), bf16 operands, fp32 accumulate.
+//
+// Replaces nn.Conv2d(3,64,7,2,3) -> BatchNorm2d -> ReLU of reference src/resnet.py:137-139,199-201 in the bf16
+// inference mode.  Cin = 3 is too thin for a TMA im2col, so the CTA builds the im2col tile itself:
+//   1. the fp32 NCHW input patch that feeds an 8x16 tile of stem outputs (21 rows x 37 cols x 3 ch) is loaded
+//      with coalesced reads, rounded to bf16 and stored pixel-major [y][x][c] in shared memory;
+//   2. for one output pixel and one filter row r the 7x3 = 21 taps are CONTIGUOUS in that layout, so the A tile
+//      (128 pixels x K) is 7 segments of 24 bf16 per row (21 taps + 3 that meet zero weights), K = 7*24 = 168,
+//      padded to 192 = three 64-wide K blocks; rows are written straight into the 128-byte-swizzled K-major
+//      layout tcgen05 expects (16-byte chunk index XOR row%8);
+//   3. one thread issues 12 tcgen05.mma (M=128, N=64, K=16) against the weights (64 x 192 bf16, TMA-loaded once
+//      per CTA), accumulator in TMEM;
+//   4. warps 0-3 read TMEM, apply scale/bias/ReLU and store 64 bf16 channels (128 contiguous bytes) per pixel.
+// Two CTAs per SM (77 KB smem each) overlap one CTA's global loads/stores with the other's build/MMA.
+#include <cuda.h>
+
+#include "hk_common.cuh"
+#include "hk_ptx.cuh"
+
+namespace hk {
+
+constexpr int ST_TILE_H = 8, ST_TILE_W = 16;            // stem-output pixels per tile (128 = UMMA M)
+constexpr int ST_PATCH_H = 2 * ST_TILE_H + 5;           // 21 input rows
+constexpr int ST_PATCH_W = 2 * ST_TILE_W + 6;           // 38 columns (37 used + 1 so segment reads stay in range)
+constexpr int ST_SEG = 24;                              // bf16 per filter row in the A tile (21 taps + 3 pad)
+constexpr int ST_K = 192;                               // 7*24 = 168 padded to 3 K blocks of 64
+constexpr int ST_KBLOCKS = ST_K / 64;
+constexpr int ST_COUT = 64;
+constexpr int ST_THREADS = 256;
+constexpr int ST_A_BYTES = 128 * 128 * ST_KBLOCKS;      // 48 KB
+constexpr int ST_B_BYTES = ST_COUT * 128 * ST_KBLOCKS;  // 24 KB
+constexpr int ST_PATCH_ELEMS = ST_PATCH_H * ST_PATCH_W * 3 + 8;
+constexpr int ST_SMEM_BYTES = 1024 + ST_A_BYTES + ST_B_BYTES + ((ST_PATCH_ELEMS * 2 + 15) & ~15) + 64;
+
+struct StemTcArgs {
+  const float* x;   // (B,3,H,W) fp32
+  const float* scale;
+  const float* bias;
+  __nv_bfloat16* y;  // (B,Ho,Wo,64) bf16
+  int B, H, W, Ho, Wo;
+  int tiles_x, tiles_per_img, num_tiles;
+};
+
+// byte offset of (row, 16-byte chunk) inside one 128-row x 128-byte K block, SWIZZLE_128B
+__device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
+
+__global__ void __launch_bounds__(ST_THREADS, 2)
+stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                   // 3 K blocks x [128 rows][128 B]
+  uint8_t* sB = smem + ST_A_BYTES;                      // 3 K blocks x [64 rows][128 B]
+  __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(sB + ST_B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + ((ST_PATCH_ELEMS * 2 + 15) & ~15));
+  uint64_t* w_bar = bars;       // weights landed
+  uint64_t* mma_bar = bars + 1; // accumulator ready / A tile free
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    ptx::prefetch_tensormap(&map_w);
+    ptx::mbar_init(w_bar, 1);
+    ptx::mbar_init(mma_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_smem, 64);
+    ptx::tmem_relinquish();
+  }
+  // zero the K padding of the A tile once: k in [168,192) = chunks 5..7 of K block 2, every row
+  for (int i = tid; i < 128 * 3; i += ST_THREADS) {
+    const int row = i / 3, chunk = 5 + i % 3;
+    *reinterpret_cast<uint4*>(sA + 2 * 16384 + sw128_off(row, chunk)) = make_uint4(0, 0, 0, 0);
+  }
+  for (int i = tid; i < 8; i += ST_THREADS) patch[ST_PATCH_H * ST_PATCH_W * 3 + i] = __float2bfloat16(0.f);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (tid == 0) {  // weights: three (64 k x 64 cout) boxes, once per CTA
+    ptx::mbar_arrive_expect_tx(w_bar, ST_B_BYTES);
+    for (int kb = 0; kb < ST_KBLOCKS; ++kb) ptx::tma_load_2d(sB + kb * 8192, &map_w, w_bar, kb * 64, 0);
+  }
+
+  constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, ST_COUT);
+  uint32_t mma_phase = 0;
+  bool first = true;
+
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    const int b = tile / a.tiles_per_img;
+    const int rem = tile - b * a.tiles_per_img;
+    const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+    const int oy0 = ty * ST_TILE_H, ox0 = tx * ST_TILE_W;
+    const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
+
+    // ---- 1. input patch -> smem, bf16, [y][x][c] ----
+    const float* xb = a.x + (size_t)b * 3 * a.H * a.W;
+    for (int i = tid; i < 3 * ST_PATCH_H * ST_PATCH_W; i += ST_THREADS) {
+      const int px = i % ST_PATCH_W;
+      const int r2 = i / ST_PATCH_W;
+      const int py = r2 % ST_PATCH_H, c = r2 / ST_PATCH_H;
+      const int iy = iy0 + py, ix = ix0 + px;
+      float v = 0.f;
+      if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) v = __ldg(xb + ((size_t)c * a.H + iy) * a.W + ix);
+      patch[(py * ST_PATCH_W + px) * 3 + c] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();  // patch complete; also: previous tile's epilogue has drained TMEM (all warps passed it)
+
+    // ---- 2. im2col rows into the swizzled A tile ----
+    // 128 pixels x 7 filter rows = 896 segments of 24 bf16 (48 B = 3 chunks); k0 = r*24 -> chunk index r*3 overall
+    for (int sidx = tid; sidx < 128 * 7; sidx += ST_THREADS) {
+      const int row = sidx & 127, r = sidx >> 7;
+      const int py = row >> 4, px = row & 15;
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(patch + ((2 * py + r) * ST_PATCH_W + 2 * px) * 3);
+      uint32_t v[12];
+#pragma unroll
+      for (int j = 0; j < 12; ++j) v[j] = src[j];
+#pragma unroll
+      for (int cidx = 0; cidx < 3; ++cidx) {
+        const int gchunk = r * 3 + cidx;  // 16-byte chunk index along K (0..20)
+        uint8_t* dst = sA + (gchunk >> 3) * 16384 + sw128_off(row, gchunk & 7);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(v[4 * cidx], v[4 * cidx + 1], v[4 * cidx + 2], v[4 * cidx + 3]);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to tcgen05
+    ptx::tc_fence_before();
+    __syncthreads();
+
+    // ---- 3. MMA ----
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      if (first) ptx::mbar_wait(w_bar, 0, 11);
+      const uint32_t a0 = ptx::smem_u32(sA), b0 = ptx::smem_u32(sB);
+#pragma unroll
+      for (int kb = 0; kb < ST_KBLOCKS; ++kb) {
+        const uint64_t adesc = ptx::make_smem_desc_sw128(a0 + kb * 16384);
+        const uint64_t bdesc = ptx::make_smem_desc_sw128(b0 + kb * 8192);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+      }
+      ptx::umma_commit(mma_bar);
+    }
+    first = false;
+
+    // ---- 4. epilogue (warps 0-3); every thread waits so the A tile / patch can be reused afterwards ----
+    ptx::mbar_wait(mma_bar, mma_phase, 12);
+    mma_phase ^= 1;
+    ptx::tc_fence_after();
+    if (warp < 4) {
+      const int row = warp * 32 + lane;
+      const int oy = oy0 + (row >> 4), ox = ox0 + (row & 15);
+      const bool valid = oy < a.Ho && ox < a.Wo;
+      __nv_bfloat16* dst = a.y + (((size_t)b * a.Ho + oy) * a.Wo + ox) * ST_COUT;
+#pragma unroll
+      for (int c0 = 0; c0 < ST_COUT; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
+        ptx::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c = c0 + g * 8;
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.scale + c));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.scale + c + 4));
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(a.bias + c));
+            const float4 t1 = __ldg(reinterpret_cast<const float4*>(a.bias + c + 4));
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(__uint_as_float(r[g * 8 + j]), sc[j], bi[j]), 0.f);
+            *reinterpret_cast<uint4*>(dst + c) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          }
+        }
+      }
+      ptx::tc_fence_before();
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 64);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();
+
+// OIHW (64,3,7,7) fp32 -> (64, 192) bf16 with k = r*24 + s*3 + c, zeros elsewhere
+__global__ void stem_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ST_COUT * ST_K) return;
+  const int o = i / ST_K, k = i - o * ST_K;
+  const int r = k / ST_SEG, j = k - r * ST_SEG;
+  float v = 0.f;
+  if (r < 7 && j < 21) {
+    const int s = j / 3, c = j - s * 3;
+    v = w[((o * 3 + c) * 7 + r) * 7 + s];
+  }
+  out[i] = __float2bfloat16_rn(v);
+}
+
+}  // namespace hk
+
+extern "C" {
+
+size_t hk_stem_packed_weight_bytes(void) { return (size_t)hk::ST_COUT * hk::ST_K * sizeof(__nv_bfloat16); }
+
+int hk_stem_pack_weights(const float* w_oihw, void* w_out, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(w_oihw && w_out, "hk_stem_pack_weights: null pointer");
+  stem_pack_kernel<<<ceil_div(ST_COUT * ST_K, 256), 256, 0, as_stream(stream)>>>(w_oihw, static_cast<__nv_bfloat16*>(w_out));
+  return check_launch("stem_pack_kernel");
+}
+
+int hk_stem_fwd(const float* x_nchw, const void* w_packed, const float* scale, const float* bias, void* y_nhwc, int B, int H,
+                int W, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(x_nchw && w_packed && scale && bias && y_nhwc, "hk_stem_fwd: null pointer");
+  HK_REQUIRE(B > 0 && H >= 7 && W >= 7, "hk_stem_fwd: bad shape");
+  HK_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_nhwc) & 15) == 0,
+             "hk_stem_fwd: buffers must be 16-byte aligned");
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return fail(HK_ERR_CUDA, "hk_stem_fwd: cuTensorMapEncodeTiled entry point not available");
+  CUtensorMap mw;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)ST_K, (cuuint64_t)ST_COUT};
+    const cuuint64_t strides[1] = {(cuuint64_t)ST_K * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)ST_COUT};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "hk_stem_fwd: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  }
+  StemTcArgs a;
+  a.x = x_nchw; a.scale = scale; a.bias = bias; a.y = static_cast<__nv_bfloat16*>(y_nhwc);
+  a.B = B; a.H = H; a.W = W;
+  a.Ho = (H + 6 - 7) / 2 + 1;
+  a.Wo = (W + 6 - 7) / 2 + 1;
+  a.tiles_x = ceil_div(a.Wo, ST_TILE_W);
+  a.tiles_per_img = a.tiles_x * ceil_div(a.Ho, ST_TILE_H);
+  const long long nt = (long long)a.tiles_per_img * B;
+  HK_REQUIRE(nt < 0x7fffffffLL, "hk_stem_fwd: too many tiles");
+  a.num_tiles = (int)nt;
+  static int attr_dev_mask = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_dev_mask & (1 << dev))) {
+    cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(HK_ERR_CUDA, "hk_stem_fwd: smem attribute: %s", cudaGetErrorString(e));
+    attr_dev_mask |= (1 << dev);
+  }
+  int grid = 2 * sm_count();
+  if (grid > a.num_tiles) grid = a.num_tiles;
+  stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM_BYTES, as_stream(stream)>>>(mw, a);
+  return check_launch("stem_tc_kernel");
+}
+
+}  // extern "C"

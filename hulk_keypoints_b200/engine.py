@@ -72,6 +72,7 @@ class InferenceEngine:
         self.use_cuda_graph = use_cuda_graph
         # stride-2 convs (layer2.0.conv1 and its 1x1 downsample) may be routed to the CUDA-core kernel
         self.stride2_algo = HK_CONV_TCGEN05
+        self.stem_on_tensor_cores = True  # bf16 mode: tcgen05 stem; False keeps the fp32 CUDA-core stem
         self._packed: Optional[Dict[str, _PackedConv]] = None
         self._packed_key = None
         self._plans: Dict[Tuple[int, int, int], _Plan] = {}
@@ -102,6 +103,7 @@ class InferenceEngine:
         self.device = dev
         tc = self.precision == "bf16"
         packed: Dict[str, _PackedConv] = {"stem": self._pack_one(net.conv1, net.bn1, HK_CONV_FFMA)}
+        self._stem_w_tc = ops.stem_pack_weights(net.conv1.weight) if (tc and self.stem_on_tensor_cores) else None
         for i, blk in enumerate(net.blocks()):
             def algo_for(conv):
                 if not tc:
@@ -128,7 +130,10 @@ class InferenceEngine:
         net = self.model.resnet.resnet34_8s
         P = self._packed
         n = 0
-        self._conv(P["stem"], plan.x, plan.stem, relu=True, in_is_nchw=True); n += 1
+        if self._stem_w_tc is not None:
+            ops.stem(plan.x, self._stem_w_tc, P["stem"].scale, P["stem"].bias, out=plan.stem); n += 1
+        else:
+            self._conv(P["stem"], plan.x, plan.stem, relu=True, in_is_nchw=True); n += 1
         cur = 0
         x = plan.view(cur, plan.h4, plan.w4, 64)
         ops.maxpool3x3s2(plan.stem, out=x); n += 1

@@ -73,6 +73,31 @@ def conv_bn_act(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, bi
     return out
 
 
+def stem_pack_weights(w_oihw: torch.Tensor) -> torch.Tensor:
+    """conv1.weight (64,3,7,7) fp32 -> the (64,192) bf16 K layout of the tensor-core stem."""
+    _need_cuda(w_oihw)
+    if tuple(w_oihw.shape) != (64, 3, 7, 7):
+        raise ValueError("stem weight must be (64,3,7,7)")
+    w = w_oihw.detach().contiguous().float()
+    out = torch.empty(int(lib().hk_stem_packed_weight_bytes()) // 2, device=w.device, dtype=torch.bfloat16)
+    check(lib().hk_stem_pack_weights(ptr(w), ptr(out), stream_ptr()), "hk_stem_pack_weights")
+    return out
+
+
+def stem(x_nchw: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B,3,H,W) fp32 -> conv7x7 s2 + affine + ReLU -> (B,H/2,W/2,64) bf16 NHWC on tcgen05."""
+    _need_cuda(x_nchw, w_packed, scale, bias, out)
+    if x_nchw.dtype != torch.float32 or not x_nchw.is_contiguous() or x_nchw.shape[1] != 3:
+        raise ValueError("stem needs a contiguous (B,3,H,W) fp32 input")
+    B, _, H, W = x_nchw.shape
+    Ho, Wo = conv_out_hw(H, W, 7, 2, 3, 1)
+    if out is None:
+        out = torch.empty((B, Ho, Wo, 64), device=x_nchw.device, dtype=torch.bfloat16)
+    check(lib().hk_stem_fwd(ptr(x_nchw), ptr(w_packed), ptr(scale), ptr(bias), ptr(out), B, H, W, stream_ptr()), "hk_stem_fwd")
+    return out
+
+
 def maxpool3x3s2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(x, out)
     B, H, W, Cc = x.shape

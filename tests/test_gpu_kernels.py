@@ -294,3 +294,20 @@ def test_conv_tcgen05_vs_oracle(case):
     tol = 2.0 ** -8 * ref.abs() + 1e-3 * max(1.0, ref.abs().max().item())   # one bf16 rounding of the output
     bad = (err > tol).sum().item()
     assert bad == 0, f"{bad} / {err.numel()} outputs off; max err {err.max().item():.4g}, ref max {ref.abs().max().item():.4g}"
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 96), (1, 480, 640), (3, 50, 70)])
+def test_stem_tcgen05_vs_oracle(shape):
+    B, H, W = shape
+    g = torch.Generator().manual_seed(31)
+    x = torch.rand(B, 3, H, W, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * (2.0 / (49 * 64)) ** 0.5
+    s, b = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
+    ref = _conv_ref(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), s, b, None, 2, 3, 1, True)
+    y = ops.stem(x.to(dev()), ops.stem_pack_weights(w.to(dev())), s.to(dev()), b.to(dev()))
+    torch.cuda.synchronize()
+    got = y.float().cpu().permute(0, 3, 1, 2).double()
+    assert got.shape == ref.shape
+    err = (got - ref).abs()
+    tol = 2.0 ** -8 * ref.abs() + 1e-3 * max(1.0, ref.abs().max().item())
+    assert (err > tol).sum().item() == 0, f"max err {err.max().item():.4g}"
