@@ -203,14 +203,14 @@ int conv_ffma_launch(const HkConvDesc& d, const void* x, const void* w, const fl
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo) {
-  const int cg = C / VEC;
-  const long long total = (long long)B * Ho * Wo * cg;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(t % cg);
-    long long r = t / cg;
-    const int ox = (int)(r % Wo); r /= Wo;
-    const int oy = (int)(r % Ho);
-    const int b = (int)(r / Ho);
+  const unsigned cg = (unsigned)(C / VEC);
+  const unsigned total = (unsigned)B * Ho * Wo * cg;  // host guarantees < 2^32
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const unsigned g = t % cg;
+    unsigned r = t / cg;
+    const int ox = (int)(r % (unsigned)Wo); r /= (unsigned)Wo;
+    const int oy = (int)(r % (unsigned)Ho);
+    const int b = (int)(r / (unsigned)Ho);
     float best[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) best[j] = -INFINITY;
@@ -262,8 +262,9 @@ extern "C" int hk_maxpool3x3s2_fwd(const void* x, void* y, int dtype, int batch,
   const int vec = dtype == HK_F32 ? 4 : 8;
   HK_REQUIRE(c % vec == 0, "hk_maxpool3x3s2_fwd: C=%d must be a multiple of %d", c, vec);
   const long long total = (long long)batch * out_h * out_w * (c / vec);
+  HK_REQUIRE(total < 0xffffffffLL, "hk_maxpool3x3s2_fwd: tensor too large for 32-bit indexing");
   int blocks = (int)ceil_div_ll(total, 256);
-  const int cap = sm_count() * 16;
+  const int cap = sm_count() * 32;
   if (blocks > cap) blocks = cap;
   if (dtype == HK_F32)
     maxpool3x3s2_kernel<float, 4><<<blocks, 256, 0, as_stream(stream)>>>(static_cast<const float*>(x), static_cast<float*>(y),

@@ -6,10 +6,13 @@
 // the conv and the upsample on all 1000 channels and slices afterwards; both ops act per output
 // channel, so only the K kept rows are computed here.
 //
-//   1. head_logits_kernel: one warp per low-res pixel; 128-bit loads of the C-vector, K dot products
-//      against fc rows staged in shared memory, warp-shuffle reduction -> (B,K,h,w) fp32 logits (L2-resident).
+//   1. head_logits_kernel: one warp per low-res pixel (two pixels in flight per warp); 128-bit loads of the
+//      C-vector; fc rows live in REGISTERS in groups of 4 keypoints (the config.py case K=4 needs one
+//      group); a 6-shuffle multi-value butterfly reduces the 4 dot products -> (B,K,h,w) fp32 logits, which
+//      stay L2-resident for step 2.
 //   2. head_upsample_sigmoid_kernel: one thread per 4 consecutive output x; ATen's align_corners
 //      arithmetic (scale=(in-1)/(out-1), src=scale*dst, lambda=src-floor) in fp32, sigmoid, float4 store.
+//      All index math is 32-bit (64-bit div/mod was the bottleneck of the first version).
 #include "hk_common.cuh"
 
 namespace hk {
@@ -35,89 +38,138 @@ __device__ __forceinline__ void load8<float>(const float* p, float* f) {
   f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
-template <typename FeatT>
+// Sum v[0..3] over the 32 lanes with 6 shuffles; afterwards lane 8*k holds the total of v[k].
+__device__ __forceinline__ float reduce4(const float (&v)[4], int lane) {
+  const bool hi = (lane & 16) != 0;
+  float k0 = hi ? v[2] : v[0], k1 = hi ? v[3] : v[1];
+  const float s0 = hi ? v[0] : v[2], s1 = hi ? v[1] : v[3];
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  const bool hi2 = (lane & 8) != 0;
+  float kk = hi2 ? k1 : k0;
+  const float s = hi2 ? k0 : k1;
+  kk += __shfl_xor_sync(0xffffffffu, s, 8);
+  kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+  kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+  kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+  return kk;
+}
+
+// SLABS = C / 256 (1 or 2).  Keypoints are processed in groups of 4 (weights of the group in registers).
+template <typename FeatT, int SLABS>
 __global__ void __launch_bounds__(kHeadThreads)
 head_logits_kernel(const FeatT* __restrict__ feat, const float* __restrict__ w_fc, const float* __restrict__ b_fc,
-                   float* __restrict__ logits, long long pixels, int hw, int K, int C) {
-  extern __shared__ float sw[];  // K*C fc rows
-  for (int i = threadIdx.x; i < K * C; i += kHeadThreads) sw[i] = w_fc[i];
-  __syncthreads();
+                   float* __restrict__ logits, int pixels, int hw, int K, int C) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = kHeadThreads >> 5;
-  const int slabs = C >> 8;  // 256 channels per pass (32 lanes x 8)
-  for (long long pix = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); pix < pixels;
-       pix += (long long)gridDim.x * warps_per_block) {
-    float f[kHeadMaxPerLane];
-    const FeatT* src = feat + pix * C;
+  const int wstride = gridDim.x * warps_per_block;
+  constexpr int PER = SLABS * 8;
+  for (int kg = 0; kg < K; kg += 4) {
+    float wr[4][PER];
 #pragma unroll
-    for (int s = 0; s < kHeadMaxPerLane / 8; ++s)
-      if (s < slabs) load8<FeatT>(src + s * 256 + lane * 8, f + s * 8);
-    const long long b = pix / hw;
-    const int rem = (int)(pix - b * hw);
-    for (int k = 0; k < K; ++k) {
-      float acc = 0.f;
-      const float* wk = sw + k * C;
+    for (int j = 0; j < 4; ++j) {
+      const int k = min(kg + j, K - 1);
 #pragma unroll
-      for (int s = 0; s < kHeadMaxPerLane / 8; ++s) {
-        if (s < slabs) {
-          const float4 w0 = *reinterpret_cast<const float4*>(wk + s * 256 + lane * 8);
-          const float4 w1 = *reinterpret_cast<const float4*>(wk + s * 256 + lane * 8 + 4);
-          acc = fmaf(f[s * 8 + 0], w0.x, acc);
-          acc = fmaf(f[s * 8 + 1], w0.y, acc);
-          acc = fmaf(f[s * 8 + 2], w0.z, acc);
-          acc = fmaf(f[s * 8 + 3], w0.w, acc);
-          acc = fmaf(f[s * 8 + 4], w1.x, acc);
-          acc = fmaf(f[s * 8 + 5], w1.y, acc);
-          acc = fmaf(f[s * 8 + 6], w1.z, acc);
-          acc = fmaf(f[s * 8 + 7], w1.w, acc);
+      for (int s = 0; s < SLABS; ++s) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w_fc + (size_t)k * C + s * 256 + lane * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(w_fc + (size_t)k * C + s * 256 + lane * 8 + 4));
+        wr[j][s * 8 + 0] = a.x; wr[j][s * 8 + 1] = a.y; wr[j][s * 8 + 2] = a.z; wr[j][s * 8 + 3] = a.w;
+        wr[j][s * 8 + 4] = b.x; wr[j][s * 8 + 5] = b.y; wr[j][s * 8 + 6] = b.z; wr[j][s * 8 + 7] = b.w;
+      }
+    }
+    const int kq = kg + (lane >> 3);  // keypoint whose total lands in this lane (lanes 0, 8, 16, 24)
+    const float bq = (kq < K) ? __ldg(b_fc + kq) : 0.f;
+    for (int pix = blockIdx.x * warps_per_block + (threadIdx.x >> 5); pix < pixels; pix += 2 * wstride) {
+      const int pix2 = pix + wstride;
+      const bool has2 = pix2 < pixels;
+      float f0[PER], f1[PER];
+#pragma unroll
+      for (int s = 0; s < SLABS; ++s) load8<FeatT>(feat + (size_t)pix * C + s * 256 + lane * 8, f0 + s * 8);
+      if (has2) {
+#pragma unroll
+        for (int s = 0; s < SLABS; ++s) load8<FeatT>(feat + (size_t)pix2 * C + s * 256 + lane * 8, f1 + s * 8);
+      }
+      float a0[4], a1[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a0[j] = 0.f;
+        a1[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) a0[j] = fmaf(f0[i], wr[j][i], a0[j]);
+        if (has2) {
+#pragma unroll
+          for (int i = 0; i < PER; ++i) a1[j] = fmaf(f1[i], wr[j][i], a1[j]);
         }
       }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-      if (lane == 0) logits[(b * K + k) * hw + rem] = acc + __ldg(b_fc + k);
+      const float r0 = reduce4(a0, lane);
+      const float r1 = reduce4(a1, lane);
+      if ((lane & 7) == 0 && kq < K) {
+        const int b = pix / hw, rem = pix - b * hw;
+        logits[((size_t)b * K + kq) * hw + rem] = r0 + bq;
+        if (has2) {
+          const int b2 = pix2 / hw, rem2 = pix2 - b2 * hw;
+          logits[((size_t)b2 * K + kq) * hw + rem2] = r1 + bq;
+        }
+      }
     }
   }
 }
 
-__device__ __forceinline__ float sigmoidf_ref(float v) { return 1.0f / (1.0f + expf(-v)); }
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_f(float v) {
+  if (FAST) return __fdividef(1.0f, 1.0f + __expf(-v));
+  return 1.0f / (1.0f + expf(-v));
+}
 
+// One thread = 4 consecutive output x of one output row.  rows = maps*H, wq = ceil(W/4); rows*wq < 2^31.
+template <bool FAST>
 __global__ void __launch_bounds__(256)
-head_upsample_sigmoid_kernel(const float* __restrict__ logits, float* __restrict__ heat, int maps, int h, int w, int H,
-                             int W, float ry, float rx) {
-  const int wq = (W + 3) >> 2;
-  const long long total = (long long)maps * H * wq;
-  const bool vec = (W & 3) == 0;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int xq = (int)(t % wq);
-    const long long r = t / wq;
-    const int Y = (int)(r % H);
-    const int map = (int)(r / H);
-    const float sy = ry * (float)Y;
-    const int y0 = min((int)sy, h - 1);
-    const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
-    const float ly = sy - (float)y0, hy = 1.0f - ly;
-    const float* row0 = logits + ((size_t)map * h + y0) * w;
-    const float* row1 = logits + ((size_t)map * h + y1) * w;
-    float o[4];
+head_upsample_sigmoid_kernel(const float* __restrict__ logits, float* __restrict__ heat, unsigned total, int h, int w,
+                             int H, int W, unsigned wq, float ry, float rx) {
+  const unsigned t = blockIdx.x * 256u + threadIdx.x;
+  if (t >= total) return;
+  const unsigned row = t / wq;           // map * H + Y
+  const unsigned xq = t - row * wq;
+  const unsigned map = row / (unsigned)H;
+  const int Y = (int)(row - map * (unsigned)H);
+  const float sy = ry * (float)Y;
+  const int y0 = min((int)sy, h - 1);
+  const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, hy = 1.0f - ly;
+  const float* row0 = logits + ((size_t)map * h + y0) * w;
+  const float* row1 = logits + ((size_t)map * h + y1) * w;
+  float o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int X = min(xq * 4 + j, W - 1);
-      const float sx = rx * (float)X;
-      const int x0 = min((int)sx, w - 1);
-      const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
-      const float lx = sx - (float)x0, hx = 1.0f - lx;
-      const float v = hy * (hx * __ldg(row0 + x0) + lx * __ldg(row0 + x1)) + ly * (hx * __ldg(row1 + x0) + lx * __ldg(row1 + x1));
-      o[j] = sigmoidf_ref(v);
-    }
-    float* dst = heat + ((size_t)map * H + Y) * W + xq * 4;
-    if (vec) {
-      __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (xq * 4 + j < W) dst[j] = o[j];
-    }
+  for (int j = 0; j < 4; ++j) {
+    const int X = min((int)xq * 4 + j, W - 1);
+    const float sx = rx * (float)X;
+    const int x0 = min((int)sx, w - 1);
+    const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float lx = sx - (float)x0, hx = 1.0f - lx;
+    const float v = hy * (hx * __ldg(row0 + x0) + lx * __ldg(row0 + x1)) + ly * (hx * __ldg(row1 + x0) + lx * __ldg(row1 + x1));
+    o[j] = sigmoid_f<FAST>(v);
   }
+  float* dst = heat + (size_t)row * W + xq * 4;
+  if ((W & 3) == 0) {
+    __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((int)xq * 4 + j < W) dst[j] = o[j];
+  }
+}
+
+template <typename FeatT>
+static void launch_logits(const void* feat, const float* w_fc, const float* b_fc, float* logits, int pixels, int hw, int K, int C,
+                          cudaStream_t s) {
+  int blocks = ceil_div(pixels, (kHeadThreads / 32) * 2);
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (C == 512)
+    head_logits_kernel<FeatT, 2><<<blocks, kHeadThreads, 0, s>>>(static_cast<const FeatT*>(feat), w_fc, b_fc, logits, pixels, hw, K, C);
+  else
+    head_logits_kernel<FeatT, 1><<<blocks, kHeadThreads, 0, s>>>(static_cast<const FeatT*>(feat), w_fc, b_fc, logits, pixels, hw, K, C);
 }
 
 }  // namespace hk
@@ -127,43 +179,30 @@ extern "C" int hk_head_fwd(const void* feat, int feat_dtype, const float* w_fc, 
   using namespace hk;
   HK_REQUIRE(feat && w_fc && b_fc && logits_ws && heat, "hk_head_fwd: null pointer");
   HK_REQUIRE(B > 0 && K > 0 && h > 0 && w > 0 && H > 0 && W > 0, "hk_head_fwd: bad shape");
-  HK_REQUIRE(C % 256 == 0 && C <= 32 * kHeadMaxPerLane, "hk_head_fwd: C=%d must be a multiple of 256 and <= 512", C);
-  HK_REQUIRE((size_t)K * C * sizeof(float) <= 200 * 1024, "hk_head_fwd: K=%d too large for shared memory", K);
+  HK_REQUIRE(C == 256 || C == 512, "hk_head_fwd: C=%d must be 256 or 512", C);
   HK_REQUIRE(feat_dtype == HK_BF16 || feat_dtype == HK_F32, "hk_head_fwd: feat dtype must be bf16 or f32");
-  HK_REQUIRE((reinterpret_cast<uintptr_t>(feat) & 15) == 0 && (reinterpret_cast<uintptr_t>(heat) & 15) == 0,
-             "hk_head_fwd: feat/heat must be 16-byte aligned");
+  HK_REQUIRE((reinterpret_cast<uintptr_t>(feat) & 15) == 0 && (reinterpret_cast<uintptr_t>(heat) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(w_fc) & 15) == 0,
+             "hk_head_fwd: feat/heat/w_fc must be 16-byte aligned");
+  HK_REQUIRE((long long)B * h * w < 0x7fffffffLL, "hk_head_fwd: too many low-res pixels");
+  const long long total_ll = (long long)B * K * H * ((W + 3) / 4);
+  HK_REQUIRE(total_ll < 0xffffffffLL, "hk_head_fwd: heatmap too large for 32-bit indexing");
   cudaStream_t s = as_stream(stream);
-  const long long pixels = (long long)B * h * w;
-  const size_t smem = (size_t)K * C * sizeof(float);
-  int blocks = (int)ceil_div_ll(pixels, (kHeadThreads / 32) * 4);
-  const int cap = sm_count() * 8;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  cudaError_t e;
-  if (feat_dtype == HK_BF16) {
-    if (smem > 48 * 1024) {
-      e = cudaFuncSetAttribute(head_logits_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return fail(HK_ERR_CUDA, "hk_head_fwd: smem attribute: %s", cudaGetErrorString(e));
-    }
-    head_logits_kernel<__nv_bfloat16><<<blocks, kHeadThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(feat), w_fc, b_fc,
-                                                                        logits_ws, pixels, h * w, K, C);
-  } else {
-    if (smem > 48 * 1024) {
-      e = cudaFuncSetAttribute(head_logits_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return fail(HK_ERR_CUDA, "hk_head_fwd: smem attribute: %s", cudaGetErrorString(e));
-    }
-    head_logits_kernel<float><<<blocks, kHeadThreads, smem, s>>>(static_cast<const float*>(feat), w_fc, b_fc, logits_ws, pixels,
-                                                                h * w, K, C);
-  }
+  const int pixels = B * h * w;
+  if (feat_dtype == HK_BF16) launch_logits<__nv_bfloat16>(feat, w_fc, b_fc, logits_ws, pixels, h * w, K, C, s);
+  else launch_logits<float>(feat, w_fc, b_fc, logits_ws, pixels, h * w, K, C, s);
   int rc = check_launch("head_logits_kernel");
   if (rc) return rc;
   // ATen area_pixel_compute_scale(align_corners=True): (in - 1) / (out - 1) in float, 0 when out == 1
   const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  const long long total = (long long)B * K * H * ((W + 3) / 4);
-  int ublocks = (int)ceil_div_ll(total, 256);
-  const int ucap = sm_count() * 16;
-  if (ublocks > ucap) ublocks = ucap;
-  head_upsample_sigmoid_kernel<<<ublocks, 256, 0, s>>>(logits_ws, heat, B * K, h, w, H, W, ry, rx);
+  const unsigned total = (unsigned)total_ll;
+  const unsigned wq = (unsigned)((W + 3) / 4);
+  const unsigned ublocks = (total + 255u) / 256u;
+  // bf16 features = throughput mode: ex2/rcp-approx sigmoid (<= 2 ulp); fp32 features = correctness mode: expf + IEEE divide
+  if (feat_dtype == HK_BF16)
+    head_upsample_sigmoid_kernel<true><<<ublocks, 256, 0, s>>>(logits_ws, heat, total, h, w, H, W, wq, ry, rx);
+  else
+    head_upsample_sigmoid_kernel<false><<<ublocks, 256, 0, s>>>(logits_ws, heat, total, h, w, H, W, wq, ry, rx);
   return check_launch("head_upsample_sigmoid_kernel");
 }

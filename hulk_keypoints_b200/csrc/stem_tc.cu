@@ -88,25 +88,50 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemTcArgs a) {
   uint32_t mma_phase = 0;
   bool first = true;
 
+  // Software pipeline: the NEXT tile's input patch is fetched into registers (PATCH_PER_THREAD independent global
+  // loads in flight per thread) while the current tile is built, multiplied and stored.
+  constexpr int PATCH_N = 3 * ST_PATCH_H * ST_PATCH_W;
+  constexpr int PATCH_PER_THREAD = (PATCH_N + ST_THREADS - 1) / ST_THREADS;
+  float pre[PATCH_PER_THREAD];
+  auto prefetch_patch = [&](int t) {
+    const int pb = t / a.tiles_per_img;
+    const int prem = t - pb * a.tiles_per_img;
+    const int pty = prem / a.tiles_x, ptx_ = prem - pty * a.tiles_x;
+    const int piy0 = 2 * pty * ST_TILE_H - 3, pix0 = 2 * ptx_ * ST_TILE_W - 3;
+    const float* xb = a.x + (size_t)pb * 3 * a.H * a.W;
+#pragma unroll
+    for (int j = 0; j < PATCH_PER_THREAD; ++j) {
+      const int i = tid + j * ST_THREADS;
+      const int px = i % ST_PATCH_W;
+      const int r2 = i / ST_PATCH_W;
+      const int py = r2 % ST_PATCH_H, c = r2 / ST_PATCH_H;
+      const int iy = piy0 + py, ix = pix0 + px;
+      float v = 0.f;
+      if (i < PATCH_N && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) v = __ldg(xb + ((size_t)c * a.H + iy) * a.W + ix);
+      pre[j] = v;
+    }
+  };
+  if ((int)blockIdx.x < a.num_tiles) prefetch_patch(blockIdx.x);
+
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
     const int b = tile / a.tiles_per_img;
     const int rem = tile - b * a.tiles_per_img;
     const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
     const int oy0 = ty * ST_TILE_H, ox0 = tx * ST_TILE_W;
-    const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
 
-    // ---- 1. input patch -> smem, bf16, [y][x][c] ----
-    const float* xb = a.x + (size_t)b * 3 * a.H * a.W;
-    for (int i = tid; i < 3 * ST_PATCH_H * ST_PATCH_W; i += ST_THREADS) {
-      const int px = i % ST_PATCH_W;
-      const int r2 = i / ST_PATCH_W;
-      const int py = r2 % ST_PATCH_H, c = r2 / ST_PATCH_H;
-      const int iy = iy0 + py, ix = ix0 + px;
-      float v = 0.f;
-      if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) v = __ldg(xb + ((size_t)c * a.H + iy) * a.W + ix);
-      patch[(py * ST_PATCH_W + px) * 3 + c] = __float2bfloat16_rn(v);
+    // ---- 1. prefetched input patch -> smem, bf16, [y][x][c] ----
+#pragma unroll
+    for (int j = 0; j < PATCH_PER_THREAD; ++j) {
+      const int i = tid + j * ST_THREADS;
+      if (i < PATCH_N) {
+        const int px = i % ST_PATCH_W;
+        const int r2 = i / ST_PATCH_W;
+        const int py = r2 % ST_PATCH_H, c = r2 / ST_PATCH_H;
+        patch[(py * ST_PATCH_W + px) * 3 + c] = __float2bfloat16_rn(pre[j]);
+      }
     }
     __syncthreads();  // patch complete; also: previous tile's epilogue has drained TMEM (all warps passed it)
+    if (tile + (int)gridDim.x < a.num_tiles) prefetch_patch(tile + gridDim.x);
 
     // ---- 2. im2col rows into the swizzled A tile ----
     // 128 pixels x 7 filter rows = 896 segments of 24 bf16 (48 B = 3 chunks); k0 = r*24 -> chunk index r*3 overall

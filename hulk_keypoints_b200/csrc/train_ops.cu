@@ -26,12 +26,12 @@ gauss_targets_kernel(const float* __restrict__ uv, int H, int W, float denom, Ou
   const int map = blockIdx.y;
   const float u = __ldg(uv + 2 * map), v = __ldg(uv + 2 * map + 1);
   const int wq = (W + 3) >> 2;
-  const long long total = (long long)wq * H;
+  const unsigned total = (unsigned)wq * (unsigned)H;
   OutT* dst = out + (size_t)map * H * W;
   const bool vec = (W & 3) == 0;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int y = (int)(t / wq);
-    const int x0 = (int)(t % wq) << 2;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int y = (int)(t / (unsigned)wq);
+    const int x0 = (int)(t - (unsigned)y * (unsigned)wq) << 2;
     float g[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) g[j] = gauss_value((float)(x0 + j), (float)y, u, v, denom);
@@ -80,9 +80,9 @@ bce_fwd_bwd_kernel(const float* __restrict__ pred, const void* __restrict__ targ
       const float4 a = __ldcs(reinterpret_cast<const float4*>(target) + q);
       t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w;
     } else {
-      const long long e = q << 2;
-      const int map = (int)(e / hw);
-      const int rem = (int)(e - (long long)map * hw);
+      const unsigned e = (unsigned)q << 2;  // host guarantees n < 2^32 in label mode
+      const int map = (int)(e / (unsigned)hw);
+      const int rem = (int)(e - (unsigned)map * (unsigned)hw);
       const int y = rem / W, x0 = rem - y * W;
       const float u = __ldg(uv + 2 * map), v = __ldg(uv + 2 * map + 1);
 #pragma unroll
@@ -196,6 +196,7 @@ int hk_bce_fwd_bwd(const float* pred, int pred_is_logits, const void* target_or_
     else HK_BCE_LAUNCH(1, target_or_null, nullptr);
   } else {
     HK_REQUIRE(sigma > 0.f, "hk_bce_fwd_bwd: sigma must be positive");
+    HK_REQUIRE(n < 0xffffffffLL, "hk_bce_fwd_bwd: label mode supports up to 2^32 elements");
     HK_BCE_LAUNCH(2, nullptr, uv_or_null);
   }
 #undef HK_BCE_LAUNCH
