@@ -275,6 +275,10 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const ConvTcA
   return check_launch("conv_tc_kernel");
 }
 
+bool conv_tc_c64_applicable(const HkConvDesc& d);
+int conv_tc_c64_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
+                       const void* residual, void* y, cudaStream_t s);
+
 int conv_tc_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
                    const void* residual, void* y, cudaStream_t s) {
   HK_REQUIRE(d.in_dtype == HK_BF16 && d.out_dtype == HK_BF16 && !d.in_is_nchw, "conv(tcgen05): needs NHWC bf16 in and out");
@@ -286,6 +290,9 @@ int conv_tc_launch(const HkConvDesc& d, const void* x, const void* w, const floa
              "conv(tcgen05): buffers must be 16-byte aligned");
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return fail(HK_ERR_CUDA, "conv(tcgen05): cuTensorMapEncodeTiled entry point not available");
+
+  // layer1 shape (3x3, 64 -> 64, stride 1): resident weights + haloed boxes, 3.6x less L2->SM traffic
+  if (conv_tc_c64_applicable(d)) return conv_tc_c64_launch(d, x, w, scale, bias, residual, y, s);
 
   const int block_n = d.out_c % 256 == 0 ? 256 : (d.out_c % 128 == 0 ? 128 : 64);
   const int ktot = d.kh * d.kw * d.in_c;

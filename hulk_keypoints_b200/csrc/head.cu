@@ -20,23 +20,33 @@ namespace hk {
 constexpr int kHeadThreads = 256;
 constexpr int kHeadMaxPerLane = 16;  // C <= 512
 
+// 8 consecutive channels held RAW in registers (bf16: one uint4; fp32: two float4) and unpacked at first use, so
+// several pixels' loads can be in flight without doubling the register footprint.
 template <typename FeatT>
-__device__ __forceinline__ void load8(const FeatT* p, float* f);
+struct Raw8;
 template <>
-__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
-  const uint4 q = __ldcs(reinterpret_cast<const uint4*>(p));
-  unpack_bf16x2(q.x, f[0], f[1]);
-  unpack_bf16x2(q.y, f[2], f[3]);
-  unpack_bf16x2(q.z, f[4], f[5]);
-  unpack_bf16x2(q.w, f[6], f[7]);
-}
+struct Raw8<__nv_bfloat16> {
+  uint4 q;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { q = __ldcs(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void unpack(float* f) const {
+    unpack_bf16x2(q.x, f[0], f[1]);
+    unpack_bf16x2(q.y, f[2], f[3]);
+    unpack_bf16x2(q.z, f[4], f[5]);
+    unpack_bf16x2(q.w, f[6], f[7]);
+  }
+};
 template <>
-__device__ __forceinline__ void load8<float>(const float* p, float* f) {
-  const float4 a = __ldcs(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
-  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
-  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-}
+struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = __ldcs(reinterpret_cast<const float4*>(p));
+    b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void unpack(float* f) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
 
 // Sum v[0..3] over the 32 lanes with 6 shuffles; afterwards lane 8*k holds the total of v[k].
 __device__ __forceinline__ float reduce4(const float (&v)[4], int lane) {
@@ -79,36 +89,37 @@ head_logits_kernel(const FeatT* __restrict__ feat, const float* __restrict__ w_f
     }
     const int kq = kg + (lane >> 3);  // keypoint whose total lands in this lane (lanes 0, 8, 16, 24)
     const float bq = (kq < K) ? __ldg(b_fc + kq) : 0.f;
-    for (int pix = blockIdx.x * warps_per_block + (threadIdx.x >> 5); pix < pixels; pix += 2 * wstride) {
-      const int pix2 = pix + wstride;
-      const bool has2 = pix2 < pixels;
-      float f0[PER], f1[PER];
+    // NPIX pixels in flight per warp: all feature loads are issued before the first use (HBM latency hiding)
+    constexpr int NPIX = sizeof(FeatT) == 2 ? 4 : 2;
+    for (int pix0 = blockIdx.x * warps_per_block + (threadIdx.x >> 5); pix0 < pixels; pix0 += NPIX * wstride) {
+      Raw8<FeatT> raw[NPIX][SLABS];
 #pragma unroll
-      for (int s = 0; s < SLABS; ++s) load8<FeatT>(feat + (size_t)pix * C + s * 256 + lane * 8, f0 + s * 8);
-      if (has2) {
+      for (int p = 0; p < NPIX; ++p) {
+        const int pix = pix0 + p * wstride;
+        if (pix < pixels) {
 #pragma unroll
-        for (int s = 0; s < SLABS; ++s) load8<FeatT>(feat + (size_t)pix2 * C + s * 256 + lane * 8, f1 + s * 8);
-      }
-      float a0[4], a1[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        a0[j] = 0.f;
-        a1[j] = 0.f;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) a0[j] = fmaf(f0[i], wr[j][i], a0[j]);
-        if (has2) {
-#pragma unroll
-          for (int i = 0; i < PER; ++i) a1[j] = fmaf(f1[i], wr[j][i], a1[j]);
+          for (int s = 0; s < SLABS; ++s) raw[p][s].load(feat + (size_t)pix * C + s * 256 + lane * 8);
         }
       }
-      const float r0 = reduce4(a0, lane);
-      const float r1 = reduce4(a1, lane);
-      if ((lane & 7) == 0 && kq < K) {
-        const int b = pix / hw, rem = pix - b * hw;
-        logits[((size_t)b * K + kq) * hw + rem] = r0 + bq;
-        if (has2) {
-          const int b2 = pix2 / hw, rem2 = pix2 - b2 * hw;
-          logits[((size_t)b2 * K + kq) * hw + rem2] = r1 + bq;
+#pragma unroll
+      for (int p = 0; p < NPIX; ++p) {
+        const int pix = pix0 + p * wstride;
+        if (pix < pixels) {  // warp-uniform
+          float f[PER];
+#pragma unroll
+          for (int s = 0; s < SLABS; ++s) raw[p][s].unpack(f + s * 8);
+          float acc[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[j] = 0.f;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) acc[j] = fmaf(f[i], wr[j][i], acc[j]);
+          }
+          const float r = reduce4(acc, lane);
+          if ((lane & 7) == 0 && kq < K) {
+            const int b = pix / hw, rem = pix - b * hw;
+            logits[((size_t)b * K + kq) * hw + rem] = r + bq;
+          }
         }
       }
     }
@@ -121,48 +132,61 @@ __device__ __forceinline__ float sigmoid_f(float v) {
   return 1.0f / (1.0f + expf(-v));
 }
 
-// One thread = 4 consecutive output x of one output row.  rows = maps*H, wq = ceil(W/4); rows*wq < 2^31.
+// One CTA = one output row (map = blockIdx.z, Y = blockIdx.y); one thread = 4 consecutive output x.  The two source
+// rows are staged in shared memory; no integer division anywhere.  FAST (bf16 mode): the vertical lerp is done once
+// per source column while staging (separable form); exact (fp32 mode): ATen's operation order
+// hy*(hx*a + lx*b) + ly*(hx*c + lx*d) is kept so the result tracks the reference to the last ulp or two.
 template <bool FAST>
 __global__ void __launch_bounds__(256)
-head_upsample_sigmoid_kernel(const float* __restrict__ logits, float* __restrict__ heat, unsigned total, int h, int w,
-                             int H, int W, unsigned wq, float ry, float rx) {
-  const unsigned t = blockIdx.x * 256u + threadIdx.x;
-  if (t >= total) return;
-  const unsigned row = t / wq;           // map * H + Y
-  const unsigned xq = t - row * wq;
-  const unsigned map = row / (unsigned)H;
-  const int Y = (int)(row - map * (unsigned)H);
+head_upsample_sigmoid_kernel(const float* __restrict__ logits, float* __restrict__ heat, int h, int w, int H, int W,
+                             int wq, float ry, float rx) {
+  extern __shared__ float srow[];  // FAST: w floats; exact: 2*w floats
+  const int map = blockIdx.z, Y = blockIdx.y;
   const float sy = ry * (float)Y;
   const int y0 = min((int)sy, h - 1);
   const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
   const float ly = sy - (float)y0, hy = 1.0f - ly;
   const float* row0 = logits + ((size_t)map * h + y0) * w;
   const float* row1 = logits + ((size_t)map * h + y1) * w;
+  for (int i = threadIdx.x; i < w; i += blockDim.x) {
+    const float a = __ldg(row0 + i), c = __ldg(row1 + i);
+    if (FAST) {
+      srow[i] = hy * a + ly * c;
+    } else {
+      srow[i] = a;
+      srow[w + i] = c;
+    }
+  }
+  __syncthreads();
+  const int xq = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xq >= wq) return;
   float o[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int X = min((int)xq * 4 + j, W - 1);
+    const int X = min(xq * 4 + j, W - 1);
     const float sx = rx * (float)X;
     const int x0 = min((int)sx, w - 1);
     const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
     const float lx = sx - (float)x0, hx = 1.0f - lx;
-    const float v = hy * (hx * __ldg(row0 + x0) + lx * __ldg(row0 + x1)) + ly * (hx * __ldg(row1 + x0) + lx * __ldg(row1 + x1));
+    float v;
+    if (FAST) v = hx * srow[x0] + lx * srow[x1];
+    else v = hy * (hx * srow[x0] + lx * srow[x1]) + ly * (hx * srow[w + x0] + lx * srow[w + x1]);
     o[j] = sigmoid_f<FAST>(v);
   }
-  float* dst = heat + (size_t)row * W + xq * 4;
+  float* dst = heat + ((size_t)map * H + Y) * W + xq * 4;
   if ((W & 3) == 0) {
     __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if ((int)xq * 4 + j < W) dst[j] = o[j];
+      if (xq * 4 + j < W) dst[j] = o[j];
   }
 }
 
 template <typename FeatT>
 static void launch_logits(const void* feat, const float* w_fc, const float* b_fc, float* logits, int pixels, int hw, int K, int C,
                           cudaStream_t s) {
-  int blocks = ceil_div(pixels, (kHeadThreads / 32) * 2);
+  int blocks = ceil_div(pixels, (kHeadThreads / 32) * 4);
   const int cap = sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
@@ -185,8 +209,6 @@ extern "C" int hk_head_fwd(const void* feat, int feat_dtype, const float* w_fc, 
                  (reinterpret_cast<uintptr_t>(w_fc) & 15) == 0,
              "hk_head_fwd: feat/heat/w_fc must be 16-byte aligned");
   HK_REQUIRE((long long)B * h * w < 0x7fffffffLL, "hk_head_fwd: too many low-res pixels");
-  const long long total_ll = (long long)B * K * H * ((W + 3) / 4);
-  HK_REQUIRE(total_ll < 0xffffffffLL, "hk_head_fwd: heatmap too large for 32-bit indexing");
   cudaStream_t s = as_stream(stream);
   const int pixels = B * h * w;
   if (feat_dtype == HK_BF16) launch_logits<__nv_bfloat16>(feat, w_fc, b_fc, logits_ws, pixels, h * w, K, C, s);
@@ -196,13 +218,15 @@ extern "C" int hk_head_fwd(const void* feat, int feat_dtype, const float* w_fc, 
   // ATen area_pixel_compute_scale(align_corners=True): (in - 1) / (out - 1) in float, 0 when out == 1
   const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  const unsigned total = (unsigned)total_ll;
-  const unsigned wq = (unsigned)((W + 3) / 4);
-  const unsigned ublocks = (total + 255u) / 256u;
-  // bf16 features = throughput mode: ex2/rcp-approx sigmoid (<= 2 ulp); fp32 features = correctness mode: expf + IEEE divide
+  const int wq = (W + 3) / 4;
+  HK_REQUIRE(H <= 65535 && B * K <= 65535 && w <= 4096, "hk_head_fwd: H, B*K or w exceed the launch grid limits");
+  int threads = ((wq + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  dim3 grid(ceil_div(wq, threads), H, B * K);
+  // bf16 features = throughput mode: separable lerp + ex2/rcp-approx sigmoid; fp32 features = correctness mode
   if (feat_dtype == HK_BF16)
-    head_upsample_sigmoid_kernel<true><<<ublocks, 256, 0, s>>>(logits_ws, heat, total, h, w, H, W, wq, ry, rx);
+    head_upsample_sigmoid_kernel<true><<<grid, threads, (size_t)w * sizeof(float), s>>>(logits_ws, heat, h, w, H, W, wq, ry, rx);
   else
-    head_upsample_sigmoid_kernel<false><<<ublocks, 256, 0, s>>>(logits_ws, heat, total, h, w, H, W, wq, ry, rx);
+    head_upsample_sigmoid_kernel<false><<<grid, threads, (size_t)2 * w * sizeof(float), s>>>(logits_ws, heat, h, w, H, W, wq, ry, rx);
   return check_launch("head_upsample_sigmoid_kernel");
 }

@@ -39,7 +39,12 @@ struct StemTcArgs {
   __nv_bfloat16* y;  // (B,Ho,Wo,64) bf16
   int B, H, W, Ho, Wo;
   int tiles_x, tiles_per_img, num_tiles;
+  long long* dbg;  // optional phase timeline of CTA 0 (tools/diag_stem_timeline.py); null in production
 };
+#define ST_STAMP(slot)                                                                            \
+  do {                                                                                            \
+    if (a.dbg && blockIdx.x == 0 && tid == 0 && dbg_tile < 24) a.dbg[dbg_tile * 8 + (slot)] = clock64(); \
+  } while (0)
 
 // byte offset of (row, 16-byte chunk) inside one 128-row x 128-byte K block, SWIZZLE_128B
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
@@ -90,30 +95,36 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemTcArgs a) {
 
   // Software pipeline: the NEXT tile's input patch is fetched into registers (PATCH_PER_THREAD independent global
   // loads in flight per thread) while the current tile is built, multiplied and stored.
-  constexpr int PATCH_N = 3 * ST_PATCH_H * ST_PATCH_W;
-  constexpr int PATCH_PER_THREAD = (PATCH_N + ST_THREADS - 1) / ST_THREADS;
-  float pre[PATCH_PER_THREAD];
+  // Work split: the patch is 3*21 = 63 (channel, row) segments of 38 floats; warp w owns segments w, w+8, ...
+  // (warp-uniform row arithmetic, no per-element div/mod), lane l loads columns l and l+32 (the latter for l < 6).
+  constexpr int PATCH_ROWS = 3 * ST_PATCH_H;                       // 63
+  constexpr int ROWS_PER_WARP = (PATCH_ROWS + 7) / 8;              // 8
+  float pre[ROWS_PER_WARP][2];
   auto prefetch_patch = [&](int t) {
     const int pb = t / a.tiles_per_img;
     const int prem = t - pb * a.tiles_per_img;
     const int pty = prem / a.tiles_x, ptx_ = prem - pty * a.tiles_x;
     const int piy0 = 2 * pty * ST_TILE_H - 3, pix0 = 2 * ptx_ * ST_TILE_W - 3;
     const float* xb = a.x + (size_t)pb * 3 * a.H * a.W;
+    const int ix_a = pix0 + lane, ix_b = pix0 + lane + 32;
+    const bool ok_a = ix_a >= 0 && ix_a < a.W;
+    const bool ok_b = lane < ST_PATCH_W - 32 && ix_b >= 0 && ix_b < a.W;
 #pragma unroll
-    for (int j = 0; j < PATCH_PER_THREAD; ++j) {
-      const int i = tid + j * ST_THREADS;
-      const int px = i % ST_PATCH_W;
-      const int r2 = i / ST_PATCH_W;
-      const int py = r2 % ST_PATCH_H, c = r2 / ST_PATCH_H;
-      const int iy = piy0 + py, ix = pix0 + px;
-      float v = 0.f;
-      if (i < PATCH_N && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) v = __ldg(xb + ((size_t)c * a.H + iy) * a.W + ix);
-      pre[j] = v;
+    for (int j = 0; j < ROWS_PER_WARP; ++j) {
+      const int seg = warp + 8 * j;                                // warp-uniform
+      const int c = seg / ST_PATCH_H, py = seg - c * ST_PATCH_H;
+      const int iy = piy0 + py;
+      const bool ok_row = seg < PATCH_ROWS && iy >= 0 && iy < a.H;
+      const float* rowp = xb + ((size_t)c * a.H + (ok_row ? iy : 0)) * a.W;
+      pre[j][0] = (ok_row && ok_a) ? __ldg(rowp + ix_a) : 0.f;
+      pre[j][1] = (ok_row && ok_b) ? __ldg(rowp + ix_b) : 0.f;
     }
   };
   if ((int)blockIdx.x < a.num_tiles) prefetch_patch(blockIdx.x);
 
-  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+  int dbg_tile = 0;
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++dbg_tile) {
+    ST_STAMP(0);
     const int b = tile / a.tiles_per_img;
     const int rem = tile - b * a.tiles_per_img;
     const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
@@ -121,17 +132,18 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemTcArgs a) {
 
     // ---- 1. prefetched input patch -> smem, bf16, [y][x][c] ----
 #pragma unroll
-    for (int j = 0; j < PATCH_PER_THREAD; ++j) {
-      const int i = tid + j * ST_THREADS;
-      if (i < PATCH_N) {
-        const int px = i % ST_PATCH_W;
-        const int r2 = i / ST_PATCH_W;
-        const int py = r2 % ST_PATCH_H, c = r2 / ST_PATCH_H;
-        patch[(py * ST_PATCH_W + px) * 3 + c] = __float2bfloat16_rn(pre[j]);
+    for (int j = 0; j < ROWS_PER_WARP; ++j) {
+      const int seg = warp + 8 * j;
+      if (seg < PATCH_ROWS) {
+        const int c = seg / ST_PATCH_H, py = seg - c * ST_PATCH_H;
+        __nv_bfloat16* dstp = patch + (py * ST_PATCH_W) * 3 + c;
+        dstp[lane * 3] = __float2bfloat16_rn(pre[j][0]);
+        if (lane < ST_PATCH_W - 32) dstp[(lane + 32) * 3] = __float2bfloat16_rn(pre[j][1]);
       }
     }
+    ST_STAMP(1);
     __syncthreads();  // patch complete; also: previous tile's epilogue has drained TMEM (all warps passed it)
-    if (tile + (int)gridDim.x < a.num_tiles) prefetch_patch(tile + gridDim.x);
+    ST_STAMP(2);
 
     // ---- 2. im2col rows into the swizzled A tile ----
     // 128 pixels x 7 filter rows = 896 segments of 24 bf16 (48 B = 3 chunks); k0 = r*24 -> chunk index r*3 overall
@@ -149,9 +161,11 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemTcArgs a) {
         *reinterpret_cast<uint4*>(dst) = make_uint4(v[4 * cidx], v[4 * cidx + 1], v[4 * cidx + 2], v[4 * cidx + 3]);
       }
     }
+    ST_STAMP(3);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to tcgen05
     ptx::tc_fence_before();
     __syncthreads();
+    ST_STAMP(4);
 
     // ---- 3. MMA ----
     if (tid == 0) {
@@ -168,41 +182,44 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemTcArgs a) {
       ptx::umma_commit(mma_bar);
     }
     first = false;
+    // next tile's input patch -> registers while the tensor core works on this one
+    if (tile + (int)gridDim.x < a.num_tiles) prefetch_patch(tile + gridDim.x);
+    ST_STAMP(5);
 
-    // ---- 4. epilogue (warps 0-3); every thread waits so the A tile / patch can be reused afterwards ----
+    // ---- 4. epilogue (all 8 warps: warp%4 = TMEM lane quarter, warp/4 = channel half) ----
     ptx::mbar_wait(mma_bar, mma_phase, 12);
     mma_phase ^= 1;
     ptx::tc_fence_after();
-    if (warp < 4) {
-      const int row = warp * 32 + lane;
+    ST_STAMP(6);
+    {
+      const int q = warp & 3, c0 = (warp >> 2) * 32;
+      const int row = q * 32 + lane;
       const int oy = oy0 + (row >> 4), ox = ox0 + (row & 15);
       const bool valid = oy < a.Ho && ox < a.Wo;
       __nv_bfloat16* dst = a.y + (((size_t)b * a.Ho + oy) * a.Wo + ox) * ST_COUT;
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+      ptx::tmem_ld_wait();
+      if (valid) {
 #pragma unroll
-      for (int c0 = 0; c0 < ST_COUT; c0 += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
-        ptx::tmem_ld_wait();
-        if (valid) {
+        for (int g = 0; g < 4; ++g) {
+          const int c = c0 + g * 8;
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.scale + c));
+          const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.scale + c + 4));
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(a.bias + c));
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(a.bias + c + 4));
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+          float v[8];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int c = c0 + g * 8;
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.scale + c));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.scale + c + 4));
-            const float4 t0 = __ldg(reinterpret_cast<const float4*>(a.bias + c));
-            const float4 t1 = __ldg(reinterpret_cast<const float4*>(a.bias + c + 4));
-            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(__uint_as_float(r[g * 8 + j]), sc[j], bi[j]), 0.f);
-            *reinterpret_cast<uint4*>(dst + c) =
-                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          }
+          for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(__uint_as_float(r[g * 8 + j]), sc[j], bi[j]), 0.f);
+          *reinterpret_cast<uint4*>(dst + c) =
+              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
       }
       ptx::tc_fence_before();
     }
+    ST_STAMP(7);
   }
 
   ptx::tc_fence_before();
@@ -245,6 +262,10 @@ int hk_stem_pack_weights(const float* w_oihw, void* w_out, void* stream) {
   return check_launch("stem_pack_kernel");
 }
 
+static long long* g_stem_dbg = nullptr;
+// Undocumented diagnostic hook (not in the public header): device buffer of 24*8 int64 receiving CTA 0's phase clocks.
+__attribute__((visibility("default"))) void hk_debug_set_stem_timeline(long long* dev_buf) { g_stem_dbg = dev_buf; }
+
 int hk_stem_fwd(const float* x_nchw, const void* w_packed, const float* scale, const float* bias, void* y_nhwc, int B, int H,
                 int W, void* stream) {
   using namespace hk;
@@ -268,6 +289,7 @@ int hk_stem_fwd(const float* x_nchw, const void* w_packed, const float* scale, c
   StemTcArgs a;
   a.x = x_nchw; a.scale = scale; a.bias = bias; a.y = static_cast<__nv_bfloat16*>(y_nhwc);
   a.B = B; a.H = H; a.W = W;
+  a.dbg = g_stem_dbg;
   a.Ho = (H + 6 - 7) / 2 + 1;
   a.Wo = (W + 6 - 7) / 2 + 1;
   a.tiles_x = ceil_div(a.Wo, ST_TILE_W);

@@ -311,3 +311,18 @@ def test_stem_tcgen05_vs_oracle(shape):
     err = (got - ref).abs()
     tol = 2.0 ** -8 * ref.abs() + 1e-3 * max(1.0, ref.abs().max().item())
     assert (err > tol).sum().item() == 0, f"max err {err.max().item():.4g}"
+
+
+C64_CASES = [
+    # B, H, W, dil, residual, relu   (3x3, 64 -> 64, stride 1: the layer1 specialisation)
+    (1, 8, 16, 1, False, False),      # exactly one tile
+    (2, 120, 160, 1, True, True),     # layer1 shape: 300 tiles > 148 SMs
+    (3, 20, 28, 1, True, True),       # ragged tiles in both directions
+    (1, 24, 32, 2, False, True),      # dilation 2 (taller halo box)
+]
+
+
+@pytest.mark.parametrize("case", C64_CASES)
+def test_conv_tcgen05_c64_specialisation(case):
+    B, H, W, dil, residual, relu = case
+    test_conv_tcgen05_vs_oracle((B, H, W, 64, 64, 3, 1, dil, residual, relu))

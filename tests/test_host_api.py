@@ -150,3 +150,23 @@ def test_ops_refuse_cpu_tensors():
         ops.argmax_decode(torch.zeros(1, 1, 4, 4))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.gauss_targets(torch.zeros(1, 1, 2), 4, 4, 1.0)
+
+
+def test_dropin_shims_reexport_the_package(monkeypatch):
+    """`from src.model import KeypointsGauss` etc. (train.py:11-12, analysis.py:8-10) resolve to our classes when the
+    dropin/ directory stands in for the reference's src/ (INTEGRATION.md §1)."""
+    import importlib
+    import sys
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "dropin"))
+    for name in [n for n in sys.modules if n == "src" or n.startswith("src.") or n == "config"]:
+        monkeypatch.delitem(sys.modules, name)
+    model = importlib.import_module("src.model")
+    dataset = importlib.import_module("src.dataset")
+    prediction = importlib.import_module("src.prediction")
+    config = importlib.import_module("config")
+    assert model.KeypointsGauss is hk.KeypointsGauss
+    assert dataset.KeypointsDataset is hk.KeypointsDataset and dataset.transform is hk.transform
+    assert dataset.gauss_2d_batch is hk.gauss_2d_batch and prediction.Prediction is hk.Prediction
+    assert (config.NUM_KEYPOINTS, config.IMG_HEIGHT, config.IMG_WIDTH, config.GAUSS_SIGMA) == (4, 480, 640, 8)
+    m = model.KeypointsGauss(config.NUM_KEYPOINTS, img_height=config.IMG_HEIGHT, img_width=config.IMG_WIDTH)
+    assert len(m.state_dict()) == 218
