@@ -200,3 +200,39 @@ def test_high_resolution_more_keypoints():
     h32 = m32.cuda().eval()(x)
     print("hi-res bf16 vs fp32: mean", (heat - h32).abs().mean().item(), "max", (heat - h32).abs().max().item())
     assert (heat - h32).abs().mean().item() < 2e-2
+
+
+# ------------------------------------------------------------------ training step (BASELINE config 4)
+def test_train_step_matches_reference_formulation():
+    """Our step (K-row head, fused sigmoid+BCE with on-the-fly Gaussian targets) against the reference's as-written
+    formulation (1000-channel fc + upsample + slice, sigmoid, .double(), nn.BCELoss on fp64 gauss_2d_batch targets;
+    train.py:18-26, model.py:19-22, resnet_dilated.py:24-28) on the same weights and batch: loss and gradients agree,
+    dead fc rows get exactly zero gradient."""
+    import torch.nn.functional as F
+    torch.manual_seed(1)
+    m = hk.KeypointsGauss(4).cuda().train()
+    ref = hk.KeypointsGauss(4).cuda().train()
+    ref.load_state_dict(m.state_dict())
+    gen = torch.Generator().manual_seed(9)
+    img, uv = synth_batch(gen, 2, 64, 96)
+    img, uv = img.cuda(), uv.cuda()
+    loss = train_ops.sigmoid_bce_loss(m.forward_logits(img), uv=uv, sigma=8.0)
+    loss.backward()
+    net = ref.resnet.resnet34_8s
+    full = net.fc(net.features(img))                                            # all 1000 channels
+    up = F.interpolate(full, size=img.shape[2:], mode="bilinear", align_corners=True)
+    pred = torch.sigmoid(up[:, :4])
+    gt = torch.stack([hk.gauss_2d_batch(96, 64, 8, uv[b, :, 0], uv[b, :, 1]) for b in range(2)])
+    loss_ref = torch.nn.BCELoss()(pred.double(), gt)
+    loss_ref.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-6 * abs(loss_ref.item())
+    gm = dict(m.named_parameters())
+    worst = 1.0
+    for name, p in ref.named_parameters():
+        a, b = gm[name].grad.flatten().double(), p.grad.flatten().double()
+        if b.norm() == 0:
+            assert a.norm() == 0
+            continue
+        worst = min(worst, float(torch.dot(a, b) / (a.norm() * b.norm())))
+    assert worst > 0.999, worst
+    assert gm["resnet.resnet34_8s.fc.weight"].grad[4:].abs().sum().item() == 0.0
