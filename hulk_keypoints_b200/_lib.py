@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libhulk_sm100.so")
 
 # enums of include/hulk_sm100.h
 HK_F32, HK_BF16, HK_F64 = 0, 1, 2
-HK_CONV_TCGEN05, HK_CONV_FFMA = 0, 1
+HK_CONV_TCGEN05, HK_CONV_FFMA, HK_CONV_TCGEN05_1CTA = 0, 1, 2
 ABI_VERSION = 1
 
 EXPORTS = (

@@ -275,6 +275,9 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const ConvTcA
   return check_launch("conv_tc_kernel");
 }
 
+bool conv_tc2_applicable(const HkConvDesc& d);
+int conv_tc2_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
+                    const void* residual, void* y, cudaStream_t s);
 bool conv_tc_c64_applicable(const HkConvDesc& d);
 int conv_tc_c64_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
                        const void* residual, void* y, cudaStream_t s);
@@ -292,7 +295,10 @@ int conv_tc_launch(const HkConvDesc& d, const void* x, const void* w, const floa
   if (!encode) return fail(HK_ERR_CUDA, "conv(tcgen05): cuTensorMapEncodeTiled entry point not available");
 
   // layer1 shape (3x3, 64 -> 64, stride 1): resident weights + haloed boxes, 3.6x less L2->SM traffic
-  if (conv_tc_c64_applicable(d)) return conv_tc_c64_launch(d, x, w, scale, bias, residual, y, s);
+  const bool specialised = d.algo != HK_CONV_TCGEN05_1CTA;
+  if (specialised && conv_tc_c64_applicable(d)) return conv_tc_c64_launch(d, x, w, scale, bias, residual, y, s);
+  // Cout >= 128: CTA-pair kernel (cta_group::2, M=256), half the weight tile per SM
+  if (specialised && conv_tc2_applicable(d)) return conv_tc2_launch(d, x, w, scale, bias, residual, y, s);
 
   const int block_n = d.out_c % 256 == 0 ? 256 : (d.out_c % 128 == 0 ? 128 : 64);
   const int ktot = d.kh * d.kw * d.in_c;
@@ -357,7 +363,7 @@ extern "C" int hk_conv_bn_act_fwd(const HkConvDesc* desc, const void* x, const v
   HK_REQUIRE(d.in_h + 2 * d.pad >= eh && d.in_w + 2 * d.pad >= ew, "hk_conv_bn_act_fwd: kernel larger than padded input");
   HK_REQUIRE(d.out_h == (d.in_h + 2 * d.pad - eh) / d.stride + 1 && d.out_w == (d.in_w + 2 * d.pad - ew) / d.stride + 1,
              "hk_conv_bn_act_fwd: out_h/out_w (%d,%d) inconsistent with the descriptor", d.out_h, d.out_w);
-  if (d.algo == HK_CONV_TCGEN05) return conv_tc_launch(d, x, w_packed, scale, bias, residual_or_null, y, as_stream(stream));
+  if (d.algo == HK_CONV_TCGEN05 || d.algo == HK_CONV_TCGEN05_1CTA) return conv_tc_launch(d, x, w_packed, scale, bias, residual_or_null, y, as_stream(stream));
   if (d.algo == HK_CONV_FFMA) return conv_ffma_launch(d, x, w_packed, scale, bias, residual_or_null, y, as_stream(stream));
   return fail(HK_ERR_BAD_ARG, "hk_conv_bn_act_fwd: unknown algo %d", d.algo);
 }

@@ -1,0 +1,364 @@
+// 2-CTA (cta_group::2) tcgen05 implicit-GEMM convolution: the CTA PAIR of one TPC computes a 256-pixel x BLOCK_N tile.
+//
+// Same math and data path as conv_tc_kernel (TMA tap-shifted boxes of the NHWC activation as A, K-major weights
+// as B, TMEM accumulators, fused scale/bias/residual/ReLU epilogue), but one tcgen05.mma.cta_group::2 (M=256) is
+// issued by the leader CTA for both SMs: each CTA stages its own 128 rows of A and only HALF of the weight tile
+// (BLOCK_N/2 rows); the tensor cores exchange the B halves over the pair's private path.  Per CTA that cuts the
+// shared-memory operand reads from (4 KB + 32*N B) to (4 KB + 16*N B) per K=16 step and halves the L2->SM weight
+// traffic -- the two things that bound the 1-CTA kernel (SS-mode MMA at N=256 needs ~96 B/clk of smem reads; measured
+// sustain is ~85 B/clk, i.e. 88 % tensor-pipe activity; N=128 needs 128 B/clk).
+//
+// Protocol (per stage s, accumulator buffer a):
+//   full[s]       lives in the LEADER's smem, 2 arrivals (both producers) + 2x STAGE_BYTES of TMA transaction bytes;
+//                 both CTAs issue cp.async.bulk.tensor...cta_group::2 whose completion is routed to the leader's barrier
+//   empty[s]      one per CTA; tcgen05.commit.cta_group::2...multicast::cluster arrives on both when the MMAs retire
+//   tmem_full[a]  one per CTA (multicast commit); each CTA's epilogue drains its own 128 TMEM lanes
+//   tmem_empty[a] in the leader, 2 x 128 arrivals (the peer's epilogue threads arrive remotely via mapa)
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "hk_common.cuh"
+#include "hk_ptx.cuh"
+
+namespace hk {
+
+constexpr int T2_BOX_H = 4, T2_BOX_W = 16;
+constexpr int T2_BOX_BYTES = 64 * 128;   // 8 KB: 64 pixels x 64 ch bf16
+constexpr int T2_A_BYTES = 2 * T2_BOX_BYTES;  // 128 rows per CTA
+constexpr int T2_THREADS = 256;
+
+struct ConvTc2Args {
+  const float* scale;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* y;
+  int B, Ho, Wo, Cout;
+  int Cin, kh, kw, stride, pad, dil, relu;
+  int tiles_x, tiles_per_img, num_boxes;
+  int num_m_tiles, num_n_tiles, cblocks;  // m tiles of 256 pixels (4 boxes)
+};
+
+template <int BLOCK_N>
+struct Tc2Cfg {
+  static constexpr int HALF_N = BLOCK_N / 2;
+  static constexpr int B_BYTES = HALF_N * 128;
+  static constexpr int STAGE_BYTES = T2_A_BYTES + B_BYTES;
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+namespace ptx {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared-window address: -> the pair leader's copy
+__device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* leader_bar, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this smem offset in BOTH CTAs of the pair once the issued MMAs have retired
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+}  // namespace ptx
+
+__device__ __forceinline__ void t2_decode_box(const ConvTc2Args& a, int box, int& b, int& y0, int& x0) {
+  if (box < a.num_boxes) {
+    b = box / a.tiles_per_img;
+    const int r = box - b * a.tiles_per_img;
+    const int ty = r / a.tiles_x;
+    y0 = ty * T2_BOX_H;
+    x0 = (r - ty * a.tiles_x) * T2_BOX_W;
+  } else {
+    b = a.B;  // out of range in the batch dimension: TMA zero fill, stores masked
+    y0 = 0;
+    x0 = 0;
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvTc2Args a) {
+  using Cfg = Tc2Cfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int total_tiles = a.num_m_tiles * a.num_n_tiles;
+  const int num_kb = a.kh * a.kw * a.cblocks;
+
+  ptx::cluster_sync_all();
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_x);
+    ptx::prefetch_tensormap(&map_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      ptx::mbar_init(&full_bar[i], 2);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full_bar[i], 1);
+      ptx::mbar_init(&tmem_empty_bar[i], 256);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc2(tmem_ptr_smem, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish2();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      uint32_t stage = 0, phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int m_tile = tile / a.num_n_tiles, n_tile = tile - m_tile * a.num_n_tiles;
+        int b0, y0, x0, b1, y1, x1;
+        t2_decode_box(a, 4 * m_tile + 2 * (int)rank, b0, y0, x0);
+        t2_decode_box(a, 4 * m_tile + 2 * (int)rank + 1, b1, y1, x1);
+        const int n_row0 = n_tile * BLOCK_N + (int)rank * Cfg::HALF_N;
+        for (int r = 0; r < a.kh; ++r) {
+          for (int s = 0; s < a.kw; ++s) {
+            const int dy = r * a.dil - a.pad, dx = s * a.dil - a.pad;
+            const int kbase = (r * a.kw + s) * a.Cin;
+            for (int cb = 0; cb < a.cblocks; ++cb) {
+              ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 31);
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              ptx::tma2_load_4d(sa, &map_x, &full_bar[stage], cb * 64, x0 * a.stride + dx, y0 * a.stride + dy, b0);
+              ptx::tma2_load_4d(sa + T2_BOX_BYTES, &map_x, &full_bar[stage], cb * 64, x1 * a.stride + dx, y1 * a.stride + dy, b1);
+              ptx::tma2_load_2d(sa + T2_A_BYTES, &map_w, &full_bar[stage], kbase + cb * 64, n_row0);
+              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              else ptx::mbar_arrive_remote(&full_bar[stage], 0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(256, BLOCK_N);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 32);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase, 33);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
+          const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + T2_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma2_commit_mc(&empty_bar[stage]);
+          if (kb == num_kb - 1) ptx::umma2_commit_mc(&tmem_full_bar[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      // all remote arrivals of the last two accumulator uses must land before this CTA's barriers go away
+      if (it >= 1) { const uint32_t j = it - 1; ptx::mbar_wait(&tmem_empty_bar[j & 1], (j >> 1) & 1, 34); }
+      if (it >= 2) { const uint32_t j = it - 2; ptx::mbar_wait(&tmem_empty_bar[j & 1], (j >> 1) & 1, 35); }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 TMEM lanes) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int py = (row & 63) >> 4, px = row & 15;
+    uint32_t it = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const int m_tile = tile / a.num_n_tiles, n_tile = tile - m_tile * a.num_n_tiles;
+      int b, y0, x0;
+      t2_decode_box(a, 4 * m_tile + 2 * (int)rank + (row >> 6), b, y0, x0);
+      const int oy = y0 + py, ox = x0 + px;
+      const bool valid = (b < a.B) && (oy < a.Ho) && (ox < a.Wo);
+      const size_t off = valid ? (((size_t)b * a.Ho + oy) * a.Wo + ox) * a.Cout + (size_t)n_tile * BLOCK_N : 0;
+      const float* scale = a.scale + n_tile * BLOCK_N;
+      const float* bias = a.bias + n_tile * BLOCK_N;
+
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 36);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(taddr + c0, r);
+        ptx::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c = c0 + g * 8;
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+            const float4 t1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[g * 8 + j]), sc[j], bi[j]);
+            if (a.residual) {
+              const uint4 rq = __ldg(reinterpret_cast<const uint4*>(a.residual + off + c));
+              float lo, hi;
+              unpack_bf16x2(rq.x, lo, hi); v[0] += lo; v[1] += hi;
+              unpack_bf16x2(rq.y, lo, hi); v[2] += lo; v[3] += hi;
+              unpack_bf16x2(rq.z, lo, hi); v[4] += lo; v[5] += hi;
+              unpack_bf16x2(rq.w, lo, hi); v[6] += lo; v[7] += hi;
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            *reinterpret_cast<uint4*>(a.y + off + c) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive_remote(&tmem_empty_bar[acc], 0);  // leader's barrier counts both CTAs' epilogue threads
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();
+
+bool conv_tc2_applicable(const HkConvDesc& d) {
+  static const bool disabled = getenv("HK_DISABLE_2CTA") != nullptr;
+  return !disabled && d.out_c % 128 == 0 && d.in_c % 64 == 0 && (d.stride == 1 || d.stride == 2);
+}
+
+template <int BLOCK_N>
+static int launch_tc2(const CUtensorMap& mx, const CUtensorMap& mw, const ConvTc2Args& a, cudaStream_t s) {
+  using Cfg = Tc2Cfg<BLOCK_N>;
+  static int attr_dev_mask = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_dev_mask & (1 << dev))) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): smem attribute (%d B): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+    attr_dev_mask |= (1 << dev);
+  }
+  const int total = a.num_m_tiles * a.num_n_tiles;
+  int clusters = sm_count() / 2;
+  if (clusters > total) clusters = total;
+  conv_tc2_kernel<BLOCK_N><<<2 * clusters, T2_THREADS, Cfg::SMEM_BYTES, s>>>(mx, mw, a);
+  return check_launch("conv_tc2_kernel");
+}
+
+int conv_tc2_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
+                    const void* residual, void* y, cudaStream_t s) {
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled entry point not available");
+  const int block_n = d.out_c % 256 == 0 ? 256 : 128;
+  const int ktot = d.kh * d.kw * d.in_c;
+  CUtensorMap mx, mw;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)d.in_c, (cuuint64_t)d.in_w, (cuuint64_t)d.in_h, (cuuint64_t)d.batch};
+    const cuuint64_t strides[3] = {(cuuint64_t)d.in_c * 2, (cuuint64_t)d.in_w * d.in_c * 2, (cuuint64_t)d.in_h * d.in_w * d.in_c * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)(T2_BOX_W * d.stride), (cuuint32_t)(T2_BOX_H * d.stride), 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
+    CUresult r = encode(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d.out_c};
+    const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)(block_n / 2)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  }
+  ConvTc2Args a;
+  a.scale = scale; a.bias = bias;
+  a.residual = static_cast<const __nv_bfloat16*>(residual);
+  a.y = static_cast<__nv_bfloat16*>(y);
+  a.B = d.batch; a.Ho = d.out_h; a.Wo = d.out_w; a.Cout = d.out_c;
+  a.Cin = d.in_c; a.kh = d.kh; a.kw = d.kw; a.stride = d.stride; a.pad = d.pad; a.dil = d.dil; a.relu = d.relu;
+  a.tiles_x = ceil_div(d.out_w, T2_BOX_W);
+  a.tiles_per_img = a.tiles_x * ceil_div(d.out_h, T2_BOX_H);
+  const long long boxes = (long long)a.tiles_per_img * d.batch;
+  HK_REQUIRE(boxes < 0x3fffffffLL, "conv(tcgen05,2cta): too many tiles");
+  a.num_boxes = (int)boxes;
+  a.num_m_tiles = (a.num_boxes + 3) / 4;
+  a.num_n_tiles = d.out_c / block_n;
+  a.cblocks = d.in_c / 64;
+  return block_n == 256 ? launch_tc2<256>(mx, mw, a, s) : launch_tc2<128>(mx, mw, a, s);
+}
+
+}  // namespace hk

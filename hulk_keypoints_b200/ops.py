@@ -59,7 +59,7 @@ def conv_bn_act(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, bi
         raise ValueError(f"weight cin {cin_w} != input channels {Cin}")
     Ho, Wo = conv_out_hw(H, W, kh, stride, pad, dil)
     if out is None:
-        out = torch.empty((B, Ho, Wo, cout), device=x.device, dtype=out_dtype or (torch.bfloat16 if algo == HK_CONV_TCGEN05 else x.dtype))
+        out = torch.empty((B, Ho, Wo, cout), device=x.device, dtype=out_dtype or (x.dtype if algo == HK_CONV_FFMA else torch.bfloat16))
     elif tuple(out.shape) != (B, Ho, Wo, cout):
         raise ValueError(f"out shape {tuple(out.shape)} != {(B, Ho, Wo, cout)}")
     if residual is not None and (tuple(residual.shape) != tuple(out.shape) or residual.dtype != out.dtype):

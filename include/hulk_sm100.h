@@ -49,7 +49,9 @@ typedef enum HkDType { HK_F32 = 0, HK_BF16 = 1, HK_F64 = 2 } HkDType;
 /* Which kernel family executes a convolution. */
 typedef enum HkConvAlgo {
   HK_CONV_TCGEN05 = 0, /* bf16 operands, fp32 accumulate in TMEM, TMA-fed implicit GEMM            */
-  HK_CONV_FFMA = 1     /* fp32 CUDA-core implicit GEMM: the fp32 correctness mode */
+  HK_CONV_FFMA = 1,    /* fp32 CUDA-core implicit GEMM: the fp32 correctness mode */
+  HK_CONV_TCGEN05_1CTA = 2 /* force the generic single-CTA tcgen05 kernel (no cta_group::2 / layer1 specialisation);
+                              same results, kept for shapes the specialised kernels do not cover and for A/B runs */
 } HkConvAlgo;
 
 /*

@@ -276,7 +276,13 @@ TC_CASES = [
 
 
 @pytest.mark.parametrize("case", TC_CASES)
-def test_conv_tcgen05_vs_oracle(case):
+def test_conv_tcgen05_single_cta_kernel(case):
+    """The generic 1-CTA kernel on every shape (the default route sends Cout>=128 to the CTA-pair kernel)."""
+    test_conv_tcgen05_vs_oracle(case, algo=_lib.HK_CONV_TCGEN05_1CTA)
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_vs_oracle(case, algo=_lib.HK_CONV_TCGEN05):
     B, H, W, cin, cout, k, stride, dil, residual, relu = case
     x, w, s, b, res, pad = _conv_case(*case, seed=21)
     xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
@@ -286,7 +292,7 @@ def test_conv_tcgen05_vs_oracle(case):
     wp, _, _ = ops.pack_conv_weights(w.to(dev()), None, 1e-5, torch.bfloat16)
     y = ops.conv_bn_act(xb.permute(0, 2, 3, 1).contiguous().to(dev()), wp, s.to(dev()), b.to(dev()), stride=stride, pad=pad,
                         dil=dil, relu=relu, residual=None if resb is None else resb.permute(0, 2, 3, 1).contiguous().to(dev()),
-                        algo=_lib.HK_CONV_TCGEN05)
+                        algo=algo)
     torch.cuda.synchronize()
     got = y.float().cpu().permute(0, 3, 1, 2).double()
     assert got.shape == ref.shape
