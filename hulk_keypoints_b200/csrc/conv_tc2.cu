@@ -14,6 +14,12 @@
 //   empty[s]      one per CTA; tcgen05.commit.cta_group::2...multicast::cluster arrives on both when the MMAs retire
 //   tmem_full[a]  one per CTA (multicast commit); each CTA's epilogue drains its own 128 TMEM lanes
 //   tmem_empty[a] in the leader, 2 x 128 arrivals (the peer's epilogue threads arrive remotely via mapa)
+//
+// Epilogue through shared memory and TMA (64-channel chunks, three 16 KB staging buffers per CTA): the residual chunk is
+// TMA-loaded into the swizzled staging buffer one chunk ahead, each thread fixes up its own row in place (conflict-free
+// with the 128-byte swizzle) and one elected thread issues the TMA stores.  The direct version (16-byte accesses at a
+// >= 256-byte lane stride) cost 32 L1 wavefronts per warp instruction and made the 1x1 downsample convs and the
+// N=128 layer epilogue-bound.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -43,9 +49,11 @@ struct Tc2Cfg {
   static constexpr int HALF_N = BLOCK_N / 2;
   static constexpr int B_BYTES = HALF_N * 128;
   static constexpr int STAGE_BYTES = T2_A_BYTES + B_BYTES;
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+  static constexpr int STAGING_BUFS = 3;               // chunk c uses buffer c % 3: its previous user is 3 chunks old
+  static constexpr int STAGING_BYTES = STAGING_BUFS * 128 * 128;  // 128-row x 64-channel bf16 chunk buffers
+  static constexpr int STAGES = (160 * 1024) / STAGE_BYTES > 8 ? 8 : (160 * 1024) / STAGE_BYTES;  // 5 (N=256) / 6 (N=128)
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
 };
 
 namespace ptx {
@@ -123,16 +131,19 @@ __device__ __forceinline__ void t2_decode_box(const ConvTc2Args& a, int box, int
 
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvTc2Args a) {
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res, const ConvTc2Args a) {
   using Cfg = Tc2Cfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;  // 3 x [128 rows][128 B], 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_bar = tmem_empty_bar + 2;  // [3]: residual chunk landed in staging buffer i
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -145,6 +156,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_x);
     ptx::prefetch_tensormap(&map_w);
+    ptx::prefetch_tensormap(&map_y);
+    if (a.residual) ptx::prefetch_tensormap(&map_res);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -155,6 +168,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       ptx::mbar_init(&tmem_full_bar[i], 1);
       ptx::mbar_init(&tmem_empty_bar[i], 256);
     }
+    for (int i = 0; i < 3; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -222,63 +236,96 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       if (it >= 2) { const uint32_t j = it - 2; ptx::mbar_wait(&tmem_empty_bar[j & 1], (j >> 1) & 1, 35); }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (both CTAs, own 128 TMEM lanes) =====================
+    // ===================== epilogue (both CTAs, own 128 TMEM lanes; 128 threads, named barrier 1) =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int py = (row & 63) >> 4, px = row & 15;
-    uint32_t it = 0;
+    const bool elected = (warp == 4 && lane == 0);
+    const int sw = row & 7;
+    constexpr int CHUNKS = BLOCK_N / 64;
+    const bool has_res = a.residual != nullptr;
+    uint32_t it = 0, chunk_ctr = 0;      // chunk_ctr selects the staging buffer and the res_bar phase
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int m_tile = tile / a.num_n_tiles, n_tile = tile - m_tile * a.num_n_tiles;
-      int b, y0, x0;
-      t2_decode_box(a, 4 * m_tile + 2 * (int)rank + (row >> 6), b, y0, x0);
-      const int oy = y0 + py, ox = x0 + px;
-      const bool valid = (b < a.B) && (oy < a.Ho) && (ox < a.Wo);
-      const size_t off = valid ? (((size_t)b * a.Ho + oy) * a.Wo + ox) * a.Cout + (size_t)n_tile * BLOCK_N : 0;
-      const float* scale = a.scale + n_tile * BLOCK_N;
-      const float* bias = a.bias + n_tile * BLOCK_N;
+      int b0, y0, x0, b1, y1, x1;          // this CTA's two 4x16 boxes (64 rows each)
+      t2_decode_box(a, 4 * m_tile + 2 * (int)rank, b0, y0, x0);
+      t2_decode_box(a, 4 * m_tile + 2 * (int)rank + 1, b1, y1, x1);
+      const int n0 = n_tile * BLOCK_N;
+      const float* scale = a.scale + n0;
+      const float* bias = a.bias + n0;
 
+      // elected thread only.  wait_group.read 1 = every TMA store but the newest has finished reading smem, so the buffers
+      // of chunks ctr-2 and older -- i.e. (ctr+1) % 3 and ctr % 3 -- are free.
+      auto issue_residual = [&](int chunk, uint32_t ctr) {
+        const uint32_t bsel = ctr % 3;
+        uint8_t* buf = staging + bsel * 16384;
+        ptx::mbar_arrive_expect_tx(&res_bar[bsel], 16384);
+        ptx::tma_load_4d(buf, &map_res, &res_bar[bsel], n0 + chunk * 64, x0, y0, b0);
+        ptx::tma_load_4d(buf + 8192, &map_res, &res_bar[bsel], n0 + chunk * 64, x1, y1, b1);
+      };
+      if (elected) {
+        ptx::bulk_wait_group_read1();
+        if (has_res) issue_residual(0, chunk_ctr);
+      }
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 36);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(taddr + c0, r);
+      for (int chunk = 0; chunk < CHUNKS; ++chunk, ++chunk_ctr) {
+        const uint32_t bsel = chunk_ctr % 3;
+        uint8_t* my_row = staging + bsel * 16384 + row * 128;
+        if (elected) {
+          ptx::bulk_wait_group_read1();
+          if (has_res && chunk + 1 < CHUNKS) issue_residual(chunk + 1, chunk_ctr + 1);  // one chunk ahead
+        }
+        ptx::named_bar_sync(1, 128);  // staging[bsel] is free for everybody (elected passed its wait_group)
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld_32x32(taddr + chunk * 64, r0);
+        ptx::tmem_ld_32x32(taddr + chunk * 64 + 32, r1);
         ptx::tmem_ld_wait();
-        if (valid) {
+        if (chunk == CHUNKS - 1) {  // accumulator fully drained: release it to the MMA warp
+          ptx::tc_fence_before();
+          ptx::mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+        }
+        if (has_res) ptx::mbar_wait(&res_bar[bsel], (chunk_ctr / 3) & 1, 37);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int c = c0 + g * 8;
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
-            const float4 t0 = __ldg(reinterpret_cast<const float4*>(bias + c));
-            const float4 t1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
-            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-            float v[8];
+        for (int g = 0; g < 8; ++g) {
+          const int c = chunk * 64 + g * 8;
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c));
+          const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+          float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[g * 8 + j]), sc[j], bi[j]);
-            if (a.residual) {
-              const uint4 rq = __ldg(reinterpret_cast<const uint4*>(a.residual + off + c));
-              float lo, hi;
-              unpack_bf16x2(rq.x, lo, hi); v[0] += lo; v[1] += hi;
-              unpack_bf16x2(rq.y, lo, hi); v[2] += lo; v[3] += hi;
-              unpack_bf16x2(rq.z, lo, hi); v[4] += lo; v[5] += hi;
-              unpack_bf16x2(rq.w, lo, hi); v[6] += lo; v[7] += hi;
-            }
-            if (a.relu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            *reinterpret_cast<uint4*>(a.y + off + c) =
-                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(g < 4 ? r0[g * 8 + j] : r1[(g - 4) * 8 + j]), sc[j], bi[j]);
+          uint4* slot = reinterpret_cast<uint4*>(my_row + (((g ^ sw) & 7) << 4));  // 128-byte swizzle, as TMA expects
+          if (has_res) {
+            const uint4 rr = *slot;
+            float lo, hi;
+            unpack_bf16x2(rr.x, lo, hi); v[0] += lo; v[1] += hi;
+            unpack_bf16x2(rr.y, lo, hi); v[2] += lo; v[3] += hi;
+            unpack_bf16x2(rr.z, lo, hi); v[4] += lo; v[5] += hi;
+            unpack_bf16x2(rr.w, lo, hi); v[6] += lo; v[7] += hi;
           }
+          if (a.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          *slot = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::named_bar_sync(1, 128);
+        if (elected) {
+          const uint8_t* buf = staging + bsel * 16384;
+          ptx::tma_store_4d(&map_y, buf, n0 + chunk * 64, x0, y0, b0);         // clipped outside the image / batch
+          ptx::tma_store_4d(&map_y, buf + 8192, n0 + chunk * 64, x1, y1, b1);
+          ptx::bulk_commit_group();
         }
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive_remote(&tmem_empty_bar[acc], 0);  // leader's barrier counts both CTAs' epilogue threads
     }
+    if (elected) ptx::bulk_wait_group0();
   }
 
   ptx::tc_fence_before();
@@ -300,7 +347,8 @@ bool conv_tc2_applicable(const HkConvDesc& d) {
 }
 
 template <int BLOCK_N>
-static int launch_tc2(const CUtensorMap& mx, const CUtensorMap& mw, const ConvTc2Args& a, cudaStream_t s) {
+static int launch_tc2(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& mres,
+                      const ConvTc2Args& a, cudaStream_t s) {
   using Cfg = Tc2Cfg<BLOCK_N>;
   static int attr_dev_mask = 0;
   int dev = 0;
@@ -313,7 +361,7 @@ static int launch_tc2(const CUtensorMap& mx, const CUtensorMap& mw, const ConvTc
   const int total = a.num_m_tiles * a.num_n_tiles;
   int clusters = sm_count() / 2;
   if (clusters > total) clusters = total;
-  conv_tc2_kernel<BLOCK_N><<<2 * clusters, T2_THREADS, Cfg::SMEM_BYTES, s>>>(mx, mw, a);
+  conv_tc2_kernel<BLOCK_N><<<2 * clusters, T2_THREADS, Cfg::SMEM_BYTES, s>>>(mx, mw, my, mres, a);
   return check_launch("conv_tc2_kernel");
 }
 
@@ -344,6 +392,23 @@ int conv_tc2_launch(const HkConvDesc& d, const void* x, const void* w, const flo
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
   }
+  CUtensorMap my, mres;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)d.out_c, (cuuint64_t)d.out_w, (cuuint64_t)d.out_h, (cuuint64_t)d.batch};
+    const cuuint64_t strides[3] = {(cuuint64_t)d.out_c * 2, (cuuint64_t)d.out_w * d.out_c * 2, (cuuint64_t)d.out_h * d.out_w * d.out_c * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)T2_BOX_W, (cuuint32_t)T2_BOX_H, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&my, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled(output) failed: %d", (int)r);
+    mres = my;
+    if (residual) {
+      r = encode(&mres, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(residual), dims, strides, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled(residual) failed: %d", (int)r);
+    }
+  }
   ConvTc2Args a;
   a.scale = scale; a.bias = bias;
   a.residual = static_cast<const __nv_bfloat16*>(residual);
@@ -358,7 +423,7 @@ int conv_tc2_launch(const HkConvDesc& d, const void* x, const void* w, const flo
   a.num_m_tiles = (a.num_boxes + 3) / 4;
   a.num_n_tiles = d.out_c / block_n;
   a.cblocks = d.in_c / 64;
-  return block_n == 256 ? launch_tc2<256>(mx, mw, a, s) : launch_tc2<128>(mx, mw, a, s);
+  return block_n == 256 ? launch_tc2<256>(mx, mw, my, mres, a, s) : launch_tc2<128>(mx, mw, my, mres, a, s);
 }
 
 }  // namespace hk
