@@ -30,7 +30,8 @@ constexpr int ST_THREADS = 256;
 constexpr int ST_A_BYTES = 128 * 128 * ST_KBLOCKS;      // 48 KB
 constexpr int ST_B_BYTES = ST_COUT * 128 * ST_KBLOCKS;  // 24 KB
 constexpr int ST_PATCH_ELEMS = ST_PATCH_H * ST_PATCH_W * 3 + 8;
-constexpr int ST_SMEM_BYTES = 1024 + ST_A_BYTES + ST_B_BYTES + ((ST_PATCH_ELEMS * 2 + 15) & ~15) + 64;
+constexpr int ST_OUT_BYTES = 128 * 128;                 // output tile staging: 128 px x 64 ch bf16, swizzled for the TMA store
+constexpr int ST_SMEM_BYTES = 1024 + ST_A_BYTES + ST_B_BYTES + ST_OUT_BYTES + ((ST_PATCH_ELEMS * 2 + 15) & ~15) + 64;
 
 struct StemTcArgs {
   const float* x;   // (B,3,H,W) fp32
@@ -50,12 +51,13 @@ struct StemTcArgs {
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
 
 __global__ void __launch_bounds__(ST_THREADS, 2)
-stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemTcArgs a) {
+stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y, const StemTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                                   // 3 K blocks x [128 rows][128 B]
   uint8_t* sB = smem + ST_A_BYTES;                      // 3 K blocks x [64 rows][128 B]
-  __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(sB + ST_B_BYTES);
+  uint8_t* sOut = sB + ST_B_BYTES;                      // [128 rows][128 B], 1024-aligned
+  __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(sOut + ST_OUT_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + ((ST_PATCH_ELEMS * 2 + 15) & ~15));
   uint64_t* w_bar = bars;       // weights landed
   uint64_t* mma_bar = bars + 1; // accumulator ready / A tile free
@@ -65,6 +67,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemTcArgs a) {
 
   if (tid == 0) {
     ptx::prefetch_tensormap(&map_w);
+    ptx::prefetch_tensormap(&map_y);
     ptx::mbar_init(w_bar, 1);
     ptx::mbar_init(mma_bar, 1);
     ptx::fence_mbar_init();
@@ -125,6 +128,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemTcArgs a) {
   int dbg_tile = 0;
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++dbg_tile) {
     ST_STAMP(0);
+    if (tid == 0) ptx::bulk_wait_group_read0();  // previous tile's TMA store has drained the staging buffer
     const int b = tile / a.tiles_per_img;
     const int rem = tile - b * a.tiles_per_img;
     const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
@@ -194,34 +198,38 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemTcArgs a) {
     {
       const int q = warp & 3, c0 = (warp >> 2) * 32;
       const int row = q * 32 + lane;
-      const int oy = oy0 + (row >> 4), ox = ox0 + (row & 15);
-      const bool valid = oy < a.Ho && ox < a.Wo;
-      __nv_bfloat16* dst = a.y + (((size_t)b * a.Ho + oy) * a.Wo + ox) * ST_COUT;
+      uint8_t* my_row = sOut + row * 128;
+      const int sw = row & 7;
       uint32_t r[32];
       ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
       ptx::tmem_ld_wait();
-      if (valid) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int c = c0 + g * 8;
-          const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.scale + c));
-          const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.scale + c + 4));
-          const float4 t0 = __ldg(reinterpret_cast<const float4*>(a.bias + c));
-          const float4 t1 = __ldg(reinterpret_cast<const float4*>(a.bias + c + 4));
-          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-          float v[8];
+      for (int g = 0; g < 4; ++g) {
+        const int c = c0 + g * 8;
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.scale + c));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.scale + c + 4));
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(a.bias + c));
+        const float4 t1 = __ldg(reinterpret_cast<const float4*>(a.bias + c + 4));
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+        float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(__uint_as_float(r[g * 8 + j]), sc[j], bi[j]), 0.f);
-          *reinterpret_cast<uint4*>(dst + c) =
-              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        }
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(__uint_as_float(r[g * 8 + j]), sc[j], bi[j]), 0.f);
+        *reinterpret_cast<uint4*>(my_row + ((((c >> 3) ^ sw) & 7) << 4)) =
+            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
       }
       ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+    }
+    __syncthreads();
+    if (tid == 0) {  // one coalesced tile store; rows / columns beyond the image are clipped by the TMA unit
+      ptx::tma_store_4d(&map_y, sOut, 0, ox0, oy0, b);
+      ptx::bulk_commit_group();
     }
     ST_STAMP(7);
   }
 
+  if (tid == 0) ptx::bulk_wait_group0();
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -286,6 +294,17 @@ int hk_stem_fwd(const float* x_nchw, const void* w_packed, const float* scale, c
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "hk_stem_fwd: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   }
+  CUtensorMap my;
+  {
+    const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+    const cuuint64_t dims[4] = {64, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {128, (cuuint64_t)Wo * 128, (cuuint64_t)Ho * Wo * 128};
+    const cuuint32_t box[4] = {64, (cuuint32_t)ST_TILE_W, (cuuint32_t)ST_TILE_H, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&my, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y_nhwc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "hk_stem_fwd: cuTensorMapEncodeTiled(output) failed with CUresult %d", (int)r);
+  }
   StemTcArgs a;
   a.x = x_nchw; a.scale = scale; a.bias = bias; a.y = static_cast<__nv_bfloat16*>(y_nhwc);
   a.B = B; a.H = H; a.W = W;
@@ -307,7 +326,7 @@ int hk_stem_fwd(const float* x_nchw, const void* w_packed, const float* scale, c
   }
   int grid = 2 * sm_count();
   if (grid > a.num_tiles) grid = a.num_tiles;
-  stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM_BYTES, as_stream(stream)>>>(mw, a);
+  stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM_BYTES, as_stream(stream)>>>(mw, my, a);
   return check_launch("stem_tc_kernel");
 }
 
