@@ -297,42 +297,55 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- end to end through the public API, host buffers ----------------
     copy_stream = torch.cuda.Stream(device=dev)
     compute = torch.cuda.current_stream()
-    dev_in = [torch.empty((B, 3, H, W), device=dev, dtype=torch.float32) for _ in range(2)]
     host_yx = [torch.empty((B, K_KEYPOINTS, 2), dtype=torch.int32).pin_memory() for _ in range(2)]
     host_mv = [torch.empty((B, K_KEYPOINTS), dtype=torch.float32).pin_memory() for _ in range(2)]
     in_ready = [torch.cuda.Event() for _ in range(2)]
     in_free = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_loop(steps):
-        for j in range(2):
-            in_free[j].record(compute)
-        for i in range(steps):
-            j = i & 1
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(in_free[j])
-                dev_in[j].copy_(host_imgs[j], non_blocking=True)     # H2D of this step's images
-                in_ready[j].record(copy_stream)
-            compute.wait_event(in_ready[j])
-            heat, yx = model.heatmaps_and_keypoints(dev_in[j])        # public API (engine forward + decode)
-            in_free[j].record(compute)
-            host_yx[j].copy_(yx, non_blocking=True)                   # D2H of the step's result
-            host_mv[j].copy_(plan.maxval, non_blocking=True)
-        compute.synchronize()
+    def measure_e2e(host_in):
+        """host_in: two pinned host batches (fp32 (B,3,H,W) as ToTensor yields, or uint8 (B,H,W,3) as cv2 yields)."""
+        dev_in = [torch.empty(host_in[0].shape, device=dev, dtype=host_in[0].dtype) for _ in range(2)]
 
-    e2e_loop(max(2, args.warmup))
-    barrier()
-    t0 = time.perf_counter()
-    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s2.record()
-    e2e_loop(args.steps)
-    e2.record()
-    e2.synchronize()
-    barrier()
-    e2e_ms = max_over_ranks(max(s2.elapsed_time(e2), 0.0))
-    wall_ms = (time.perf_counter() - t0) * 1e3
+        def loop(steps):
+            for j in range(2):
+                in_free[j].record(compute)
+            for i in range(steps):
+                j = i & 1
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(in_free[j])
+                    dev_in[j].copy_(host_in[j], non_blocking=True)       # H2D of this step's images
+                    in_ready[j].record(copy_stream)
+                compute.wait_event(in_ready[j])
+                heat, yx = model.heatmaps_and_keypoints(dev_in[j])        # public API (engine forward + decode)
+                in_free[j].record(compute)
+                host_yx[j].copy_(yx, non_blocking=True)                   # D2H of the step's result
+                host_mv[j].copy_(plan.maxval, non_blocking=True)
+            compute.synchronize()
+
+        loop(max(2, args.warmup))
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        s2.record()
+        loop(args.steps)
+        e2.record()
+        e2.synchronize()
+        barrier()
+        ms = max_over_ranks(max(s2.elapsed_time(e2), 0.0))
+        wall = (time.perf_counter() - t0) * 1e3
+        return ms, wall, host_in[0].numel() * host_in[0].element_size()
+
+    e2e_ms, wall_ms, h2d = measure_e2e(host_imgs)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
-    h2d = B * 3 * H * W * 4
     d2h = B * K_KEYPOINTS * 2 * 4 + B * K_KEYPOINTS * 4
+    e2e_u8 = None
+    if args.precision == "bf16":
+        gen8 = torch.Generator().manual_seed(3000 + rank)
+        host_u8 = [torch.randint(0, 256, (B, H, W, 3), generator=gen8, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        u8_ms, u8_wall, u8_h2d = measure_e2e(host_u8)
+        e2e_u8 = {"value": world * B * args.steps / (u8_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": u8_h2d,
+                  "d2h_bytes_per_step": d2h, "ms_per_step": u8_ms / args.steps,
+                  "note": "same loop fed (B,H,W,3) uint8 host images (cv2 layout); /255 fused into the stem load"}
 
     # ---------------- roofline of the dominant kernel (live CUDA-event timing per launch) ----------------
     rows = per_launch_breakdown(engine, plan)
@@ -375,7 +388,8 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
                 "note": "pinned-host fp32 images -> device, forward + decode, keypoints + peak values -> host; "
                         "H2D double-buffered on a copy stream"},
-        "gpu_launches": launches_per_step * args.steps * 2,  # device-resident loop + e2e loop
+        "e2e_uint8_input": e2e_u8,
+        "gpu_launches": launches_per_step * args.steps * (3 if e2e_u8 else 2),  # device-resident loop + e2e loop(s)
         "gpu_launches_per_step": launches_per_step,
         "roofline": roof,
         "clocks": clocks,

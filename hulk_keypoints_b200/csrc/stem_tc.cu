@@ -34,7 +34,7 @@ constexpr int ST_OUT_BYTES = 128 * 128;                 // output tile staging: 
 constexpr int ST_SMEM_BYTES = 1024 + ST_A_BYTES + ST_B_BYTES + ST_OUT_BYTES + ((ST_PATCH_ELEMS * 2 + 15) & ~15) + 64;
 
 struct StemTcArgs {
-  const float* x;   // (B,3,H,W) fp32
+  const void* x;    // (B,3,H,W) fp32 NCHW, or (B,H,W,3) uint8 (cv2 layout) in the U8 instantiation
   const float* scale;
   const float* bias;
   __nv_bfloat16* y;  // (B,Ho,Wo,64) bf16
@@ -50,6 +50,7 @@ struct StemTcArgs {
 // byte offset of (row, 16-byte chunk) inside one 128-row x 128-byte K block, SWIZZLE_128B
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
 
+template <bool U8>
 __global__ void __launch_bounds__(ST_THREADS, 2)
 stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y, const StemTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -102,25 +103,55 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   // (warp-uniform row arithmetic, no per-element div/mod), lane l loads columns l and l+32 (the latter for l < 6).
   constexpr int PATCH_ROWS = 3 * ST_PATCH_H;                       // 63
   constexpr int ROWS_PER_WARP = (PATCH_ROWS + 7) / 8;              // 8
-  float pre[ROWS_PER_WARP][2];
+  // U8 input (B,H,W,3): a patch row is 38 px * 3 = 114 contiguous BYTES already in [x][c] order; warp w owns patch rows
+  // w, w+8, w+16 and lane l loads bytes l, l+32, l+64, l+96 of each.
+  constexpr int U8_ROW_BYTES = ST_PATCH_W * 3;                     // 114
+  constexpr int U8_ROWS_PER_WARP = (ST_PATCH_H + 7) / 8;           // 3
+  float pre[U8 ? 1 : ROWS_PER_WARP][2];
+  uint32_t pre8[U8 ? U8_ROWS_PER_WARP : 1];
   auto prefetch_patch = [&](int t) {
     const int pb = t / a.tiles_per_img;
     const int prem = t - pb * a.tiles_per_img;
     const int pty = prem / a.tiles_x, ptx_ = prem - pty * a.tiles_x;
     const int piy0 = 2 * pty * ST_TILE_H - 3, pix0 = 2 * ptx_ * ST_TILE_W - 3;
-    const float* xb = a.x + (size_t)pb * 3 * a.H * a.W;
-    const int ix_a = pix0 + lane, ix_b = pix0 + lane + 32;
-    const bool ok_a = ix_a >= 0 && ix_a < a.W;
-    const bool ok_b = lane < ST_PATCH_W - 32 && ix_b >= 0 && ix_b < a.W;
+    if constexpr (U8) {
+      const uint8_t* xb = static_cast<const uint8_t*>(a.x) + (size_t)pb * a.H * a.W * 3;
+      bool ok[4];
 #pragma unroll
-    for (int j = 0; j < ROWS_PER_WARP; ++j) {
-      const int seg = warp + 8 * j;                                // warp-uniform
-      const int c = seg / ST_PATCH_H, py = seg - c * ST_PATCH_H;
-      const int iy = piy0 + py;
-      const bool ok_row = seg < PATCH_ROWS && iy >= 0 && iy < a.H;
-      const float* rowp = xb + ((size_t)c * a.H + (ok_row ? iy : 0)) * a.W;
-      pre[j][0] = (ok_row && ok_a) ? __ldg(rowp + ix_a) : 0.f;
-      pre[j][1] = (ok_row && ok_b) ? __ldg(rowp + ix_b) : 0.f;
+      for (int t4 = 0; t4 < 4; ++t4) {
+        const int j = lane + 32 * t4;
+        const int ix = pix0 + j / 3;
+        ok[t4] = j < U8_ROW_BYTES && ix >= 0 && ix < a.W;
+      }
+#pragma unroll
+      for (int jr = 0; jr < U8_ROWS_PER_WARP; ++jr) {
+        const int py = warp + 8 * jr;                              // warp-uniform
+        const int iy = piy0 + py;
+        const bool ok_row = py < ST_PATCH_H && iy >= 0 && iy < a.H;
+        const uint8_t* rowp = xb + ((size_t)(ok_row ? iy : 0) * a.W + pix0) * 3;  // may point before the row start; guarded
+        uint32_t packed = 0;
+#pragma unroll
+        for (int t4 = 0; t4 < 4; ++t4) {
+          const uint32_t v = (ok_row && ok[t4]) ? (uint32_t)__ldg(rowp + lane + 32 * t4) : 0u;
+          packed |= v << (8 * t4);
+        }
+        pre8[jr] = packed;
+      }
+    } else {
+      const float* xb = static_cast<const float*>(a.x) + (size_t)pb * 3 * a.H * a.W;
+      const int ix_a = pix0 + lane, ix_b = pix0 + lane + 32;
+      const bool ok_a = ix_a >= 0 && ix_a < a.W;
+      const bool ok_b = lane < ST_PATCH_W - 32 && ix_b >= 0 && ix_b < a.W;
+#pragma unroll
+      for (int j = 0; j < ROWS_PER_WARP; ++j) {
+        const int seg = warp + 8 * j;                                // warp-uniform
+        const int c = seg / ST_PATCH_H, py = seg - c * ST_PATCH_H;
+        const int iy = piy0 + py;
+        const bool ok_row = seg < PATCH_ROWS && iy >= 0 && iy < a.H;
+        const float* rowp = xb + ((size_t)c * a.H + (ok_row ? iy : 0)) * a.W;
+        pre[j][0] = (ok_row && ok_a) ? __ldg(rowp + ix_a) : 0.f;
+        pre[j][1] = (ok_row && ok_b) ? __ldg(rowp + ix_b) : 0.f;
+      }
     }
   };
   if ((int)blockIdx.x < a.num_tiles) prefetch_patch(blockIdx.x);
@@ -135,14 +166,30 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const int oy0 = ty * ST_TILE_H, ox0 = tx * ST_TILE_W;
 
     // ---- 1. prefetched input patch -> smem, bf16, [y][x][c] ----
+    if constexpr (U8) {
 #pragma unroll
-    for (int j = 0; j < ROWS_PER_WARP; ++j) {
-      const int seg = warp + 8 * j;
-      if (seg < PATCH_ROWS) {
-        const int c = seg / ST_PATCH_H, py = seg - c * ST_PATCH_H;
-        __nv_bfloat16* dstp = patch + (py * ST_PATCH_W) * 3 + c;
-        dstp[lane * 3] = __float2bfloat16_rn(pre[j][0]);
-        if (lane < ST_PATCH_W - 32) dstp[(lane + 32) * 3] = __float2bfloat16_rn(pre[j][1]);
+      for (int jr = 0; jr < U8_ROWS_PER_WARP; ++jr) {
+        const int py = warp + 8 * jr;
+        if (py < ST_PATCH_H) {
+          __nv_bfloat16* dstp = patch + py * U8_ROW_BYTES;
+#pragma unroll
+          for (int t4 = 0; t4 < 4; ++t4) {
+            const int j = lane + 32 * t4;
+            // ToTensor semantics (reference dataset.py:16): uint8 / 255 in fp32, then the bf16 operand rounding
+            if (j < U8_ROW_BYTES) dstp[j] = __float2bfloat16_rn(__fdiv_rn((float)((pre8[jr] >> (8 * t4)) & 0xffu), 255.0f));
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < ROWS_PER_WARP; ++j) {
+        const int seg = warp + 8 * j;
+        if (seg < PATCH_ROWS) {
+          const int c = seg / ST_PATCH_H, py = seg - c * ST_PATCH_H;
+          __nv_bfloat16* dstp = patch + (py * ST_PATCH_W) * 3 + c;
+          dstp[lane * 3] = __float2bfloat16_rn(pre[j][0]);
+          if (lane < ST_PATCH_W - 32) dstp[(lane + 32) * 3] = __float2bfloat16_rn(pre[j][1]);
+        }
       }
     }
     ST_STAMP(1);
@@ -274,10 +321,10 @@ static long long* g_stem_dbg = nullptr;
 // Undocumented diagnostic hook (not in the public header): device buffer of 24*8 int64 receiving CTA 0's phase clocks.
 __attribute__((visibility("default"))) void hk_debug_set_stem_timeline(long long* dev_buf) { g_stem_dbg = dev_buf; }
 
-int hk_stem_fwd(const float* x_nchw, const void* w_packed, const float* scale, const float* bias, void* y_nhwc, int B, int H,
-                int W, void* stream) {
+static int stem_launch(const void* x, bool u8, const void* w_packed, const float* scale, const float* bias, void* y_nhwc, int B,
+                       int H, int W, void* stream) {
   using namespace hk;
-  HK_REQUIRE(x_nchw && w_packed && scale && bias && y_nhwc, "hk_stem_fwd: null pointer");
+  HK_REQUIRE(x && w_packed && scale && bias && y_nhwc, "hk_stem_fwd: null pointer");
   HK_REQUIRE(B > 0 && H >= 7 && W >= 7, "hk_stem_fwd: bad shape");
   HK_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_nhwc) & 15) == 0,
              "hk_stem_fwd: buffers must be 16-byte aligned");
@@ -306,7 +353,7 @@ int hk_stem_fwd(const float* x_nchw, const void* w_packed, const float* scale, c
     if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "hk_stem_fwd: cuTensorMapEncodeTiled(output) failed with CUresult %d", (int)r);
   }
   StemTcArgs a;
-  a.x = x_nchw; a.scale = scale; a.bias = bias; a.y = static_cast<__nv_bfloat16*>(y_nhwc);
+  a.x = x; a.scale = scale; a.bias = bias; a.y = static_cast<__nv_bfloat16*>(y_nhwc);
   a.B = B; a.H = H; a.W = W;
   a.dbg = g_stem_dbg;
   a.Ho = (H + 6 - 7) / 2 + 1;
@@ -316,18 +363,30 @@ int hk_stem_fwd(const float* x_nchw, const void* w_packed, const float* scale, c
   const long long nt = (long long)a.tiles_per_img * B;
   HK_REQUIRE(nt < 0x7fffffffLL, "hk_stem_fwd: too many tiles");
   a.num_tiles = (int)nt;
-  static int attr_dev_mask = 0;
+  static int attr_dev_mask[2] = {0, 0};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!(attr_dev_mask & (1 << dev))) {
-    cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES);
+  if (!(attr_dev_mask[u8] & (1 << dev))) {
+    cudaError_t e = u8 ? cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES)
+                       : cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES);
     if (e != cudaSuccess) return fail(HK_ERR_CUDA, "hk_stem_fwd: smem attribute: %s", cudaGetErrorString(e));
-    attr_dev_mask |= (1 << dev);
+    attr_dev_mask[u8] |= (1 << dev);
   }
   int grid = 2 * sm_count();
   if (grid > a.num_tiles) grid = a.num_tiles;
-  stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM_BYTES, as_stream(stream)>>>(mw, my, a);
+  if (u8) stem_tc_kernel<true><<<grid, ST_THREADS, ST_SMEM_BYTES, as_stream(stream)>>>(mw, my, a);
+  else stem_tc_kernel<false><<<grid, ST_THREADS, ST_SMEM_BYTES, as_stream(stream)>>>(mw, my, a);
   return check_launch("stem_tc_kernel");
+}
+
+int hk_stem_fwd(const float* x_nchw, const void* w_packed, const float* scale, const float* bias, void* y_nhwc, int B, int H,
+                int W, void* stream) {
+  return stem_launch(x_nchw, false, w_packed, scale, bias, y_nhwc, B, H, W, stream);
+}
+
+int hk_stem_fwd_u8(const uint8_t* x_nhwc_u8, const void* w_packed, const float* scale, const float* bias, void* y_nhwc, int B,
+                   int H, int W, void* stream) {
+  return stem_launch(x_nhwc_u8, true, w_packed, scale, bias, y_nhwc, B, H, W, stream);
 }
 
 }  // extern "C"

@@ -46,6 +46,8 @@ class _Plan:
         h8, w8 = ops.conv_out_hw(h4, w4, 3, 2, 1, 1)
         self.h2, self.w2, self.h4, self.w4, self.h8, self.w8 = h2, w2, h4, w4, h8, w8
         self.x = torch.empty((B, 3, H, W), device=dev, dtype=torch.float32)
+        self.x_u8: Optional[torch.Tensor] = None  # (B,H,W,3) uint8 staging, allocated on first uint8 call
+        self.input_is_u8 = False
         self.stem = torch.empty((B, h2, w2, 64), device=dev, dtype=adt)
         max_elems = max(B * h4 * w4 * 64, B * h8 * w8 * 512)
         self.pool = [torch.empty(max_elems, device=dev, dtype=adt) for _ in range(4)]
@@ -131,7 +133,8 @@ class InferenceEngine:
         P = self._packed
         n = 0
         if self._stem_w_tc is not None:
-            ops.stem(plan.x, self._stem_w_tc, P["stem"].scale, P["stem"].bias, out=plan.stem); n += 1
+            src = plan.x_u8 if plan.input_is_u8 else plan.x
+            ops.stem(src, self._stem_w_tc, P["stem"].scale, P["stem"].bias, out=plan.stem); n += 1
         else:
             self._conv(P["stem"], plan.x, plan.stem, relu=True, in_is_nchw=True); n += 1
         cur = 0
@@ -173,29 +176,42 @@ class InferenceEngine:
         if not self.use_cuda_graph:
             plan.launches = self._enqueue(plan, decode)
             return
-        if plan.graph is None or plan.graph_decode != decode:
+        if plan.graph is None or plan.graph_decode != (decode, plan.input_is_u8):
             # warm-up run outside capture (function attributes, lazy module load), then capture
             plan.launches = self._enqueue(plan, decode)
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._enqueue(plan, decode)
-            plan.graph, plan.graph_decode = g, decode
+            plan.graph, plan.graph_decode = g, (decode, plan.input_is_u8)
         plan.graph.replay()
 
     def forward(self, x: torch.Tensor, decode: bool = False, clone: bool = True):
-        """(B,3,H,W) or (3,H,W) fp32 CUDA -> heat (B,K,H,W) fp32 [, yx (B,K,2) int32]."""
+        """(B,3,H,W) / (3,H,W) fp32, or (B,H,W,3) / (H,W,3) uint8 (cv2 layout), CUDA -> heat (B,K,H,W) fp32 [, yx (B,K,2)]."""
+        u8 = x.dtype == torch.uint8
         if x.dim() == 3:
             x = x.unsqueeze(0)
-        if x.dim() != 4 or x.shape[1] != 3:
-            raise ValueError(f"expected (B,3,H,W) input, got {tuple(x.shape)}")
+        if x.dim() != 4 or (x.shape[3] if u8 else x.shape[1]) != 3:
+            raise ValueError(f"expected (B,3,H,W) float or (B,H,W,3) uint8 input, got {tuple(x.shape)} {x.dtype}")
         self._ensure_packed()
         if x.device != self.device:
             raise RuntimeError(f"input on {x.device} but model on {self.device}")
-        B, _, H, W = x.shape
+        if u8:
+            B, H, W, _ = x.shape
+        else:
+            B, _, H, W = x.shape
         plan = self.plan_for(B, H, W)
         with torch.no_grad():
-            plan.x.copy_(x)  # fp32 cast + contiguous NCHW in one pass
+            if u8 and self._stem_w_tc is not None:
+                if plan.x_u8 is None:
+                    plan.x_u8 = torch.empty((B, H, W, 3), device=self.device, dtype=torch.uint8)
+                plan.x_u8.copy_(x)
+                plan.input_is_u8 = True
+            else:
+                # fp32 path (and the fp32 correctness mode for uint8 input: ToTensor semantics, dataset.py:16)
+                # (tensor / tensor keeps IEEE division on the GPU; tensor / python-scalar would multiply by 1/255)
+                plan.x.copy_(x.permute(0, 3, 1, 2).float() / torch.full((), 255.0, device=x.device) if u8 else x)
+                plan.input_is_u8 = False
             self.run_plan(plan, decode)
             heat = plan.heat.clone() if clone else plan.heat
             if decode:

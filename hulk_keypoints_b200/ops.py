@@ -84,17 +84,29 @@ def stem_pack_weights(w_oihw: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def stem(x_nchw: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor,
+def stem(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor,
          out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """(B,3,H,W) fp32 -> conv7x7 s2 + affine + ReLU -> (B,H/2,W/2,64) bf16 NHWC on tcgen05."""
-    _need_cuda(x_nchw, w_packed, scale, bias, out)
-    if x_nchw.dtype != torch.float32 or not x_nchw.is_contiguous() or x_nchw.shape[1] != 3:
-        raise ValueError("stem needs a contiguous (B,3,H,W) fp32 input")
-    B, _, H, W = x_nchw.shape
+    """conv7x7 s2 + affine + ReLU on tcgen05 -> (B,H/2,W/2,64) bf16 NHWC.
+    x: (B,3,H,W) fp32 NCHW (the reference's tensor) or (B,H,W,3) uint8 (cv2 layout; /255 fused into the load)."""
+    _need_cuda(x, w_packed, scale, bias, out)
+    if not x.is_contiguous() or x.dim() != 4:
+        raise ValueError("stem needs a contiguous 4-D input")
+    if x.dtype == torch.uint8:
+        if x.shape[3] != 3:
+            raise ValueError("uint8 input must be (B,H,W,3)")
+        B, H, W, _ = x.shape
+        fn, name = lib().hk_stem_fwd_u8, "hk_stem_fwd_u8"
+    elif x.dtype == torch.float32:
+        if x.shape[1] != 3:
+            raise ValueError("fp32 input must be (B,3,H,W)")
+        B, _, H, W = x.shape
+        fn, name = lib().hk_stem_fwd, "hk_stem_fwd"
+    else:
+        raise ValueError("stem input must be fp32 NCHW or uint8 NHWC")
     Ho, Wo = conv_out_hw(H, W, 7, 2, 3, 1)
     if out is None:
-        out = torch.empty((B, Ho, Wo, 64), device=x_nchw.device, dtype=torch.bfloat16)
-    check(lib().hk_stem_fwd(ptr(x_nchw), ptr(w_packed), ptr(scale), ptr(bias), ptr(out), B, H, W, stream_ptr()), "hk_stem_fwd")
+        out = torch.empty((B, Ho, Wo, 64), device=x.device, dtype=torch.bfloat16)
+    check(fn(ptr(x), ptr(w_packed), ptr(scale), ptr(bias), ptr(out), B, H, W, stream_ptr()), name)
     return out
 
 

@@ -106,6 +106,11 @@ HK_API size_t hk_stem_packed_weight_bytes(void);
 HK_API int hk_stem_pack_weights(const float* w_oihw, void* w_out, void* stream);
 HK_API int hk_stem_fwd(const float* x_nchw, const void* w_packed, const float* scale, const float* bias,
                        void* y_nhwc, int B, int H, int W, void* stream);
+/* Same, reading the image as cv2.imread delivers it: (B,H,W,3) uint8.  The ToTensor step of the reference
+ * (src/dataset.py:16,71 / analysis.py:37: HWC uint8 -> CHW float32 / 255) is fused into the load, so the host->device
+ * copy is 4x smaller. */
+HK_API int hk_stem_fwd_u8(const uint8_t* x_nhwc_u8, const void* w_packed, const float* scale, const float* bias,
+                          void* y_nhwc, int B, int H, int W, void* stream);
 
 /* MaxPool2d(kernel 3, stride 2, pad 1) on NHWC.  Replaces src/resnet.py:141,202. */
 HK_API int hk_maxpool3x3s2_fwd(const void* x, void* y, int dtype, int batch, int in_h, int in_w, int c,

@@ -332,3 +332,16 @@ C64_CASES = [
 def test_conv_tcgen05_c64_specialisation(case):
     B, H, W, dil, residual, relu = case
     test_conv_tcgen05_vs_oracle((B, H, W, 64, 64, 3, 1, dil, residual, relu))
+
+
+def test_stem_uint8_input_matches_float_path():
+    """(B,H,W,3) uint8 input with /255 fused into the load == the fp32 NCHW path fed ToTensor(img) (dataset.py:16)."""
+    g = torch.Generator().manual_seed(33)
+    img = torch.randint(0, 256, (2, 70, 90, 3), generator=g, dtype=torch.uint8)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.05
+    s, b = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
+    wp = ops.stem_pack_weights(w.to(dev()))
+    y8 = ops.stem(img.to(dev()), wp, s.to(dev()), b.to(dev()))
+    xf = img.permute(0, 3, 1, 2).float().div(255).contiguous()
+    yf = ops.stem(xf.to(dev()), wp, s.to(dev()), b.to(dev()))
+    assert torch.equal(y8, yf)

@@ -236,3 +236,18 @@ def test_train_step_matches_reference_formulation():
         worst = min(worst, float(torch.dot(a, b) / (a.norm() * b.norm())))
     assert worst > 0.999, worst
     assert gm["resnet.resnet34_8s.fc.weight"].grad[4:].abs().sum().item() == 0.0
+
+
+def test_uint8_image_input_end_to_end(sd_cal):
+    """analysis.py reads a BGR uint8 image and applies ToTensor before .cuda(); feeding the uint8 HWC image directly
+    (additive API) gives the same heatmaps and keypoints in both precisions."""
+    g = torch.Generator().manual_seed(17)
+    img = torch.randint(0, 256, (2, 96, 128, 3), generator=g, dtype=torch.uint8)
+    as_float = hk.transform(img[0].numpy())                       # the reference's transform on one image
+    assert torch.equal(as_float, img[0].permute(2, 0, 1).float().div(255))
+    xf = img.permute(0, 3, 1, 2).float().div(255).contiguous().cuda()
+    for precision in ("bf16", "fp32"):
+        m = make_model(sd_cal, precision)
+        h_u8, yx_u8 = m.heatmaps_and_keypoints(img.cuda())
+        h_f, yx_f = m.heatmaps_and_keypoints(xf)
+        assert torch.equal(h_u8, h_f) and torch.equal(yx_u8, yx_f), precision
