@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4, help="per-GPU batch (config.py: 4)")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"], help="FusedAdam (hk_adam_step) or torch.optim.Adam")
     ap.add_argument("--reference-loss", action="store_true", help="use torch's .double()+BCELoss on fp64 targets (train.py:21-25)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -49,7 +50,11 @@ def main():
     torch.manual_seed(0)
     model = hk.KeypointsGauss(4, img_height=args.height, img_width=args.width).to(dev).train()
     parallel.broadcast_model(model)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
+    if args.optimizer == "fused" and not args.reference_loss:
+        from hulk_keypoints_b200.optim import FusedAdam
+        opt = FusedAdam(model.parameters(), lr=1e-4, weight_decay=1e-4)
+    else:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
     B, H, W = args.batch, args.height, args.width
     g = torch.Generator().manual_seed(2000 + rank)
     img = torch.rand(B, 3, H, W, generator=g).to(dev)
@@ -92,7 +97,8 @@ def main():
             "data": "synthetic", "loss": float(loss.item()),
             "config": {"workload": f"train step, per-GPU batch {B}, {H}x{W}, K=4, Adam lr 1e-4 wd 1e-4 (BASELINE.json configs[3])",
                        "loss_path": "torch BCELoss on fp64 targets" if args.reference_loss else "fused hk_bce_fwd_bwd, targets on the fly",
-                       "parallelism": f"data-parallel x{world}, bucketed NCCL all-reduce"}}), flush=True)
+                       "optimizer": type(opt).__name__,
+                       "parallelism": f"data-parallel x{world}, NCCL all-reduce of the gradients"}}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -23,7 +23,7 @@ EXPORTS = (
     "hk_version", "hk_last_error", "hk_check_device", "hk_pack_conv_weights", "hk_conv_bn_act_fwd",
     "hk_maxpool3x3s2_fwd", "hk_head_fwd", "hk_argmax_workspace_bytes", "hk_argmax_decode",
     "hk_gauss_targets", "hk_bce_workspace_bytes", "hk_bce_fwd_bwd",
-    "hk_stem_packed_weight_bytes", "hk_stem_pack_weights", "hk_stem_fwd", "hk_stem_fwd_u8",
+    "hk_stem_packed_weight_bytes", "hk_stem_pack_weights", "hk_stem_fwd", "hk_stem_fwd_u8", "hk_adam_step",
 )
 
 
@@ -65,6 +65,8 @@ def _declare(lib):
     lib.hk_stem_pack_weights.argtypes = [vp, vp, vp]
     lib.hk_stem_fwd.restype = i
     lib.hk_stem_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
+    lib.hk_adam_step.restype = i
+    lib.hk_adam_step.argtypes = [vp, vp, vp, vp, C.c_longlong, f, f, f, f, f, i, vp]
     lib.hk_stem_fwd_u8.restype = i
     lib.hk_stem_fwd_u8.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
     lib.hk_bce_workspace_bytes.restype = sz

@@ -49,11 +49,19 @@ def loss_from_batch(sample_batched, model, use_cuda: bool = True) -> torch.Tenso
 
 def train_step(model, optimizer, img: torch.Tensor, uv: torch.Tensor, sigma: float = 8.0, allreduce=None) -> torch.Tensor:
     """One step of reference train.py:33-36 (zero_grad, forward, backward, step) with targets generated from
-    labels on the fly.  `allreduce(params)` is called between backward and step (data-parallel exchange)."""
-    optimizer.zero_grad(set_to_none=True)
+    labels on the fly.  `optimizer` is a `hulk_keypoints_b200.optim.FusedAdam` (flat buffers: one all-reduce, one
+    update kernel) or any torch optimizer; `allreduce(params)` (data-parallel exchange) runs between backward and step
+    for torch optimizers, FusedAdam reduces its flat gradient buffer itself."""
+    fused = hasattr(optimizer, "flat_grad")
+    if fused:
+        optimizer.zero_grad()
+    else:
+        optimizer.zero_grad(set_to_none=True)
     loss = sigmoid_bce_loss(model.forward_logits(img), uv=uv, sigma=sigma)
     loss.backward()
-    if allreduce is not None:
+    if fused:
+        optimizer.all_reduce_grads()
+    elif allreduce is not None:
         allreduce(model.parameters())
     optimizer.step()
     return loss.detach()

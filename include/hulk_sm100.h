@@ -160,6 +160,12 @@ HK_API int hk_bce_fwd_bwd(const float* pred, int pred_is_logits, const void* tar
                    const float* uv_or_null, int B, int K, int H, int W, float sigma,
                    double* loss, float* grad_logits_or_null, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- optimiser ----
+ * One fused Adam step over flat fp32 buffers (coupled L2 weight decay, no amsgrad) -- torch.optim.Adam(lr, weight_decay)
+ * of train.py:79 as applied at train.py:36.  `step` is the 1-based step count used for the bias corrections. */
+HK_API int hk_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

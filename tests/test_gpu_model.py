@@ -251,3 +251,29 @@ def test_uint8_image_input_end_to_end(sd_cal):
         h_u8, yx_u8 = m.heatmaps_and_keypoints(img.cuda())
         h_f, yx_f = m.heatmaps_and_keypoints(xf)
         assert torch.equal(h_u8, h_f) and torch.equal(yx_u8, yx_f), precision
+
+
+def test_fused_adam_training_tracks_torch_adam():
+    """Three steps of our train_step with FusedAdam vs torch.optim.Adam on identical models/batches: same losses and
+    (nearly) the same weights afterwards."""
+    from hulk_keypoints_b200.optim import FusedAdam
+    torch.manual_seed(2)
+    a = hk.KeypointsGauss(4).cuda().train()
+    b = hk.KeypointsGauss(4).cuda().train()
+    b.load_state_dict(a.state_dict())
+    oa = FusedAdam(a.parameters(), lr=1e-4, weight_decay=1e-4)
+    ob = torch.optim.Adam(b.parameters(), lr=1e-4, weight_decay=1e-4)
+    gen = torch.Generator().manual_seed(4)
+    for _ in range(3):
+        img, uv = synth_batch(gen, 2, 64, 96)
+        la = train_ops.train_step(a, oa, img.cuda(), uv.cuda(), sigma=8.0)
+        lb = train_ops.train_step(b, ob, img.cuda(), uv.cuda(), sigma=8.0)
+        assert abs(la.item() - lb.item()) < 1e-4 * abs(lb.item())
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        if sa[k].dtype.is_floating_point:
+            # Adam normalises by sqrt(v): where the gradient is at noise level (cuDNN backward is not bit-reproducible) the
+            # update direction can flip, so two runs may differ by up to 2*lr per step on such elements
+            assert torch.allclose(sa[k], sb[k], rtol=1e-3, atol=2 * 1e-4 * 3 + 1e-5), k
+    # the model still serves inference after its parameters became views of the flat buffer
+    assert a.eval()(rand_img(1, 1, 64, 96).cuda()).shape == (1, 4, 64, 96)

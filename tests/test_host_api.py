@@ -170,3 +170,28 @@ def test_dropin_shims_reexport_the_package(monkeypatch):
     assert (config.NUM_KEYPOINTS, config.IMG_HEIGHT, config.IMG_WIDTH, config.GAUSS_SIGMA) == (4, 480, 640, 8)
     m = model.KeypointsGauss(config.NUM_KEYPOINTS, img_height=config.IMG_HEIGHT, img_width=config.IMG_WIDTH)
     assert len(m.state_dict()) == 218
+
+
+def test_checkpoint_roundtrip_and_pretrained_import(tmp_path):
+    from hulk_keypoints_b200 import checkpoint
+    torch.manual_seed(3)
+    m = hk.KeypointsGauss(4)
+    path = str(tmp_path / "model_2_1_0.pth")
+    checkpoint.save_checkpoint(m, path)                       # train.py:47-48 format
+    sd = torch.load(path)
+    assert list(sd.keys()) == list(O.init_state_dict(0).keys())
+    m2 = hk.KeypointsGauss(4)
+    checkpoint.load_checkpoint(m2, path)                      # analysis.py:19
+    assert sd_digest(m2.state_dict()) == sd_digest(m.state_dict())
+    # torchvision-format ResNet-34 weights (what resnet34(pretrained=True) downloads, resnet.py:237-238)
+    import torchvision
+    tv = torchvision.models.resnet34(weights=None)
+    n = checkpoint.load_pretrained_backbone(m2, tv.state_dict())
+    assert n == len(tv.state_dict()) - 2                      # everything but fc.weight / fc.bias
+    own = m2.state_dict()
+    assert torch.equal(own[checkpoint.PREFIX + "layer3.0.downsample.0.weight"], tv.state_dict()["layer3.0.downsample.0.weight"])
+    assert torch.equal(own[checkpoint.PREFIX + "fc.weight"], m.state_dict()[checkpoint.PREFIX + "fc.weight"])  # untouched
+    bad = dict(tv.state_dict())
+    bad.pop("bn1.weight")
+    with pytest.raises(KeyError):
+        checkpoint.load_pretrained_backbone(m2, bad)
