@@ -42,7 +42,11 @@ struct ConvTc2Args {
   int Cin, kh, kw, stride, pad, dil, relu;
   int tiles_x, tiles_per_img, num_boxes;
   int num_m_tiles, num_n_tiles, cblocks;  // m tiles of 256 pixels (4 boxes)
+  int dbg_mode;    // diagnostics only (HK_TC2_DEBUG): bit flags 1 = skip the MMAs, 2 = skip the TMA operand loads, 4 = skip the epilogue body (results are garbage)
+  long long* dbg;  // optional timeline of cluster 0's leader CTA (tools/diag_tc2_timeline.py); null in production
 };
+#define T2_STAMP(role, t, slot) \
+  do { if (a.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (t) < 16) a.dbg[((role) * 16 + (t)) * 8 + (slot)] = clock64(); } while (0)
 
 template <int BLOCK_N>
 struct Tc2Cfg {
@@ -61,6 +65,19 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
+}
+// one lane of the (converged) warp; the branch stays warp-uniform for the compiler, so descriptors/coordinates live in
+// uniform registers instead of being moved there one by one (R2UR) in front of every UTCHMMA / UTMALDG
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
@@ -145,7 +162,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   uint64_t* res_bar = tmem_empty_bar + 2;  // [3]: residual chunk landed in staging buffer i
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 3);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp: provably uniform
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -181,12 +198,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer (both CTAs) =====================
-      uint32_t stage = 0, phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+    {
+      // ===================== TMA producer (both CTAs; whole warp waits, one elected lane issues) =====================
+      uint32_t stage = 0, phase = 0, pit = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++pit) {
         const int m_tile = tile / a.num_n_tiles, n_tile = tile - m_tile * a.num_n_tiles;
         int b0, y0, x0, b1, y1, x1;
+        T2_STAMP(0, pit, 0);
         t2_decode_box(a, 4 * m_tile + 2 * (int)rank, b0, y0, x0);
         t2_decode_box(a, 4 * m_tile + 2 * (int)rank + 1, b1, y1, x1);
         const int n_row0 = n_tile * BLOCK_N + (int)rank * Cfg::HALF_N;
@@ -195,41 +213,54 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const int dy = r * a.dil - a.pad, dx = s * a.dil - a.pad;
             const int kbase = (r * a.kw + s) * a.Cin;
             for (int cb = 0; cb < a.cblocks; ++cb) {
+              if (a.dbg_mode & 2) continue;
               ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 31);
-              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-              ptx::tma2_load_4d(sa, &map_x, &full_bar[stage], cb * 64, x0 * a.stride + dx, y0 * a.stride + dy, b0);
-              ptx::tma2_load_4d(sa + T2_BOX_BYTES, &map_x, &full_bar[stage], cb * 64, x1 * a.stride + dx, y1 * a.stride + dy, b1);
-              ptx::tma2_load_2d(sa + T2_A_BYTES, &map_w, &full_bar[stage], kbase + cb * 64, n_row0);
-              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-              else ptx::mbar_arrive_remote(&full_bar[stage], 0);
+              if (ptx::elect_one_sync()) {
+                uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                ptx::tma2_load_4d(sa, &map_x, &full_bar[stage], cb * 64, x0 * a.stride + dx, y0 * a.stride + dy, b0);
+                ptx::tma2_load_4d(sa + T2_BOX_BYTES, &map_x, &full_bar[stage], cb * 64, x1 * a.stride + dx, y1 * a.stride + dy, b1);
+                ptx::tma2_load_2d(sa + T2_A_BYTES, &map_w, &full_bar[stage], kbase + cb * 64, n_row0);
+                if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                else ptx::mbar_arrive_remote(&full_bar[stage], 0);
+              }
+              __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
         }
+        T2_STAMP(0, pit, 1);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      // ===================== MMA issuer (leader CTA only; whole warp waits, one elected lane issues) =====================
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(256, BLOCK_N);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        T2_STAMP(1, it, 0);
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 32);
         ptx::tc_fence_after();
+        T2_STAMP(1, it, 1);
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase, 33);
+          if (!(a.dbg_mode & 2)) ptx::mbar_wait(&full_bar[stage], phase, 33);
+          if (kb == 0) T2_STAMP(1, it, 2);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
           const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + T2_A_BYTES);
+          if (ptx::elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ptx::umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          ptx::umma2_commit_mc(&empty_bar[stage]);
-          if (kb == num_kb - 1) ptx::umma2_commit_mc(&tmem_full_bar[acc]);
+            for (int k = 0; k < 4; ++k)
+              if (!(a.dbg_mode & 1)) ptx::umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma2_commit_mc(&empty_bar[stage]);
+            if (kb == num_kb - 1) ptx::umma2_commit_mc(&tmem_full_bar[acc]);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        T2_STAMP(1, it, 3);
       }
       // all remote arrivals of the last two accumulator uses must land before this CTA's barriers go away
       if (it >= 1) { const uint32_t j = it - 1; ptx::mbar_wait(&tmem_empty_bar[j & 1], (j >> 1) & 1, 34); }
@@ -264,11 +295,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         ptx::tma_load_4d(buf + 8192, &map_res, &res_bar[bsel], n0 + chunk * 64, x1, y1, b1);
       };
       if (elected) {
+        T2_STAMP(2, it, 0);
         ptx::bulk_wait_group_read1();
         if (has_res) issue_residual(0, chunk_ctr);
       }
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 36);
       ptx::tc_fence_after();
+      if (elected) T2_STAMP(2, it, 1);
+      if (a.dbg_mode & 4) {
+        ptx::tc_fence_before();
+        ptx::mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+        continue;
+      }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
       for (int chunk = 0; chunk < CHUNKS; ++chunk, ++chunk_ctr) {
@@ -279,15 +317,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (has_res && chunk + 1 < CHUNKS) issue_residual(chunk + 1, chunk_ctr + 1);  // one chunk ahead
         }
         ptx::named_bar_sync(1, 128);  // staging[bsel] is free for everybody (elected passed its wait_group)
+        if (elected && chunk == 0) T2_STAMP(2, it, 2);
         uint32_t r0[32], r1[32];
         ptx::tmem_ld_32x32(taddr + chunk * 64, r0);
         ptx::tmem_ld_32x32(taddr + chunk * 64 + 32, r1);
         ptx::tmem_ld_wait();
+        if (elected && chunk == 0) T2_STAMP(2, it, 3);
         if (chunk == CHUNKS - 1) {  // accumulator fully drained: release it to the MMA warp
           ptx::tc_fence_before();
           ptx::mbar_arrive_remote(&tmem_empty_bar[acc], 0);
         }
         if (has_res) ptx::mbar_wait(&res_bar[bsel], (chunk_ctr / 3) & 1, 37);
+        if (elected && chunk == 0) T2_STAMP(2, it, 4);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const int c = chunk * 64 + g * 8;
@@ -316,7 +357,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           *slot = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
         ptx::fence_proxy_async_smem();
+        if (elected && chunk == 0) T2_STAMP(2, it, 5);
         ptx::named_bar_sync(1, 128);
+        if (elected && chunk == 0) T2_STAMP(2, it, 6);
+        if (elected && chunk == CHUNKS - 1) T2_STAMP(2, it, 7);
         if (elected) {
           const uint8_t* buf = staging + bsel * 16384;
           ptx::tma_store_4d(&map_y, buf, n0 + chunk * 64, x0, y0, b0);         // clipped outside the image / batch
@@ -340,6 +384,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_fn();
+
+static long long* g_tc2_dbg = nullptr;
+extern "C" __attribute__((visibility("default"))) void hk_debug_set_tc2_timeline(long long* dev_buf) { g_tc2_dbg = dev_buf; }
 
 bool conv_tc2_applicable(const HkConvDesc& d) {
   static const bool disabled = getenv("HK_DISABLE_2CTA") != nullptr;
@@ -423,6 +470,8 @@ int conv_tc2_launch(const HkConvDesc& d, const void* x, const void* w, const flo
   a.num_m_tiles = (a.num_boxes + 3) / 4;
   a.num_n_tiles = d.out_c / block_n;
   a.cblocks = d.in_c / 64;
+  a.dbg = g_tc2_dbg;
+  { const char* m = getenv("HK_TC2_DEBUG"); a.dbg_mode = m ? atoi(m) : 0; }
   return block_n == 256 ? launch_tc2<256>(mx, mw, my, mres, a, s) : launch_tc2<128>(mx, mw, my, mres, a, s);
 }
 
