@@ -82,7 +82,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp: provably uniform
   const int total_tiles = a.num_m_tiles * a.num_n_tiles;
   const int num_kb = a.kh * a.kw * a.cblocks;
 
@@ -111,8 +111,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    {
+      // ===================== TMA producer (whole warp waits, one elected lane issues) =====================
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / a.num_n_tiles, n_tile = tile - m_tile * a.num_n_tiles;
@@ -125,12 +125,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const int kbase = (r * a.kw + s) * a.Cin;
             for (int cb = 0; cb < a.cblocks; ++cb) {
               ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-              ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-              ptx::tma_load_4d(sa, &map_x, &full_bar[stage], cb * TC_BLOCK_K, x0 * a.stride + dx, y0 * a.stride + dy, b0);
-              ptx::tma_load_4d(sa + TC_BOX_BYTES, &map_x, &full_bar[stage], cb * TC_BLOCK_K, x1 * a.stride + dx,
-                               y1 * a.stride + dy, b1);
-              ptx::tma_load_2d(sa + TC_A_BYTES, &map_w, &full_bar[stage], kbase + cb * TC_BLOCK_K, n_tile * BLOCK_N);
+              if (ptx::elect_one_sync()) {
+                uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                ptx::tma_load_4d(sa, &map_x, &full_bar[stage], cb * TC_BLOCK_K, x0 * a.stride + dx, y0 * a.stride + dy, b0);
+                ptx::tma_load_4d(sa + TC_BOX_BYTES, &map_x, &full_bar[stage], cb * TC_BLOCK_K, x1 * a.stride + dx,
+                                 y1 * a.stride + dy, b1);
+                ptx::tma_load_2d(sa + TC_A_BYTES, &map_w, &full_bar[stage], kbase + cb * TC_BLOCK_K, n_tile * BLOCK_N);
+              }
+              __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -138,8 +141,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    {
+      // ===================== MMA issuer (whole warp waits, one elected lane issues) =====================
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(TC_BLOCK_M, BLOCK_N);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -153,13 +156,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
           const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + TC_A_BYTES);
+          if (ptx::elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+              ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            ptx::umma_commit(&empty_bar[stage]);                         // frees the smem slot when the MMAs retire
+            if (kb == num_kb - 1) ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator ready for the epilogue
           }
-          ptx::umma_commit(&empty_bar[stage]);                         // frees the smem slot when the MMAs retire
-          if (kb == num_kb - 1) ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator ready for the epilogue
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }

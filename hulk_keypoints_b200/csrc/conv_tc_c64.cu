@@ -42,7 +42,7 @@ struct ConvC64Args {
   long long* dbg;  // optional timeline of CTA 0 (tools/diag_c64_timeline.py); null in production
 };
 #define C64_STAMP(role, t, slot) \
-  do { if (a.dbg && blockIdx.x == 0 && (t) < 16) a.dbg[((role) * 16 + (t)) * 8 + (slot)] = clock64(); } while (0)
+  do { if (a.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (t) < 16) a.dbg[((role) * 16 + (t)) * 8 + (slot)] = clock64(); } while (0)
 constexpr int C64_STAGING_BYTES = 128 * 128;  // one output tile: 128 pixels x 64 ch bf16
 
 __global__ void __launch_bounds__(C64_THREADS, 1)
@@ -62,7 +62,7 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   uint64_t* res_bar = w_bar + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp: provably uniform
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_x);
@@ -93,10 +93,13 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      ptx::mbar_arrive_expect_tx(w_bar, C64_W_BYTES);
-      for (int t = 0; t < 9; ++t) ptx::tma_load_2d(sW + t * (C64_C * 128), &map_w, w_bar, t * C64_C, 0);
+    {
+      // ===================== TMA producer (whole warp waits, one elected lane issues) =====================
+      if (lane == 0) {
+        ptx::mbar_arrive_expect_tx(w_bar, C64_W_BYTES);
+        for (int t = 0; t < 9; ++t) ptx::tma_load_2d(sW + t * (C64_C * 128), &map_w, w_bar, t * C64_C, 0);
+      }
+      __syncwarp();
       uint32_t stage = 0, phase = 0;
       int dt = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++dt) {
@@ -108,15 +111,18 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           C64_STAMP(0, dt, 2 * s);
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 21);
           C64_STAMP(0, dt, 2 * s + 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], a.patch_bytes);
-          ptx::tma_load_4d(sA + stage * a.patch_bytes, &map_x, &full_bar[stage], 0, x0 + (s - 1) * a.dil, y0 - a.dil, b);
+          if (ptx::elect_one_sync()) {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], a.patch_bytes);
+            ptx::tma_load_4d(sA + stage * a.patch_bytes, &map_x, &full_bar[stage], 0, x0 + (s - 1) * a.dil, y0 - a.dil, b);
+          }
+          __syncwarp();
           if (++stage == (uint32_t)SLOTS) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    {
+      // ===================== MMA issuer (whole warp waits, one elected lane issues) =====================
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, C64_C);
       ptx::mbar_wait(w_bar, 0, 22);
       const uint32_t w0 = ptx::smem_u32(sW);
@@ -134,17 +140,20 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           C64_STAMP(1, (int)it, 2 + s);
           ptx::tc_fence_after();
           const uint32_t st = ptx::smem_u32(sA + stage * a.patch_bytes);
+          if (ptx::elect_one_sync()) {
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {  // vertical taps: same box, r*dil rows further down
-            const uint64_t adesc = ptx::make_smem_desc_sw128(st + r * a.dil * C64_ROW_BYTES);
-            const uint64_t bdesc = ptx::make_smem_desc_sw128(w0 + (r * 3 + s) * (C64_C * 128));
+            for (int r = 0; r < 3; ++r) {  // vertical taps: same box, r*dil rows further down
+              const uint64_t adesc = ptx::make_smem_desc_sw128(st + r * a.dil * C64_ROW_BYTES);
+              const uint64_t bdesc = ptx::make_smem_desc_sw128(w0 + (r * 3 + s) * (C64_C * 128));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (r | s | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (r | s | k) != 0 ? 1u : 0u);
+            }
+            ptx::umma_commit(&empty_bar[stage]);
+            if (s == 2) ptx::umma_commit(&tmem_full_bar[acc]);
           }
-          ptx::umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == (uint32_t)SLOTS) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tmem_full_bar[acc]);
         C64_STAMP(1, (int)it, 5);
       }
     }

@@ -65,6 +65,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);  // same value, provably warp-uniform for the compiler
 
   if (tid == 0) {
     ptx::prefetch_tensormap(&map_w);
@@ -219,7 +220,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     ST_STAMP(4);
 
     // ---- 3. MMA ----
-    if (tid == 0) {
+    if (warp_u == 0 && ptx::elect_one_sync()) {  // warp-uniform branch: descriptors stay in uniform registers
       ptx::tc_fence_after();
       if (first) ptx::mbar_wait(w_bar, 0, 11);
       const uint32_t a0 = ptx::smem_u32(sA), b0 = ptx::smem_u32(sB);
