@@ -24,6 +24,11 @@ EXPORTS = (
     "hk_maxpool3x3s2_fwd", "hk_head_fwd", "hk_argmax_workspace_bytes", "hk_argmax_decode",
     "hk_gauss_targets", "hk_bce_workspace_bytes", "hk_bce_fwd_bwd",
     "hk_stem_packed_weight_bytes", "hk_stem_pack_weights", "hk_stem_fwd", "hk_stem_fwd_u8", "hk_adam_step",
+    # training
+    "hk_stem_conv_fwd", "hk_bn_workspace_bytes", "hk_bn_train_stats", "hk_bn_apply_fwd", "hk_bn_train_bwd",
+    "hk_pack_conv_weights_dgrad", "hk_zero_insert2x", "hk_conv_wgrad_workspace_bytes", "hk_conv_wgrad",
+    "hk_stem_wgrad_workspace_bytes", "hk_stem_wgrad", "hk_maxpool3x3s2_bwd", "hk_head_logits_fwd",
+    "hk_head_bwd_workspace_bytes", "hk_head_bwd",
 )
 
 
@@ -69,6 +74,37 @@ def _declare(lib):
     lib.hk_adam_step.argtypes = [vp, vp, vp, vp, C.c_longlong, f, f, f, f, f, i, vp]
     lib.hk_stem_fwd_u8.restype = i
     lib.hk_stem_fwd_u8.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
+    ll = C.c_longlong
+    lib.hk_stem_conv_fwd.restype = i
+    lib.hk_stem_conv_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp]
+    lib.hk_bn_workspace_bytes.restype = sz
+    lib.hk_bn_workspace_bytes.argtypes = [i]
+    lib.hk_bn_train_stats.restype = i
+    lib.hk_bn_train_stats.argtypes = [vp, ll, i, vp, vp, vp, vp, f, f, vp, vp, vp, vp, vp, sz, vp]
+    lib.hk_bn_apply_fwd.restype = i
+    lib.hk_bn_apply_fwd.argtypes = [vp, vp, vp, vp, i, vp, ll, i, vp]
+    lib.hk_bn_train_bwd.restype = i
+    lib.hk_bn_train_bwd.argtypes = [vp, vp, vp, vp, vp, vp, ll, i, vp, vp, i, vp, vp, vp, sz, vp]
+    lib.hk_pack_conv_weights_dgrad.restype = i
+    lib.hk_pack_conv_weights_dgrad.argtypes = [vp, i, i, i, i, vp, vp]
+    lib.hk_zero_insert2x.restype = i
+    lib.hk_zero_insert2x.argtypes = [vp, vp, i, i, i, i, vp]
+    lib.hk_conv_wgrad_workspace_bytes.restype = sz
+    lib.hk_conv_wgrad_workspace_bytes.argtypes = [C.POINTER(HkConvDesc)]
+    lib.hk_conv_wgrad.restype = i
+    lib.hk_conv_wgrad.argtypes = [C.POINTER(HkConvDesc), vp, vp, vp, i, vp, sz, vp]
+    lib.hk_stem_wgrad_workspace_bytes.restype = sz
+    lib.hk_stem_wgrad_workspace_bytes.argtypes = []
+    lib.hk_stem_wgrad.restype = i
+    lib.hk_stem_wgrad.argtypes = [vp, vp, vp, i, i, i, i, vp, sz, vp]
+    lib.hk_maxpool3x3s2_bwd.restype = i
+    lib.hk_maxpool3x3s2_bwd.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp]
+    lib.hk_head_logits_fwd.restype = i
+    lib.hk_head_logits_fwd.argtypes = [vp, i, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
+    lib.hk_head_bwd_workspace_bytes.restype = sz
+    lib.hk_head_bwd_workspace_bytes.argtypes = [i, i, i, i, i]
+    lib.hk_head_bwd.restype = i
+    lib.hk_head_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp, sz, vp]
     lib.hk_bce_workspace_bytes.restype = sz
     lib.hk_bce_workspace_bytes.argtypes = [C.c_longlong]
     lib.hk_bce_fwd_bwd.restype = i

@@ -136,7 +136,7 @@ __device__ __forceinline__ float sigmoid_f(float v) {
 // rows are staged in shared memory; no integer division anywhere.  FAST (bf16 mode): the vertical lerp is done once
 // per source column while staging (separable form); exact (fp32 mode): ATen's operation order
 // hy*(hx*a + lx*b) + ly*(hx*c + lx*d) is kept so the result tracks the reference to the last ulp or two.
-template <bool FAST>
+template <bool FAST, bool SIGMOID = true>
 __global__ void __launch_bounds__(256)
 head_upsample_sigmoid_kernel(const float* __restrict__ logits, float* __restrict__ heat, int h, int w, int H, int W,
                              int wq, float ry, float rx) {
@@ -171,7 +171,7 @@ head_upsample_sigmoid_kernel(const float* __restrict__ logits, float* __restrict
     float v;
     if (FAST) v = hx * srow[x0] + lx * srow[x1];
     else v = hy * (hx * srow[x0] + lx * srow[x1]) + ly * (hx * srow[w + x0] + lx * srow[w + x1]);
-    o[j] = sigmoid_f<FAST>(v);
+    o[j] = SIGMOID ? sigmoid_f<FAST>(v) : v;
   }
   float* dst = heat + ((size_t)map * H + Y) * W + xq * 4;
   if ((W & 3) == 0) {
@@ -198,8 +198,21 @@ static void launch_logits(const void* feat, const float* w_fc, const float* b_fc
 
 }  // namespace hk
 
+static int head_fwd_impl(const void* feat, int feat_dtype, const float* w_fc, const float* b_fc, float* logits_ws, float* heat, int B,
+                         int K, int C, int h, int w, int H, int W, bool sigmoid, void* stream);
+
 extern "C" int hk_head_fwd(const void* feat, int feat_dtype, const float* w_fc, const float* b_fc, float* logits_ws,
                            float* heat, int B, int K, int C, int h, int w, int H, int W, void* stream) {
+  return head_fwd_impl(feat, feat_dtype, w_fc, b_fc, logits_ws, heat, B, K, C, h, w, H, W, true, stream);
+}
+
+extern "C" int hk_head_logits_fwd(const void* feat, int feat_dtype, const float* w_fc, const float* b_fc, float* logits_ws,
+                                  float* logits_up, int B, int K, int C, int h, int w, int H, int W, void* stream) {
+  return head_fwd_impl(feat, feat_dtype, w_fc, b_fc, logits_ws, logits_up, B, K, C, h, w, H, W, false, stream);
+}
+
+static int head_fwd_impl(const void* feat, int feat_dtype, const float* w_fc, const float* b_fc, float* logits_ws, float* heat, int B,
+                         int K, int C, int h, int w, int H, int W, bool sigmoid, void* stream) {
   using namespace hk;
   HK_REQUIRE(feat && w_fc && b_fc && logits_ws && heat, "hk_head_fwd: null pointer");
   HK_REQUIRE(B > 0 && K > 0 && h > 0 && w > 0 && H > 0 && W > 0, "hk_head_fwd: bad shape");
@@ -224,7 +237,9 @@ extern "C" int hk_head_fwd(const void* feat, int feat_dtype, const float* w_fc, 
   if (threads > 256) threads = 256;
   dim3 grid(ceil_div(wq, threads), H, B * K);
   // bf16 features = throughput mode: separable lerp + ex2/rcp-approx sigmoid; fp32 features = correctness mode
-  if (feat_dtype == HK_BF16)
+  if (!sigmoid)  // training: upsampled logits in ATen's exact operation order; the sigmoid lives in hk_bce_fwd_bwd
+    head_upsample_sigmoid_kernel<false, false><<<grid, threads, (size_t)2 * w * sizeof(float), s>>>(logits_ws, heat, h, w, H, W, wq, ry, rx);
+  else if (feat_dtype == HK_BF16)
     head_upsample_sigmoid_kernel<true><<<grid, threads, (size_t)w * sizeof(float), s>>>(logits_ws, heat, h, w, H, W, wq, ry, rx);
   else
     head_upsample_sigmoid_kernel<false><<<grid, threads, (size_t)2 * w * sizeof(float), s>>>(logits_ws, heat, h, w, H, W, wq, ry, rx);

@@ -24,6 +24,22 @@ pack_weights_kernel(const float* __restrict__ w_oihw, OutT* __restrict__ w_out, 
   }
 }
 
+// Data-gradient weights: dX = conv(dY, W') with W'[ci, r', s', co] = W[co, ci, kh-1-r', kw-1-s'] (taps flipped, channel roles
+// swapped); same pad/dilation as the forward conv when pad == dil*(k-1)/2 (every conv of this network).
+__global__ void __launch_bounds__(256)
+pack_weights_dgrad_kernel(const float* __restrict__ w_oihw, __nv_bfloat16* __restrict__ w_out, int cout, int cin, int kh, int kw) {
+  const int khw = kh * kw;
+  const long long total = (long long)cout * cin * khw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // destination index: ((ci * khw + t') * cout + co)
+    const int co = (int)(i % cout);
+    const long long r = i / cout;
+    const int t = (int)(r % khw);
+    const int ci = (int)(r / khw);
+    w_out[i] = __float2bfloat16_rn(__ldg(w_oihw + ((size_t)co * cin + ci) * khw + (khw - 1 - t)));
+  }
+}
+
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                                const float* __restrict__ var, float eps, int cout, float* __restrict__ scale,
                                float* __restrict__ bias) {
@@ -65,4 +81,15 @@ extern "C" int hk_pack_conv_weights(const float* w_oihw, const float* bn_gamma, 
   if (rc) return rc;
   bn_fold_kernel<<<ceil_div(cout, 128), 128, 0, s>>>(bn_gamma, bn_beta, bn_mean, bn_var, bn_eps, cout, scale_out, bias_out);
   return check_launch("bn_fold_kernel");
+}
+
+extern "C" int hk_pack_conv_weights_dgrad(const float* w_oihw, int cout, int cin, int kh, int kw, void* w_out, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(w_oihw && w_out, "hk_pack_conv_weights_dgrad: null pointer");
+  HK_REQUIRE(cout > 0 && cin > 0 && kh > 0 && kw > 0, "hk_pack_conv_weights_dgrad: bad shape");
+  const long long total = (long long)cout * cin * kh * kw;
+  int blocks = (int)ceil_div_ll(total, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_weights_dgrad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_oihw, static_cast<__nv_bfloat16*>(w_out), cout, cin, kh, kw);
+  return check_launch("pack_weights_dgrad_kernel");
 }

@@ -40,6 +40,7 @@ struct StemTcArgs {
   __nv_bfloat16* y;  // (B,Ho,Wo,64) bf16
   int B, H, W, Ho, Wo;
   int tiles_x, tiles_per_img, num_tiles;
+  int relu;         // 1: ReLU in the epilogue (inference / folded BN); 0: raw affine output (train-mode BN follows)
   long long* dbg;  // optional phase timeline of CTA 0 (tools/diag_stem_timeline.py); null in production
 };
 #define ST_STAMP(slot)                                                                            \
@@ -262,7 +263,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(__uint_as_float(r[g * 8 + j]), sc[j], bi[j]), 0.f);
+        for (int j = 0; j < 8; ++j) {
+          v[j] = fmaf(__uint_as_float(r[g * 8 + j]), sc[j], bi[j]);
+          if (a.relu) v[j] = fmaxf(v[j], 0.f);
+        }
         *reinterpret_cast<uint4*>(my_row + ((((c >> 3) ^ sw) & 7) << 4)) =
             make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
       }
@@ -323,7 +327,7 @@ static long long* g_stem_dbg = nullptr;
 __attribute__((visibility("default"))) void hk_debug_set_stem_timeline(long long* dev_buf) { g_stem_dbg = dev_buf; }
 
 static int stem_launch(const void* x, bool u8, const void* w_packed, const float* scale, const float* bias, void* y_nhwc, int B,
-                       int H, int W, void* stream) {
+                       int H, int W, void* stream, int relu = 1) {
   using namespace hk;
   HK_REQUIRE(x && w_packed && scale && bias && y_nhwc, "hk_stem_fwd: null pointer");
   HK_REQUIRE(B > 0 && H >= 7 && W >= 7, "hk_stem_fwd: bad shape");
@@ -357,6 +361,7 @@ static int stem_launch(const void* x, bool u8, const void* w_packed, const float
   a.x = x; a.scale = scale; a.bias = bias; a.y = static_cast<__nv_bfloat16*>(y_nhwc);
   a.B = B; a.H = H; a.W = W;
   a.dbg = g_stem_dbg;
+  a.relu = relu;
   a.Ho = (H + 6 - 7) / 2 + 1;
   a.Wo = (W + 6 - 7) / 2 + 1;
   a.tiles_x = ceil_div(a.Wo, ST_TILE_W);
@@ -383,6 +388,11 @@ static int stem_launch(const void* x, bool u8, const void* w_packed, const float
 int hk_stem_fwd(const float* x_nchw, const void* w_packed, const float* scale, const float* bias, void* y_nhwc, int B, int H,
                 int W, void* stream) {
   return stem_launch(x_nchw, false, w_packed, scale, bias, y_nhwc, B, H, W, stream);
+}
+
+int hk_stem_conv_fwd(const float* x_nchw, const void* w_packed, const float* scale, const float* bias, void* y_nhwc, int B, int H,
+                     int W, int relu, void* stream) {
+  return stem_launch(x_nchw, false, w_packed, scale, bias, y_nhwc, B, H, W, stream, relu);
 }
 
 int hk_stem_fwd_u8(const uint8_t* x_nhwc_u8, const void* w_packed, const float* scale, const float* bias, void* y_nhwc, int B,

@@ -1,0 +1,384 @@
+// Backward of the small layers around the backbone convolutions:
+//   * MaxPool2d(3, 2, 1) backward                         (autograd of src/resnet.py:141,202)
+//   * zero insertion (x2) -- turns the data gradient of a stride-2 conv into a stride-1 conv over a dilated grid
+//   * head backward: bilinear-upsample(align_corners) backward restricted to the K live channels, then the backward
+//     of the K-row 1x1 scoring conv                       (autograd of src/resnet_dilated.py:27, src/resnet.py:215)
+//   * stem weight gradient (7x7 s2, Cin=3): CUDA-core kernel, the K dimension (147) is too thin for TMA im2col
+// All deterministic (gather formulations / fixed-order partial sums; no atomics).
+#include "hk_common.cuh"
+
+namespace hk {
+
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  unpack_bf16x2(u.x, f[0], f[1]);
+  unpack_bf16x2(u.y, f[2], f[3]);
+  unpack_bf16x2(u.z, f[4], f[5]);
+  unpack_bf16x2(u.w, f[6], f[7]);
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+// ---------------------------------------------------------------- maxpool backward (gather)
+// dx[b,iy,ix,c] = sum over the (<= 4) windows containing (iy,ix) of dout[window] * [argmax(window) == (iy,ix)],
+// argmax = first maximum in (r, s) scan order among in-bounds taps, as ATen's max_pool2d_with_indices picks it.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
+                                                         __nv_bfloat16* __restrict__ dx, int B, int H, int W, int C, int Ho, int Wo) {
+  const int CG = C >> 3;
+  const long long total = (long long)B * H * W * CG;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    long long p = i / CG;
+    const int ix = (int)(p % W);
+    p /= W;
+    const int iy = (int)(p % H);
+    const int b = (int)(p / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int oy_lo = max(0, iy / 2), oy_hi = min(Ho - 1, (iy + 1) / 2);   // windows with 2*oy-1 <= iy <= 2*oy+1
+    const int ox_lo = max(0, ix / 2), ox_hi = min(Wo - 1, (ix + 1) / 2);
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        float best[8];
+        int who[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; who[j] = -1; }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int yy = 2 * oy - 1 + r;
+          if (yy < 0 || yy >= H) continue;
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int xx = 2 * ox - 1 + s;
+            if (xx < 0 || xx >= W) continue;
+            float v[8];
+            ld8(x + (((long long)b * H + yy) * W + xx) * C + cg * 8, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (v[j] > best[j] || who[j] < 0) { best[j] = v[j]; who[j] = r * 3 + s; }
+          }
+        }
+        const int me = (iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1));
+        float g[8];
+        ld8(dout + (((long long)b * Ho + oy) * Wo + ox) * C + cg * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (who[j] == me) acc[j] += g[j];
+      }
+    }
+    st8(dx + i * 8, acc);
+  }
+}
+
+// ---------------------------------------------------------------- zero insertion x2
+__global__ void __launch_bounds__(256) zero_insert2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int h,
+                                                           int w, int C) {
+  const int CG = C >> 3;
+  const int H = 2 * h, W = 2 * w;
+  const long long total = (long long)B * H * W * CG;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    long long p = i / CG;
+    const int X = (int)(p % W);
+    p /= W;
+    const int Y = (int)(p % H);
+    const int b = (int)(p / H);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (((X | Y) & 1) == 0) v = __ldg(reinterpret_cast<const uint4*>(in + (((long long)b * h + (Y >> 1)) * w + (X >> 1)) * C + cg * 8));
+    *reinterpret_cast<uint4*>(out + i * 8) = v;
+  }
+}
+
+// ---------------------------------------------------------------- head backward
+// dl[m, y, x] = sum_{Y,X} g[m, Y, X] * wy(Y, y) * wx(X, x), the transpose of ATen's align_corners bilinear
+// (src = scale*dst, i0 = (int)src, i1 = i0 + (i0 < in-1), l1 = src - i0, l0 = 1 - l1).  One thread per low-res pixel.
+__global__ void __launch_bounds__(128) upsample_bwd_kernel(const float* __restrict__ g, float* __restrict__ dl, int maps, int h, int w, int H,
+                                                          int W, float ry, float rx) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= maps * h * w) return;
+  const int x = idx % w, y = (idx / w) % h, m = idx / (w * h);
+  // candidate source rows: ry*Y in (y-1, y+1)
+  const float inv_ry = ry > 0.f ? 1.f / ry : 0.f, inv_rx = rx > 0.f ? 1.f / rx : 0.f;
+  int Ylo = ry > 0.f ? max(0, (int)floorf((float)(y - 1) * inv_ry) - 1) : 0;
+  int Yhi = ry > 0.f ? min(H - 1, (int)ceilf((float)(y + 1) * inv_ry) + 1) : H - 1;
+  int Xlo = rx > 0.f ? max(0, (int)floorf((float)(x - 1) * inv_rx) - 1) : 0;
+  int Xhi = rx > 0.f ? min(W - 1, (int)ceilf((float)(x + 1) * inv_rx) + 1) : W - 1;
+  const float* gm = g + (size_t)m * H * W;
+  float acc = 0.f;
+  for (int Y = Ylo; Y <= Yhi; ++Y) {
+    const float sy = ry * (float)Y;
+    const int y0 = min((int)sy, h - 1);
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+    const float ly = sy - (float)y0, hy = 1.0f - ly;
+    float wy = 0.f;
+    if (y0 == y) wy += hy;
+    if (y1 == y) wy += ly;
+    if (wy == 0.f) continue;
+    float rowacc = 0.f;
+    for (int X = Xlo; X <= Xhi; ++X) {
+      const float sx = rx * (float)X;
+      const int x0 = min((int)sx, w - 1);
+      const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+      const float lx = sx - (float)x0, hx = 1.0f - lx;
+      float wx = 0.f;
+      if (x0 == x) wx += hx;
+      if (x1 == x) wx += lx;
+      if (wx != 0.f) rowacc = fmaf(__ldg(gm + (size_t)Y * W + X), wx, rowacc);
+    }
+    acc = fmaf(rowacc, wy, acc);
+  }
+  dl[idx] = acc;
+}
+
+// dfeat[p, c] = sum_k dl[b, k, pix] * w[k, c]   (bf16 NHWC out); one thread per (pixel, 8 channels)
+__global__ void __launch_bounds__(256) fc_bwd_dfeat_kernel(const float* __restrict__ dl, const float* __restrict__ w_fc,
+                                                          __nv_bfloat16* __restrict__ dfeat, int B, int K, int C, int hw) {
+  const int CG = C >> 3;
+  const long long total = (long long)B * hw * CG;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    const long long p = i / CG;
+    const int b = (int)(p / hw), pix = (int)(p - (long long)b * hw);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < K; ++k) {
+      const float d = __ldg(dl + ((size_t)b * K + k) * hw + pix);
+      const float4 a = __ldg(reinterpret_cast<const float4*>(w_fc + (size_t)k * C + cg * 8));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(w_fc + (size_t)k * C + cg * 8 + 4));
+      acc[0] = fmaf(d, a.x, acc[0]); acc[1] = fmaf(d, a.y, acc[1]); acc[2] = fmaf(d, a.z, acc[2]); acc[3] = fmaf(d, a.w, acc[3]);
+      acc[4] = fmaf(d, c.x, acc[4]); acc[5] = fmaf(d, c.y, acc[5]); acc[6] = fmaf(d, c.z, acc[6]); acc[7] = fmaf(d, c.w, acc[7]);
+    }
+    st8(dfeat + i * 8, acc);
+  }
+}
+
+// partial[blk][k][c] = sum over the block's pixel slab of dl[b,k,pix] * feat[p,c];  thread = one channel pair, 4 keypoints at a time
+constexpr int FCW_SLAB = 64;
+__global__ void __launch_bounds__(256) fc_bwd_dw_partial_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ feat,
+                                                               float* __restrict__ partial, int B, int K, int C, int hw) {
+  __shared__ float sdl[4][FCW_SLAB];
+  const long long P = (long long)B * hw;
+  const long long p0 = (long long)blockIdx.x * FCW_SLAB;
+  const int n = (int)min((long long)FCW_SLAB, P - p0);
+  for (int kg = 0; kg < K; kg += 4) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 4 * FCW_SLAB; t += blockDim.x) {
+      const int j = t / FCW_SLAB, q = t - j * FCW_SLAB;
+      float v = 0.f;
+      if (q < n && kg + j < K) {
+        const long long p = p0 + q;
+        const int b = (int)(p / hw), pix = (int)(p - (long long)b * hw);
+        v = dl[((size_t)b * K + kg + j) * hw + pix];
+      }
+      sdl[j][q] = v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
+      float acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+      for (int q = 0; q < n; ++q) {
+        float f0, f1;
+        unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(feat + (p0 + q) * C + c)), f0, f1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[j][0] = fmaf(sdl[j][q], f0, acc[j][0]);
+          acc[j][1] = fmaf(sdl[j][q], f1, acc[j][1]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (kg + j < K) {
+          partial[((size_t)blockIdx.x * K + kg + j) * C + c] = acc[j][0];
+          partial[((size_t)blockIdx.x * K + kg + j) * C + c + 1] = acc[j][1];
+        }
+    }
+  }
+}
+// dw[k][c] = sum_blk partial;  db[k] = sum_p dl[b,k,pix]   (grid: K blocks)
+__global__ void __launch_bounds__(256) fc_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ dl,
+                                                             float* __restrict__ dw, float* __restrict__ db, int B, int K, int C, int hw,
+                                                             int accumulate) {
+  const int k = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += (double)partial[((size_t)b * K + k) * C + c];
+    dw[(size_t)k * C + c] = (accumulate ? dw[(size_t)k * C + c] : 0.f) + (float)s;
+  }
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int b = 0; b < B; ++b)
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) s += (double)dl[((size_t)b * K + k) * hw + i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) db[k] = (accumulate ? db[k] : 0.f) + (float)red[0];
+}
+
+// ---------------------------------------------------------------- stem weight gradient
+// dw[co][c][r][s] = sum_{b,oy,ox} dy[b,oy,ox,co] * x[b,c,2oy-3+r,2ox-3+s]      (x fp32 NCHW, dy bf16 NHWC)
+// One CTA per 8x16 output tile (persistent): input patch (3 x 21 x 37) and the dy tile (128 px x 64 co) in shared memory.  Thread t
+// owns the 4 output channels co = 4*(t&15).. and the taps k = (t>>4) + 16*i (k = (c*7 + r)*7 + s, i < 10): per pixel one float4 of dy
+// and 10 broadcast patch loads feed 40 FMAs; the 40 accumulators stay in registers over all tiles of the CTA.
+constexpr int SW_TH = 8, SW_TW = 16, SW_PH = 2 * SW_TH + 5, SW_PW = 2 * SW_TW + 5;  // 21 x 37
+constexpr int SW_KPT = 10;                                                          // ceil(147 / 16)
+__global__ void __launch_bounds__(256) stem_wgrad_partial_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                                float* __restrict__ partial, int B, int H, int W, int Ho, int Wo,
+                                                                int tiles_x, int tiles_per_img, int num_tiles) {
+  __shared__ float sx[3 * SW_PH * SW_PW];
+  __shared__ __align__(16) float sdy[SW_TH * SW_TW][64 + 4];
+  const int quad = threadIdx.x & 15, kg = threadIdx.x >> 4;
+  int koff[SW_KPT];
+#pragma unroll
+  for (int i = 0; i < SW_KPT; ++i) {
+    const int k = min(kg + 16 * i, 146);
+    const int c = k / 49, rs = k - c * 49, r = rs / 7, sft = rs - r * 7;
+    koff[i] = c * (SW_PH * SW_PW) + r * SW_PW + sft;
+  }
+  float acc[SW_KPT][4];
+#pragma unroll
+  for (int i = 0; i < SW_KPT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    const int oy0 = ty * SW_TH, ox0 = tx * SW_TW;
+    const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
+    __syncthreads();
+    for (int t = threadIdx.x; t < 3 * SW_PH * SW_PW; t += blockDim.x) {
+      const int c = t / (SW_PH * SW_PW), r2 = t - c * (SW_PH * SW_PW);
+      const int py = r2 / SW_PW, px = r2 - py * SW_PW;
+      const int iy = iy0 + py, ix = ix0 + px;
+      sx[t] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + (((size_t)b * 3 + c) * H + iy) * W + ix) : 0.f;
+    }
+    for (int t = threadIdx.x; t < SW_TH * SW_TW * 8; t += blockDim.x) {
+      const int pix = t >> 3, cg = t & 7;
+      const int oy = oy0 + pix / SW_TW, ox = ox0 + pix % SW_TW;
+      float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (oy < Ho && ox < Wo) ld8(dy + (((size_t)b * Ho + oy) * Wo + ox) * 64 + cg * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sdy[pix][cg * 8 + j] = v[j];
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int pix = 0; pix < SW_TH * SW_TW; ++pix) {
+      const float4 d = *reinterpret_cast<const float4*>(&sdy[pix][quad * 4]);
+      const int pbase = 2 * (pix / SW_TW) * SW_PW + 2 * (pix % SW_TW);
+#pragma unroll
+      for (int i = 0; i < SW_KPT; ++i) {
+        const float xv = sx[koff[i] + pbase];
+        acc[i][0] = fmaf(d.x, xv, acc[i][0]);
+        acc[i][1] = fmaf(d.y, xv, acc[i][1]);
+        acc[i][2] = fmaf(d.z, xv, acc[i][2]);
+        acc[i][3] = fmaf(d.w, xv, acc[i][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < SW_KPT; ++i) {
+    const int k = kg + 16 * i;
+    if (k < 147) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) partial[(size_t)blockIdx.x * (147 * 64) + k * 64 + quad * 4 + j] = acc[i][j];
+    }
+  }
+}
+// dw (64,3,7,7) OIHW: index co*147 + k
+__global__ void stem_wgrad_finalize_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ dw, int accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= 147 * 64) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += (double)partial[(size_t)b * (147 * 64) + j];
+  const int k = j >> 6, co = j & 63;
+  float* dst = dw + co * 147 + k;
+  *dst = (accumulate ? *dst : 0.f) + (float)s;
+}
+
+static int grid_for(long long n, int threads) {
+  long long blocks = ceil_div_ll(n, threads);
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace hk
+
+extern "C" {
+
+int hk_maxpool3x3s2_bwd(const void* dout, const void* x, void* dx, int B, int H, int W, int C, int Ho, int Wo, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(dout && x && dx, "hk_maxpool3x3s2_bwd: null pointer");
+  HK_REQUIRE(B > 0 && H > 0 && W > 0 && C >= 8 && (C & 7) == 0 && Ho == (H + 2 - 3) / 2 + 1 && Wo == (W + 2 - 3) / 2 + 1,
+             "hk_maxpool3x3s2_bwd: bad shape");
+  const long long total = (long long)B * H * W * (C >> 3);
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dout),
+                                                                         static_cast<const __nv_bfloat16*>(x),
+                                                                         static_cast<__nv_bfloat16*>(dx), B, H, W, C, Ho, Wo);
+  return check_launch("maxpool_bwd_kernel");
+}
+
+int hk_zero_insert2x(const void* in, void* out, int B, int h, int w, int C, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(in && out && B > 0 && h > 0 && w > 0 && C >= 8 && (C & 7) == 0, "hk_zero_insert2x: bad argument");
+  const long long total = (long long)B * 2 * h * 2 * w * (C >> 3);
+  zero_insert2x_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(in),
+                                                                           static_cast<__nv_bfloat16*>(out), B, h, w, C);
+  return check_launch("zero_insert2x_kernel");
+}
+
+size_t hk_head_bwd_workspace_bytes(int B, int K, int C, int h, int w) {
+  const long long P = (long long)B * h * w;
+  const long long nblk = (P + hk::FCW_SLAB - 1) / hk::FCW_SLAB;
+  return (size_t)nblk * K * C * sizeof(float);
+}
+
+int hk_head_bwd(const float* g_up, const void* feat, const float* w_fc, float* dlogits_ws, void* dfeat, float* dw_fc, float* db_fc,
+                int accumulate, int B, int K, int C, int h, int w, int H, int W, void* ws, size_t ws_bytes, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(g_up && feat && w_fc && dlogits_ws && dfeat && dw_fc && db_fc && ws, "hk_head_bwd: null pointer");
+  HK_REQUIRE(B > 0 && K > 0 && C >= 8 && (C & 7) == 0 && h > 0 && w > 0 && H > 0 && W > 0, "hk_head_bwd: bad shape");
+  HK_REQUIRE(ws_bytes >= hk_head_bwd_workspace_bytes(B, K, C, h, w), "hk_head_bwd: workspace too small");
+  HK_REQUIRE((long long)B * K * h * w < 0x7fffffffLL, "hk_head_bwd: too many low-res elements");
+  cudaStream_t s = as_stream(stream);
+  const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
+  const float rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const int n = B * K * h * w;
+  upsample_bwd_kernel<<<ceil_div(n, 128), 128, 0, s>>>(g_up, dlogits_ws, B * K, h, w, H, W, ry, rx);
+  int rc = check_launch("upsample_bwd_kernel");
+  if (rc) return rc;
+  const int hw = h * w;
+  fc_bwd_dfeat_kernel<<<grid_for((long long)B * hw * (C >> 3), 256), 256, 0, s>>>(dlogits_ws, w_fc, static_cast<__nv_bfloat16*>(dfeat), B, K,
+                                                                                 C, hw);
+  rc = check_launch("fc_bwd_dfeat_kernel");
+  if (rc) return rc;
+  const int nblk = (int)(((long long)B * hw + FCW_SLAB - 1) / FCW_SLAB);
+  fc_bwd_dw_partial_kernel<<<nblk, 256, 0, s>>>(dlogits_ws, static_cast<const __nv_bfloat16*>(feat), static_cast<float*>(ws), B, K, C, hw);
+  rc = check_launch("fc_bwd_dw_partial_kernel");
+  if (rc) return rc;
+  fc_bwd_finalize_kernel<<<K, 256, 0, s>>>(static_cast<const float*>(ws), nblk, dlogits_ws, dw_fc, db_fc, B, K, C, hw, accumulate);
+  return check_launch("fc_bwd_finalize_kernel");
+}
+
+size_t hk_stem_wgrad_workspace_bytes(void) { return (size_t)hk::sm_count() * 2 * 147 * 64 * sizeof(float); }
+
+int hk_stem_wgrad(const float* x_nchw, const void* dy_nhwc, float* dw_oihw, int accumulate, int B, int H, int W, void* ws,
+                  size_t ws_bytes, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(x_nchw && dy_nhwc && dw_oihw && ws, "hk_stem_wgrad: null pointer");
+  HK_REQUIRE(B > 0 && H >= 7 && W >= 7, "hk_stem_wgrad: bad shape");
+  HK_REQUIRE(ws_bytes >= hk_stem_wgrad_workspace_bytes(), "hk_stem_wgrad: workspace too small");
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const int tiles_x = ceil_div(Wo, SW_TW), tiles_y = ceil_div(Ho, SW_TH);
+  const int num_tiles = B * tiles_x * tiles_y;
+  int blocks = sm_count() * 2;
+  if (blocks > num_tiles) blocks = num_tiles;
+  stem_wgrad_partial_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x_nchw, static_cast<const __nv_bfloat16*>(dy_nhwc),
+                                                                  static_cast<float*>(ws), B, H, W, Ho, Wo, tiles_x, tiles_x * tiles_y,
+                                                                  num_tiles);
+  int rc = check_launch("stem_wgrad_partial_kernel");
+  if (rc) return rc;
+  stem_wgrad_finalize_kernel<<<ceil_div(147 * 64, 256), 256, 0, as_stream(stream)>>>(static_cast<const float*>(ws), blocks, dw_oihw, accumulate);
+  return check_launch("stem_wgrad_finalize_kernel");
+}
+
+}  // extern "C"

@@ -199,3 +199,159 @@ def bce_fwd_bwd(pred: torch.Tensor, target: Optional[torch.Tensor] = None, uv: O
     check(lib().hk_bce_fwd_bwd(ptr(pred), int(pred_is_logits), ptr(target), tcode, ptr(uv32), B, K, H, W, C.c_float(float(sigma)), ptr(loss),
                                ptr(grad), ptr(ws), ws.numel(), stream_ptr()), "hk_bce_fwd_bwd")
     return loss, grad
+
+
+# ------------------------------------------------------------------------------------------------ training kernels
+def stem_conv(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, relu: bool,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Stem conv7x7 s2 on tcgen05 with an explicit ReLU switch (relu=False: raw output for train-mode BN)."""
+    _need_cuda(x, w_packed, scale, bias, out)
+    if x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3 or not x.is_contiguous():
+        raise ValueError("stem_conv needs a contiguous (B,3,H,W) fp32 input")
+    B, _, H, W = x.shape
+    Ho, Wo = conv_out_hw(H, W, 7, 2, 3, 1)
+    if out is None:
+        out = torch.empty((B, Ho, Wo, 64), device=x.device, dtype=torch.bfloat16)
+    check(lib().hk_stem_conv_fwd(ptr(x), ptr(w_packed), ptr(scale), ptr(bias), ptr(out), B, H, W, int(relu), stream_ptr()),
+          "hk_stem_conv_fwd")
+    return out
+
+
+def bn_workspace(C_: int, device, extra_coef: bool = True) -> torch.Tensor:
+    n = int(lib().hk_bn_workspace_bytes(C_)) + (3 * C_ * 4 if extra_coef else 0)
+    return torch.empty(n, device=device, dtype=torch.uint8)
+
+
+def bn_train_stats(y: torch.Tensor, gamma, beta, running_mean, running_var, momentum: float, eps: float,
+                   mean: torch.Tensor, invstd: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, ws: torch.Tensor) -> None:
+    """y (...,C) bf16 NHWC -> batch mean / invstd + fused affine (scale, shift); running stats updated in place."""
+    _need_cuda(y, mean, invstd, scale, shift, ws)
+    Cc = y.shape[-1]
+    P = y.numel() // Cc
+    check(lib().hk_bn_train_stats(ptr(y), C.c_longlong(P), Cc, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+                                  C.c_float(momentum), C.c_float(eps), ptr(mean), ptr(invstd), ptr(scale), ptr(shift), ptr(ws),
+                                  ws.numel(), stream_ptr()), "hk_bn_train_stats")
+
+
+def bn_apply(y: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, relu: bool, residual: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(y, scale, shift, residual, out)
+    Cc = y.shape[-1]
+    P = y.numel() // Cc
+    if out is None:
+        out = torch.empty_like(y)
+    check(lib().hk_bn_apply_fwd(ptr(y), ptr(scale), ptr(shift), ptr(residual), int(relu), ptr(out), C.c_longlong(P), Cc, stream_ptr()),
+          "hk_bn_apply_fwd")
+    return out
+
+
+def bn_train_bwd(dout: torch.Tensor, out_mask: Optional[torch.Tensor], y: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor,
+                 gamma: Optional[torch.Tensor], dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor], dy: torch.Tensor,
+                 ws: torch.Tensor, dmasked: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    _need_cuda(dout, out_mask, y, mean, invstd, dy, ws, dmasked)
+    Cc = y.shape[-1]
+    P = y.numel() // Cc
+    check(lib().hk_bn_train_bwd(ptr(dout), ptr(out_mask), ptr(y), ptr(mean), ptr(invstd), ptr(gamma), C.c_longlong(P), Cc, ptr(dgamma),
+                                ptr(dbeta), int(accumulate), ptr(dy), ptr(dmasked), ptr(ws), ws.numel(), stream_ptr()), "hk_bn_train_bwd")
+    return dy
+
+
+def pack_conv_weights_dgrad(w_oihw: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """OIHW fp32 -> (cin, kh, kw, cout) bf16 with flipped taps: the weights of the data-gradient convolution."""
+    _need_cuda(w_oihw, out)
+    w = w_oihw.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        raise ValueError("pack_conv_weights_dgrad needs a contiguous fp32 OIHW weight")
+    cout, cin, kh, kw = w.shape
+    if out is None:
+        out = torch.empty((cin, kh, kw, cout), device=w.device, dtype=torch.bfloat16)
+    check(lib().hk_pack_conv_weights_dgrad(ptr(w), cout, cin, kh, kw, ptr(out), stream_ptr()), "hk_pack_conv_weights_dgrad")
+    return out
+
+
+def zero_insert2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, out)
+    B, h, w, Cc = x.shape
+    if out is None:
+        out = torch.empty((B, 2 * h, 2 * w, Cc), device=x.device, dtype=x.dtype)
+    check(lib().hk_zero_insert2x(ptr(x), ptr(out), B, h, w, Cc, stream_ptr()), "hk_zero_insert2x")
+    return out
+
+
+def _conv_desc(B, H, W, cin, cout, k, stride, pad, dil):
+    Ho, Wo = conv_out_hw(H, W, k, stride, pad, dil)
+    return HkConvDesc(B, H, W, cin, Ho, Wo, cout, k, k, stride, pad, dil, 0, HK_BF16, HK_BF16, 0, HK_CONV_TCGEN05), Ho, Wo
+
+
+def conv_wgrad_workspace_bytes(B, H, W, cin, cout, k, stride, pad, dil) -> int:
+    d, _, _ = _conv_desc(B, H, W, cin, cout, k, stride, pad, dil)
+    return int(lib().hk_conv_wgrad_workspace_bytes(C.byref(d)))
+
+
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, k: int, stride: int, pad: int, dil: int,
+               ws: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """dw (cout,cin,k,k) fp32 (+)= conv weight gradient from x (B,H,W,cin) bf16 and dy (B,Ho,Wo,cout) bf16 (tcgen05)."""
+    _need_cuda(x, dy, dw, ws)
+    B, H, W, cin = x.shape
+    cout = dy.shape[3]
+    d, Ho, Wo = _conv_desc(B, H, W, cin, cout, k, stride, pad, dil)
+    if tuple(dy.shape) != (B, Ho, Wo, cout) or tuple(dw.shape) != (cout, cin, k, k):
+        raise ValueError(f"conv_wgrad shape mismatch: dy {tuple(dy.shape)} dw {tuple(dw.shape)}")
+    if not (x.is_contiguous() and dy.is_contiguous() and dw.is_contiguous()) or dw.dtype != torch.float32:
+        raise ValueError("conv_wgrad needs contiguous tensors and an fp32 gradient")
+    nbytes = int(lib().hk_conv_wgrad_workspace_bytes(C.byref(d)))
+    if ws is None:
+        ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    check(lib().hk_conv_wgrad(C.byref(d), ptr(x), ptr(dy), ptr(dw), int(accumulate), ptr(ws), ws.numel(), stream_ptr()), "hk_conv_wgrad")
+    return dw
+
+
+def stem_wgrad(x_nchw: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, ws: Optional[torch.Tensor] = None,
+               accumulate: bool = False) -> torch.Tensor:
+    _need_cuda(x_nchw, dy, dw, ws)
+    B, _, H, W = x_nchw.shape
+    if ws is None:
+        ws = torch.empty(int(lib().hk_stem_wgrad_workspace_bytes()), device=dy.device, dtype=torch.uint8)
+    check(lib().hk_stem_wgrad(ptr(x_nchw), ptr(dy), ptr(dw), int(accumulate), B, H, W, ptr(ws), ws.numel(), stream_ptr()), "hk_stem_wgrad")
+    return dw
+
+
+def maxpool3x3s2_bwd(dout: torch.Tensor, x: torch.Tensor, dx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(dout, x, dx)
+    B, H, W, Cc = x.shape
+    Ho, Wo = dout.shape[1], dout.shape[2]
+    if dx is None:
+        dx = torch.empty_like(x)
+    check(lib().hk_maxpool3x3s2_bwd(ptr(dout), ptr(x), ptr(dx), B, H, W, Cc, Ho, Wo, stream_ptr()), "hk_maxpool3x3s2_bwd")
+    return dx
+
+
+def head_logits(feat: torch.Tensor, w_fc: torch.Tensor, b_fc: torch.Tensor, H: int, W: int, out: Optional[torch.Tensor] = None,
+                logits_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B,h,w,C) features -> (B,K,H,W) fp32 upsampled LOGITS (no sigmoid): the training-side head."""
+    _need_cuda(feat, w_fc, b_fc, out, logits_ws)
+    B, h, w, Cc = feat.shape
+    K = w_fc.shape[0]
+    if out is None:
+        out = torch.empty((B, K, H, W), device=feat.device, dtype=torch.float32)
+    if logits_ws is None:
+        logits_ws = torch.empty((B, K, h, w), device=feat.device, dtype=torch.float32)
+    check(lib().hk_head_logits_fwd(ptr(feat), dtype_code(feat.dtype), ptr(w_fc), ptr(b_fc), ptr(logits_ws), ptr(out), B, K, Cc, h, w,
+                                   H, W, stream_ptr()), "hk_head_logits_fwd")
+    return out
+
+
+def head_bwd(g_up: torch.Tensor, feat: torch.Tensor, w_fc: torch.Tensor, dfeat: torch.Tensor, dw_fc: torch.Tensor, db_fc: torch.Tensor,
+             dlogits_ws: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None, accumulate: bool = False):
+    """Backward of head_logits: g_up (B,K,H,W) fp32 -> dfeat (B,h,w,C) bf16, dw_fc (K,C) fp32, db_fc (K) fp32."""
+    _need_cuda(g_up, feat, w_fc, dfeat, dw_fc, db_fc, dlogits_ws, ws)
+    B, K, H, W = g_up.shape
+    _, h, w, Cc = feat.shape
+    if dlogits_ws is None:
+        dlogits_ws = torch.empty((B, K, h, w), device=feat.device, dtype=torch.float32)
+    nbytes = int(lib().hk_head_bwd_workspace_bytes(B, K, Cc, h, w))
+    if ws is None:
+        ws = torch.empty(nbytes, device=feat.device, dtype=torch.uint8)
+    check(lib().hk_head_bwd(ptr(g_up), ptr(feat), ptr(w_fc), ptr(dlogits_ws), ptr(dfeat), ptr(dw_fc), ptr(db_fc), int(accumulate), B, K,
+                            Cc, h, w, H, W, ptr(ws), ws.numel(), stream_ptr()), "hk_head_bwd")
+    return dfeat, dw_fc, db_fc

@@ -166,6 +166,66 @@ HK_API int hk_bce_fwd_bwd(const float* pred, int pred_is_logits, const void* tar
 HK_API int hk_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                         float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
 
+/* ---- training: backbone forward in train() mode and its backward ----
+ * Replaces what torch autograd does for train.py:33-36 between the input batch and the parameter gradients.  Activations are
+ * NHWC bf16 (P = B*H*W rows of C channels), statistics / parameters / parameter gradients fp32.  Every reduction is a fixed-order
+ * two-level sum (deterministic).  Convolutions in training reuse hk_conv_bn_act_fwd with scale = 1, bias = 0, relu = 0 (raw conv
+ * output); the data gradient of a conv is hk_conv_bn_act_fwd on weights repacked by hk_pack_conv_weights_dgrad.
+ */
+/* Stem conv with an explicit ReLU switch (relu = 0: raw conv output for train-mode BN).  src/resnet.py:137,199. */
+HK_API int hk_stem_conv_fwd(const float* x_nchw, const void* w_packed, const float* scale, const float* bias, void* y_nhwc,
+                            int B, int H, int W, int relu, void* stream);
+
+/* nn.BatchNorm2d in train() mode, forward statistics (src/resnet.py:46,49,139,187 under model.train()).
+ *   y (P,C) bf16 raw conv output -> mean, invstd (C) fp32 (biased variance, eps inside the sqrt), and the fused affine of the
+ *   apply pass: scale = gamma*invstd, shift = beta - mean*scale.  running_mean/var (nullable) are updated in place:
+ *   r = (1-momentum)*r + momentum*stat, with the UNBIASED variance, as torch does.  ws: hk_bn_workspace_bytes(C). */
+HK_API size_t hk_bn_workspace_bytes(int C);
+HK_API int hk_bn_train_stats(const void* y, long long P, int C, const float* gamma, const float* beta, float* running_mean,
+                             float* running_var, float momentum, float eps, float* mean_out, float* invstd_out,
+                             float* scale_out, float* shift_out, void* ws, size_t ws_bytes, void* stream);
+/* out = relu?(y*scale + shift [+ residual])  (BN apply + the in-place add and ReLU of BasicBlock.forward, src/resnet.py:64-67) */
+HK_API int hk_bn_apply_fwd(const void* y, const float* scale, const float* shift, const void* residual_or_null, int relu,
+                           void* out, long long P, int C, void* stream);
+/* Backward of ReLU (mask from the saved post-ReLU output; NULL = no ReLU) + train-mode BatchNorm:
+ *   d' = dout*[out>0]; dbeta = sum d'; dgamma = sum d'*xhat; dy = gamma*invstd*(d' - dbeta/P - xhat*dgamma/P)
+ *   dmasked_or_null receives d' (the gradient of the shortcut branch).  accumulate != 0 adds to dgamma/dbeta.
+ *   ws: hk_bn_workspace_bytes(C) + 3*C*4 bytes. */
+HK_API int hk_bn_train_bwd(const void* dout, const void* out_mask_or_null, const void* y, const float* mean, const float* invstd,
+                           const float* gamma, long long P, int C, float* dgamma, float* dbeta, int accumulate, void* dy,
+                           void* dmasked_or_null, void* ws, size_t ws_bytes, void* stream);
+
+/* Conv weights for the data gradient: (cout,cin,kh,kw) fp32 -> (cin, kh, kw, cout) bf16 with the taps flipped. */
+HK_API int hk_pack_conv_weights_dgrad(const float* w_oihw, int cout, int cin, int kh, int kw, void* w_out, void* stream);
+/* (B,h,w,C) bf16 -> (B,2h,2w,C) with the values at even (y,x) and zeros elsewhere: the data gradient of a stride-2 conv is the
+ * stride-1 data-gradient conv over this grid. */
+HK_API int hk_zero_insert2x(const void* in, void* out, int B, int h, int w, int C, void* stream);
+
+/* Conv weight gradient on tcgen05 (MN-major operands straight from the NHWC activations):
+ *   dw[co,ci,r,s] (+)= sum_{b,oy,ox} dy[b,oy,ox,co] * x[b, oy*stride-pad+r*dil, ox*stride-pad+s*dil, ci]
+ *   desc describes the FORWARD conv (x = its input, dy = gradient of its raw output); dw is OIHW fp32.
+ *   ws: hk_conv_wgrad_workspace_bytes(desc) bytes of split-K partials. */
+HK_API size_t hk_conv_wgrad_workspace_bytes(const HkConvDesc* desc);
+HK_API int hk_conv_wgrad(const HkConvDesc* desc, const void* x, const void* dy, float* dw_oihw, int accumulate, void* ws,
+                         size_t ws_bytes, void* stream);
+/* Stem (7x7 s2, Cin=3) weight gradient from the fp32 NCHW input and the bf16 NHWC output gradient. */
+HK_API size_t hk_stem_wgrad_workspace_bytes(void);
+HK_API int hk_stem_wgrad(const float* x_nchw, const void* dy_nhwc, float* dw_oihw, int accumulate, int B, int H, int W, void* ws,
+                         size_t ws_bytes, void* stream);
+
+/* MaxPool2d(3,2,1) backward (first-maximum routing, as ATen's indices). x = pool input (post-ReLU stem), NHWC bf16. */
+HK_API int hk_maxpool3x3s2_bwd(const void* dout, const void* x, void* dx, int B, int H, int W, int C, int Ho, int Wo, void* stream);
+
+/* Head in training: K-row scoring conv + bilinear upsample WITHOUT the sigmoid (hk_bce_fwd_bwd takes logits), ATen's exact
+ * operation order; and its backward: upsample-backward of g_up (B,K,H,W) to dlogits_ws (B,K,h,w), then
+ * dfeat (B,h,w,C) bf16, dw_fc (K,C) fp32, db_fc (K) fp32.  Only the K live rows of fc get a gradient, as in the reference. */
+HK_API int hk_head_logits_fwd(const void* feat, int feat_dtype, const float* w_fc, const float* b_fc, float* logits_ws,
+                              float* logits_up, int B, int K, int C, int h, int w, int H, int W, void* stream);
+HK_API size_t hk_head_bwd_workspace_bytes(int B, int K, int C, int h, int w);
+HK_API int hk_head_bwd(const float* g_up, const void* feat, const float* w_fc, float* dlogits_ws, void* dfeat, float* dw_fc,
+                       float* db_fc, int accumulate, int B, int K, int C, int h, int w, int H, int W, void* ws, size_t ws_bytes,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

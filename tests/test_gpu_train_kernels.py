@@ -1,0 +1,202 @@
+"""GPU parity tests of the training-side kernels, through the C ABI.
+
+The checker for each kernel is the torch fp32/fp64 op the reference's train step executes at that point (nn.BatchNorm2d in
+train() mode, autograd of nn.Conv2d / MaxPool2d / upsample_bilinear / the 1x1 scoring conv), evaluated on the SAME
+bf16-rounded operands, so the only differences are accumulation order and the final bf16 rounding of activations."""
+import warnings
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from hulk_keypoints_b200 import ops
+
+warnings.filterwarnings("ignore")
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+torch.backends.cudnn.allow_tf32 = False        # the checker must be true fp32
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x_nhwc):
+    return x_nhwc.permute(0, 3, 1, 2).contiguous()
+
+
+def rel_err(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------ BatchNorm (train) forward
+@pytest.mark.parametrize("C_,shape", [(64, (2, 24, 40)), (128, (3, 15, 20)), (256, (1, 15, 20)), (512, (2, 8, 16))])
+def test_bn_train_forward_matches_torch(C_, shape):
+    torch.manual_seed(C_)
+    B, H, W = shape
+    y = bf(torch.randn(B, H, W, C_, device=DEV) * 2.0 + 0.7)
+    res = bf(torch.randn(B, H, W, C_, device=DEV))
+    gamma = torch.rand(C_, device=DEV) + 0.5
+    beta = torch.randn(C_, device=DEV) * 0.1
+    rm, rv = torch.randn(C_, device=DEV) * 0.1, torch.rand(C_, device=DEV) + 0.5
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    mean, invstd, scale, shift = (torch.empty(C_, device=DEV) for _ in range(4))
+    ws = ops.bn_workspace(C_, DEV)
+    ops.bn_train_stats(y, gamma, beta, rm, rv, 0.1, 1e-5, mean, invstd, scale, shift, ws)
+    out = ops.bn_apply(y, scale, shift, relu=True, residual=res)
+    y32 = nchw(y.float())
+    ref = F.relu(F.batch_norm(y32, rm_ref, rv_ref, gamma, beta, training=True, momentum=0.1, eps=1e-5) + nchw(res.float()))
+    assert torch.allclose(mean, y32.mean(dim=(0, 2, 3)), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(invstd, 1.0 / torch.sqrt(y32.var(dim=(0, 2, 3), unbiased=False) + 1e-5), rtol=1e-4)
+    assert torch.allclose(rm, rm_ref, atol=1e-5, rtol=1e-5) and torch.allclose(rv, rv_ref, atol=1e-5, rtol=1e-4)
+    got = nchw(out.float())
+    assert torch.allclose(got, ref, atol=2e-2, rtol=1e-2)          # one bf16 rounding of the output
+    assert rel_err(got, ref) < 4e-3
+
+
+# ------------------------------------------------------------------ BatchNorm (train) + ReLU backward
+@pytest.mark.parametrize("C_,with_relu", [(64, True), (128, False), (512, True)])
+def test_bn_train_backward_matches_autograd(C_, with_relu):
+    torch.manual_seed(7 + C_)
+    B, H, W = 2, 12, 20
+    y = bf(torch.randn(B, H, W, C_, device=DEV) * 1.5 + 0.3)
+    res = bf(torch.randn(B, H, W, C_, device=DEV))
+    dout = bf(torch.randn(B, H, W, C_, device=DEV) * 1e-3)
+    gamma = torch.rand(C_, device=DEV) + 0.5
+    beta = torch.randn(C_, device=DEV) * 0.1
+    mean, invstd, scale, shift = (torch.empty(C_, device=DEV) for _ in range(4))
+    ws = ops.bn_workspace(C_, DEV)
+    ops.bn_train_stats(y, gamma, beta, None, None, 0.1, 1e-5, mean, invstd, scale, shift, ws)
+    out = ops.bn_apply(y, scale, shift, relu=with_relu, residual=res)
+    dgamma, dbeta = torch.empty(C_, device=DEV), torch.empty(C_, device=DEV)
+    dy, dmasked = torch.empty_like(y), torch.empty_like(y)
+    ops.bn_train_bwd(dout, out if with_relu else None, y, mean, invstd, gamma, dgamma, dbeta, dy, ws, dmasked=dmasked)
+    # autograd on the same operands; the ReLU mask is taken from OUR post-ReLU output (what the next layer saw)
+    y32 = nchw(y.float()).requires_grad_(True)
+    g32, b32 = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    r32 = nchw(res.float()).requires_grad_(True)
+    pre = F.batch_norm(y32, None, None, g32, b32, training=True, eps=1e-5) + r32
+    mask = (nchw(out.float()) > 0).float() if with_relu else torch.ones_like(pre)
+    (pre * mask * nchw(dout.float())).sum().backward()
+    assert rel_err(nchw(dy.float()), y32.grad) < 1e-2
+    assert rel_err(nchw(dmasked.float()), r32.grad) < 1e-6        # d' is exactly dout*mask (both bf16)
+    assert rel_err(dgamma, g32.grad) < 1e-3 and rel_err(dbeta, b32.grad) < 1e-3
+
+
+# ------------------------------------------------------------------ conv data gradient = forward kernel on repacked weights
+@pytest.mark.parametrize("cin,cout,k,dil,hw", [(64, 64, 3, 1, (24, 32)), (128, 128, 3, 1, (16, 32)), (128, 256, 3, 2, (16, 32)),
+                                               (256, 256, 3, 2, (12, 16)), (512, 512, 3, 4, (12, 16)), (256, 512, 1, 1, (12, 16))])
+def test_conv_dgrad_matches_autograd(cin, cout, k, dil, hw):
+    torch.manual_seed(cin + cout + k)
+    B, (H, W) = 2, hw
+    pad = dil * (k - 1) // 2
+    w = torch.randn(cout, cin, k, k, device=DEV) * (2.0 / (k * k * cout)) ** 0.5
+    dy = bf(torch.randn(B, H, W, cout, device=DEV))
+    extra = bf(torch.randn(B, H, W, cin, device=DEV))
+    wd = ops.pack_conv_weights_dgrad(w)
+    one, zero = torch.ones(cin, device=DEV), torch.zeros(cin, device=DEV)
+    dx = ops.conv_bn_act(dy, wd, one, zero, stride=1, pad=pad, dil=dil, relu=False, residual=extra)
+    w_b = bf(w).float()
+    ref = torch.nn.grad.conv2d_input((B, cin, H, W), w_b, nchw(dy.float()), stride=1, padding=pad, dilation=dil) + nchw(extra.float())
+    got = nchw(dx.float())
+    assert rel_err(got, ref) < 5e-3, rel_err(got, ref)
+
+
+@pytest.mark.parametrize("k", [3, 1])
+def test_conv_dgrad_stride2_via_zero_insertion(k):
+    torch.manual_seed(k)
+    B, H, W, cin, cout = 2, 24, 32, 64, 128
+    pad = (k - 1) // 2
+    w = torch.randn(cout, cin, k, k, device=DEV) * 0.05
+    Ho, Wo = ops.conv_out_hw(H, W, k, 2, pad, 1)
+    dy = bf(torch.randn(B, Ho, Wo, cout, device=DEV))
+    up = ops.zero_insert2x(dy)
+    assert tuple(up.shape) == (B, H, W, cout)
+    wd = ops.pack_conv_weights_dgrad(w)
+    one, zero = torch.ones(cin, device=DEV), torch.zeros(cin, device=DEV)
+    dx = ops.conv_bn_act(up, wd, one, zero, stride=1, pad=k - 1 - pad, dil=1, relu=False)
+    ref = torch.nn.grad.conv2d_input((B, cin, H, W), bf(w).float(), nchw(dy.float()), stride=2, padding=pad)
+    assert rel_err(nchw(dx.float()), ref) < 5e-3
+
+
+# ------------------------------------------------------------------ conv weight gradient (tcgen05, MN-major operands)
+@pytest.mark.parametrize("cin,cout,k,stride,dil,B,hw", [
+    (64, 64, 3, 1, 1, 2, (24, 32)),      # layer1 shape (Cout = 64: duplicated M rows)
+    (64, 128, 3, 2, 1, 2, (24, 32)),     # layer2.0.conv1 (stride 2 through the tensor map's element strides)
+    (64, 128, 1, 2, 1, 2, (24, 32)),     # layer2.0.downsample
+    (128, 128, 3, 1, 1, 3, (12, 16)),
+    (128, 256, 3, 1, 2, 2, (12, 16)),    # layer3.0.conv1, dilation 2
+    (256, 256, 3, 1, 2, 2, (12, 32)),
+    (256, 512, 1, 1, 1, 2, (12, 16)),    # layer4.0.downsample
+    (512, 512, 3, 1, 4, 1, (12, 16)),    # layer4, dilation 4
+    (128, 128, 3, 1, 1, 1, (10, 21)),    # ragged tiles (zero-filled boxes)
+])
+def test_conv_wgrad_matches_autograd(cin, cout, k, stride, dil, B, hw):
+    torch.manual_seed(cin * 3 + cout + k + stride)
+    H, W = hw
+    pad = dil * (k - 1) // 2
+    Ho, Wo = ops.conv_out_hw(H, W, k, stride, pad, dil)
+    x = bf(torch.randn(B, H, W, cin, device=DEV))
+    dy = bf(torch.randn(B, Ho, Wo, cout, device=DEV))
+    dw = torch.full((cout, cin, k, k), 7.0, device=DEV)            # must be overwritten, not accumulated into
+    ops.conv_wgrad(x, dy, dw, k=k, stride=stride, pad=pad, dil=dil)
+    ref = torch.nn.grad.conv2d_weight(nchw(x.float()).double(), (cout, cin, k, k), nchw(dy.float()).double(), stride=stride, padding=pad,
+                                      dilation=dil)
+    assert rel_err(dw, ref) < 1e-5, rel_err(dw, ref)              # exact products of bf16 operands, fp32 accumulation
+    dw2 = dw.clone()
+    ops.conv_wgrad(x, dy, dw2, k=k, stride=stride, pad=pad, dil=dil, accumulate=True)
+    assert rel_err(dw2, 2 * ref) < 1e-5
+
+
+def test_stem_wgrad_matches_autograd():
+    torch.manual_seed(3)
+    B, H, W = 2, 64, 96
+    x = torch.rand(B, 3, H, W, device=DEV)
+    dy = bf(torch.randn(B, H // 2, W // 2, 64, device=DEV))
+    dw = torch.empty(64, 3, 7, 7, device=DEV)
+    ops.stem_wgrad(x, dy, dw)
+    ref = torch.nn.grad.conv2d_weight(x.double(), (64, 3, 7, 7), nchw(dy.float()).double(), stride=2, padding=3)
+    assert rel_err(dw, ref) < 1e-5
+
+
+# ------------------------------------------------------------------ maxpool backward (first-maximum routing, ties from ReLU zeros)
+def test_maxpool_backward_matches_autograd_with_ties():
+    torch.manual_seed(5)
+    B, H, W, C_ = 2, 24, 40, 64
+    x = bf(F.relu(torch.randn(B, H, W, C_, device=DEV)))           # ~half zeros: many tied windows
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    dout = bf(torch.randn(B, Ho, Wo, C_, device=DEV))
+    dx = ops.maxpool3x3s2_bwd(dout, x)
+    x32 = nchw(x.float()).requires_grad_(True)
+    F.max_pool2d(x32, 3, 2, 1).backward(nchw(dout.float()))
+    got, ref = nchw(dx.float()), x32.grad
+    # sums of up to 4 bf16 gradients are rounded to bf16 once
+    assert torch.allclose(got, ref, atol=2e-2, rtol=1e-2)
+    assert torch.equal(got != 0, bf(ref).float() != 0) or rel_err(got, ref) < 5e-3
+
+
+# ------------------------------------------------------------------ head (training): logits forward and backward
+@pytest.mark.parametrize("K", [4, 7])
+def test_head_logits_forward_and_backward_match_autograd(K):
+    torch.manual_seed(K)
+    B, h, w, C_, H, W = 2, 8, 12, 512, 64, 96
+    feat = bf(torch.randn(B, h, w, C_, device=DEV))
+    w_fc = torch.randn(K, C_, device=DEV) * 0.05
+    b_fc = torch.randn(K, device=DEV) * 0.1
+    up = ops.head_logits(feat, w_fc, b_fc, H, W)
+    f32 = nchw(feat.float()).requires_grad_(True)
+    w32, b32 = w_fc.clone().requires_grad_(True), b_fc.clone().requires_grad_(True)
+    ref = F.interpolate(F.conv2d(f32, w32.view(K, C_, 1, 1), b32), size=(H, W), mode="bilinear", align_corners=True)
+    assert torch.allclose(up, ref, atol=2e-5, rtol=1e-5)
+    g = torch.randn(B, K, H, W, device=DEV) * 1e-4
+    ref.backward(g)
+    dfeat = torch.empty_like(feat)
+    dw, db = torch.empty(K, C_, device=DEV), torch.empty(K, device=DEV)
+    ops.head_bwd(g, feat, w_fc, dfeat, dw, db)
+    assert rel_err(dw, w32.grad) < 1e-4 and rel_err(db, b32.grad) < 1e-4
+    assert rel_err(nchw(dfeat.float()), f32.grad) < 5e-3         # bf16 rounding of dfeat
