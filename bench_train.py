@@ -7,8 +7,9 @@
 step = Gaussian targets from (B,K,2) labels (generated on the fly inside the fused loss kernel) + forward (train-mode
 BN, per-replica statistics) + fused sigmoid/BCE forward+backward (hk_bce_fwd_bwd) + backbone backward + gradient
 all-reduce (NCCL, bucketed) + Adam(lr 1e-4, wd 1e-4) -- the sequence of reference train.py:33-36.
-The backbone forward/backward runs on torch autograd (cuDNN) in this round (SURVEY.md §8 f1 is "next"); the loss side is
-ours.  Secondary benchmark: the headline metric is bench.py (inference images/s).
+--backend hk (default): the whole step runs on libhulk_sm100 kernels (TrainEngine: tcgen05 forward / dgrad / wgrad, train-mode
+BN kernels, fused loss, FusedAdam; one CUDA graph).  --backend autograd: the backbone runs on torch autograd / cuDNN fp32 (the
+same-box competitor).  Secondary benchmark: the headline metric is bench.py (inference images/s).
 """
 from __future__ import annotations
 
@@ -36,6 +37,9 @@ def main():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"], help="FusedAdam (hk_adam_step) or torch.optim.Adam")
     ap.add_argument("--reference-loss", action="store_true", help="use torch's .double()+BCELoss on fp64 targets (train.py:21-25)")
+    ap.add_argument("--backend", default="hk", choices=["hk", "autograd"],
+                    help="hk: whole step on libhulk_sm100 kernels (TrainEngine, bf16 tcgen05, one CUDA graph); "
+                         "autograd: backbone on torch autograd / cuDNN fp32 (the same-box competitor and the parity checker)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -71,7 +75,7 @@ def main():
                 allreduce(model.parameters())
             opt.step()
             return loss.detach()
-        return train_ops.train_step(model, opt, img, uv, sigma=8.0, allreduce=allreduce)
+        return train_ops.train_step(model, opt, img, uv, sigma=8.0, allreduce=allreduce, backend=args.backend)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -93,7 +97,11 @@ def main():
         print(json.dumps({
             "metric": "train_steps_per_sec", "value": args.steps / (ms * 1e-3), "unit": "steps/s",
             "images_per_sec": world * B * args.steps / (ms * 1e-3), "n_gpus": world, "steps": args.steps,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "dtype": "f32 (backbone, torch autograd) + f64 loss",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "dtype": ("bf16 operands / f32 accumulate (tcgen05), f32 BN stats + grads, f64 loss" if args.backend == "hk" and not args.reference_loss
+                      else "f32 (backbone, torch autograd / cuDNN) + f64 loss"),
+            "backend": "autograd" if args.reference_loss else args.backend,
+            "gpu_launches_per_step": (model.train_engine(B, H, W).launches + 1) if args.backend == "hk" and not args.reference_loss else None,
             "data": "synthetic", "loss": float(loss.item()),
             "config": {"workload": f"train step, per-GPU batch {B}, {H}x{W}, K=4, Adam lr 1e-4 wd 1e-4 (BASELINE.json configs[3])",
                        "loss_path": "torch BCELoss on fp64 targets" if args.reference_loss else "fused hk_bce_fwd_bwd, targets on the fly",

@@ -13,7 +13,7 @@
 namespace hk {
 
 constexpr int BN_THREADS = 256;
-constexpr int BN_MAX_BLOCKS = 1184;  // 148 SMs x 8
+constexpr int BN_MAX_BLOCKS = 592;  // 148 SMs x 4
 
 struct Vec8 {
   float v[8];
@@ -63,18 +63,44 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_partial_kernel(const __nv
   block_reduce_2x8(s, q, C, partial);
 }
 
-// one thread per channel: mean / invstd, the fused affine (scale, shift) of the apply pass, running statistics
-__global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int nblocks, long long P, int C, const float* __restrict__ gamma,
+// Finalize kernels: 256 threads = 32 channels x 8 slices of the per-block partials (coalesced across channels, 8-way parallel and
+// unrolled along the blocks -- a single thread per channel walking ~1000 partials serially cost 170 us per launch).
+constexpr int BN_FIN_THREADS = 256;
+__device__ __forceinline__ void bn_sum_partials(const float* __restrict__ partial, int nblocks, int C, int c, double& s, double& q) {
+  __shared__ double sh[2][8][32];
+  const int lane_c = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  if (c < C) {
+    int b = slice;
+    for (; b + 8 < nblocks; b += 16) {
+      a0 += partial[(size_t)b * 2 * C + c];
+      b0 += partial[(size_t)b * 2 * C + C + c];
+      a1 += partial[(size_t)(b + 8) * 2 * C + c];
+      b1 += partial[(size_t)(b + 8) * 2 * C + C + c];
+    }
+    if (b < nblocks) {
+      a0 += partial[(size_t)b * 2 * C + c];
+      b0 += partial[(size_t)b * 2 * C + C + c];
+    }
+  }
+  sh[0][slice][lane_c] = (double)a0 + (double)a1;
+  sh[1][slice][lane_c] = (double)b0 + (double)b1;
+  __syncthreads();
+  s = 0.0;
+  q = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s += sh[0][i][lane_c]; q += sh[1][i][lane_c]; }
+}
+
+// mean / invstd, the fused affine (scale, shift) of the apply pass, running statistics
+__global__ void __launch_bounds__(BN_FIN_THREADS) bn_stats_finalize_kernel(const float* __restrict__ partial, int nblocks, long long P, int C, const float* __restrict__ gamma,
                                          const float* __restrict__ beta, float* __restrict__ running_mean,
                                          float* __restrict__ running_var, float momentum, float eps, float* __restrict__ mean_out,
                                          float* __restrict__ invstd_out, float* __restrict__ scale_out, float* __restrict__ shift_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += (double)partial[(size_t)b * 2 * C + c];
-    q += (double)partial[(size_t)b * 2 * C + C + c];
-  }
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  double s, q;
+  bn_sum_partials(partial, nblocks, C, c, s, q);
+  if (c >= C || threadIdx.x >= 32) return;
   const double n = (double)P;
   const double mean = s / n;
   double var = q / n - mean * mean;
@@ -152,16 +178,13 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_partial_kernel(const __nv_b
 
 // dgamma, dbeta (fp32 parameter gradients; accumulate != 0 adds to what is there) and the coefficients of the apply pass:
 //   coef[0][c] = gamma*invstd, coef[1][c] = dbeta/N, coef[2][c] = dgamma/N
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, long long P, int C, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(BN_FIN_THREADS) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, long long P, int C, const float* __restrict__ gamma,
                                        const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        int accumulate, float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s1 += (double)partial[(size_t)b * 2 * C + c];
-    s2 += (double)partial[(size_t)b * 2 * C + C + c];
-  }
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  double s1, s2;
+  bn_sum_partials(partial, nblocks, C, c, s1, s2);
+  if (c >= C || threadIdx.x >= 32) return;
   const float g = gamma ? gamma[c] : 1.f;
   if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s1;
   if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s2;
@@ -201,8 +224,9 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const __nv_bfl
 
 static int bn_grid_rows(long long P, int C) {
   const int rows = BN_THREADS / (C >> 3);
-  long long blocks = ceil_div_ll(P, rows);
+  long long blocks = ceil_div_ll(P, (long long)rows * 16);  // >= 16 row iterations per block: few partials to finalize
   if (blocks > BN_MAX_BLOCKS) blocks = BN_MAX_BLOCKS;
+  if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
 static int bn_grid_elems(long long nvec) {
@@ -231,7 +255,7 @@ int hk_bn_train_stats(const void* y, long long P, int C, const float* gamma, con
   bn_stats_partial_kernel<<<blocks, BN_THREADS, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y), P, C, static_cast<float*>(ws));
   int rc = check_launch("bn_stats_partial_kernel");
   if (rc) return rc;
-  bn_stats_finalize_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(static_cast<const float*>(ws), blocks, P, C, gamma, beta,
+  bn_stats_finalize_kernel<<<ceil_div(C, 32), BN_FIN_THREADS, 0, as_stream(stream)>>>(static_cast<const float*>(ws), blocks, P, C, gamma, beta,
                                                                            running_mean, running_var, momentum, eps, mean_out,
                                                                            invstd_out, scale_out, shift_out);
   return check_launch("bn_stats_finalize_kernel");
@@ -265,7 +289,7 @@ int hk_bn_train_bwd(const void* dout, const void* out_mask_or_null, const void* 
   bn_bwd_partial_kernel<<<blocks, BN_THREADS, 0, as_stream(stream)>>>(d, m, yy, mean, invstd, P, C, partial);
   int rc = check_launch("bn_bwd_partial_kernel");
   if (rc) return rc;
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(partial, blocks, P, C, gamma, invstd, dgamma, dbeta, accumulate, coef);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 32), BN_FIN_THREADS, 0, as_stream(stream)>>>(partial, blocks, P, C, gamma, invstd, dgamma, dbeta, accumulate, coef);
   rc = check_launch("bn_bwd_finalize_kernel");
   if (rc) return rc;
   const long long nvec = P * (C >> 3);

@@ -168,6 +168,16 @@ class KeypointsGauss(nn.Module):
             self._engine = InferenceEngine(self, self.precision)
         return self._engine
 
+    def train_engine(self, batch: int, height: int, width: int):
+        """The B200 training engine (forward in train() mode + loss + backward on libhulk_sm100 kernels) for one input shape."""
+        from .train_engine import TrainEngine
+
+        key = (batch, height, width, self.resnet.resnet34_8s.conv1.weight.device)
+        engines = self.__dict__.setdefault("_train_engines", {})
+        if key not in engines:
+            engines[key] = TrainEngine(self, batch, height, width)
+        return engines[key]
+
     def set_precision(self, precision: str) -> "KeypointsGauss":
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")

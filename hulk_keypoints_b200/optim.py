@@ -43,6 +43,18 @@ class FusedAdam:
                 p.data = self.flat_param[o:o + n].view_as(p.data)
                 p.grad = self.flat_grad[o:o + n].view_as(p.data)
 
+    def adopt_grad_buffer(self, flat_grad: torch.Tensor) -> None:
+        """Use an external flat gradient buffer with this optimiser's layout (TrainEngine.flat_grad): the engine's kernels then write
+        the gradients exactly where the all-reduce and hk_adam_step read them -- no copy."""
+        if flat_grad.shape != self.flat_grad.shape or flat_grad.dtype != torch.float32 or flat_grad.device != self.flat_grad.device:
+            raise ValueError("gradient buffer layout mismatch")
+        self.flat_grad = flat_grad
+        o = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = flat_grad[o:o + n].view_as(p.data)
+            o += (n + 3) // 4 * 4
+
     def zero_grad(self, set_to_none: bool = False) -> None:
         """Keeps the gradient views alive (set_to_none would detach them from the flat buffer)."""
         self.flat_grad.zero_()

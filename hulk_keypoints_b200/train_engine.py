@@ -1,0 +1,289 @@
+"""TrainEngine: one KeypointsGauss training step (forward in train() mode + loss + backward) as a fixed sequence of
+libhulk_sm100 kernels -- the B200-native replacement of what torch autograd executes for reference train.py:33-35
+(zero_grad, forward(sample, model), loss.backward()).  SURVEY.md §8 rows a4/a9/a11/a12 and f1.
+
+Numerics: bf16 NHWC activations and bf16 conv operands (tcgen05, fp32 accumulation in TMEM), fp32 BatchNorm statistics,
+fp32 parameter gradients, fp64 loss.  BatchNorm uses the statistics of the local batch (per replica, like the reference,
+which has no SyncBN) and updates running_mean / running_var / num_batches_tracked exactly as nn.BatchNorm2d does.
+
+Per conv the forward is   y = conv(x) [raw, bf16]  ->  batch stats  ->  out = relu(gamma*xhat + beta [+ shortcut])
+and the backward          d' = dout*[out>0]  ->  (dgamma, dbeta, dy)  ->  dW = wgrad(x, dy),  dx = conv(dy, W flipped).
+All 110 parameter gradients land in ONE flat fp32 buffer laid out like FusedAdam's (one all-reduce, one update kernel);
+the 996 dead rows of the 1000-row scoring conv keep a zero gradient, as in the reference.
+
+Data layout in HBM (per engine, batch B of H x W): input (B,3,H,W) f32; per conv a raw output and an activation,
+(B,h,w,C) bf16 NHWC; (B,K,H,W) f32 upsampled logits and their gradient; scratch gradients sized by stage.
+The whole step is captured in one CUDA graph (~560 launches) and replayed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from ._lib import HK_BF16, check, lib, ptr, require_device, stream_ptr
+
+
+class _ConvT:
+    """One conv + its BatchNorm in training: parameters, packed operands, saved tensors."""
+
+    def __init__(self, name, conv, bn, B, H, W, dev):
+        self.name, self.conv, self.bn = name, conv, bn
+        self.cout, self.cin, self.k, _ = conv.weight.shape
+        self.stride, self.pad, self.dil = conv.stride[0], conv.padding[0], conv.dilation[0]
+        self.H, self.W = H, W
+        self.Ho, self.Wo = ops.conv_out_hw(H, W, self.k, self.stride, self.pad, self.dil)
+        bf = torch.bfloat16
+        self.w_fwd = torch.empty((self.cout, self.k, self.k, self.cin), device=dev, dtype=bf)
+        self.w_dgrad = torch.empty((self.cin, self.k, self.k, self.cout), device=dev, dtype=bf)
+        self.one_out = torch.empty(self.cout, device=dev)   # scale = 1 / bias = 0 of the raw forward conv (filled by the pack kernel)
+        self.zero_out = torch.empty(self.cout, device=dev)
+        self.one_in = torch.ones(self.cin, device=dev)      # same for the data-gradient conv (its "Cout" is cin)
+        self.zero_in = torch.zeros(self.cin, device=dev)
+        self.y = torch.empty((B, self.Ho, self.Wo, self.cout), device=dev, dtype=bf)   # raw conv output (saved for BN backward)
+        self.mean, self.invstd, self.scale, self.shift = (torch.empty(self.cout, device=dev) for _ in range(4))
+
+
+class TrainEngine:
+    def __init__(self, model, B: int, H: int, W: int, sigma: float = 8.0):
+        require_device()
+        if H % 8 or W % 8 or H < 32 or W < 32:
+            raise ValueError("TrainEngine needs H and W to be multiples of 8 (>= 32)")
+        net = model.resnet.resnet34_8s
+        dev = net.conv1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("TrainEngine needs the model on a CUDA device (no CPU path)")
+        self.model, self.net, self.device = model, net, dev
+        self.B, self.H, self.W, self.K, self.sigma = B, H, W, int(model.num_keypoints), float(sigma)
+        bf = torch.bfloat16
+        # ---- flat gradient buffer, FusedAdam layout (each tensor starts on a 16-byte boundary) ----
+        self.params: List[torch.nn.Parameter] = [p for p in model.parameters() if p.requires_grad]
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad_of: Dict[int, torch.Tensor] = {id(p): self.flat_grad[o:o + p.numel()].view_as(p) for p, o in zip(self.params, offs)}
+        # ---- buffers ----
+        self.x = torch.empty((B, 3, H, W), device=dev, dtype=torch.float32)
+        self.uv = torch.zeros((B, self.K, 2), device=dev, dtype=torch.float32)
+        self.target: Optional[torch.Tensor] = None      # (B,K,H,W) fp64/fp32 when the caller supplies targets instead of labels
+        h2, w2 = ops.conv_out_hw(H, W, 7, 2, 3, 1)
+        h4, w4 = (h2 + 2 - 3) // 2 + 1, (w2 + 2 - 3) // 2 + 1
+        self.h2, self.w2, self.h4, self.w4 = h2, w2, h4, w4
+        self.stem_w = torch.empty(int(lib().hk_stem_packed_weight_bytes()) // 2, device=dev, dtype=bf)
+        self.stem = _ConvT("stem", net.conv1, net.bn1, B, H, W, dev)
+        self.a0 = torch.empty((B, h2, w2, 64), device=dev, dtype=bf)
+        self.p0 = torch.empty((B, h4, w4, 64), device=dev, dtype=bf)
+        self.blocks = []
+        h, w = h4, w4
+        for i, blk in enumerate(net.blocks()):
+            c1 = _ConvT(f"b{i}.c1", blk.conv1, blk.bn1, B, h, w, dev)
+            c2 = _ConvT(f"b{i}.c2", blk.conv2, blk.bn2, B, c1.Ho, c1.Wo, dev)
+            ds = _ConvT(f"b{i}.ds", blk.downsample[0], blk.downsample[1], B, h, w, dev) if blk.downsample is not None else None
+            a1 = torch.empty_like(c1.y)
+            sc = torch.empty_like(c2.y) if ds is not None else None
+            out = torch.empty_like(c2.y)
+            self.blocks.append((c1, c2, ds, a1, sc, out))
+            h, w = c1.Ho, c1.Wo
+        self.h8, self.w8 = h, w
+        self.convs: List[_ConvT] = [self.stem] + [c for b in self.blocks for c in (b[0], b[1], b[2]) if c is not None]
+        K = self.K
+        self.logits_lr = torch.empty((B, K, h, w), device=dev, dtype=torch.float32)
+        self.logits_up = torch.empty((B, K, H, W), device=dev, dtype=torch.float32)
+        self.g_up = torch.empty((B, K, H, W), device=dev, dtype=torch.float32)
+        self.dlogits_lr = torch.empty((B, K, h, w), device=dev, dtype=torch.float32)
+        self.loss = torch.zeros((), device=dev, dtype=torch.float64)
+        n = B * K * H * W
+        self.bce_ws = torch.empty(int(lib().hk_bce_workspace_bytes(n)), device=dev, dtype=torch.uint8)
+        self.bn_ws = ops.bn_workspace(512, dev)
+        wg = max(ops.conv_wgrad_workspace_bytes(B, c.H, c.W, c.cin, c.cout, c.k, c.stride, c.pad, c.dil) for c in self.convs[1:])
+        self.wgrad_ws = torch.empty(max(wg, int(lib().hk_stem_wgrad_workspace_bytes())), device=dev, dtype=torch.uint8)
+        self.head_ws = torch.empty(int(lib().hk_head_bwd_workspace_bytes(B, K, 512, h, w)), device=dev, dtype=torch.uint8)
+        self._scratch: Dict[Tuple, torch.Tensor] = {}
+        self._bn_counters = [c.bn.num_batches_tracked for c in self.convs]
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_key = None
+        self.use_cuda_graph = os.environ.get("HK_TRAIN_NO_GRAPH") is None   # eager launches for ncu launch lists
+        self.launches = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, role: str, shape) -> torch.Tensor:
+        key = (role, tuple(shape))
+        t = self._scratch.get(key)
+        if t is None:
+            t = torch.empty(tuple(shape), device=self.device, dtype=torch.bfloat16)
+            self._scratch[key] = t
+        return t
+
+    def _g(self, p) -> torch.Tensor:
+        return self.grad_of[id(p)]
+
+    def _pack(self, c: _ConvT, with_dgrad: bool) -> int:
+        w = c.conv.weight.data
+        check(lib().hk_pack_conv_weights(ptr(w), None, None, None, None, C.c_float(1e-5), c.cout, c.cin, c.k, c.k, HK_BF16,
+                                         ptr(c.w_fwd), ptr(c.one_out), ptr(c.zero_out), stream_ptr()), "hk_pack_conv_weights")
+        n = 2
+        if with_dgrad:
+            ops.pack_conv_weights_dgrad(w, out=c.w_dgrad)
+            n += 1
+        return n
+
+    def _conv_bn(self, c: _ConvT, x, out, relu: bool, residual=None) -> int:
+        """raw conv -> batch statistics (+ running stats) -> fused normalise (+ shortcut) (+ ReLU)."""
+        ops.conv_bn_act(x, c.w_fwd, c.one_out, c.zero_out, stride=c.stride, pad=c.pad, dil=c.dil, relu=False, out=c.y)
+        bn = c.bn
+        ops.bn_train_stats(c.y, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.momentum, bn.eps, c.mean, c.invstd,
+                           c.scale, c.shift, self.bn_ws)
+        ops.bn_apply(c.y, c.scale, c.shift, relu=relu, residual=residual, out=out)
+        return 4
+
+    def _bn_bwd(self, c: _ConvT, dout, mask, dy, dmasked=None) -> int:
+        bn = c.bn
+        ops.bn_train_bwd(dout, mask, c.y, c.mean, c.invstd, bn.weight.data, self._g(bn.weight), self._g(bn.bias), dy, self.bn_ws,
+                         dmasked=dmasked)
+        return 3
+
+    def _wgrad(self, c: _ConvT, x, dy) -> int:
+        ops.conv_wgrad(x, dy, self._g(c.conv.weight), k=c.k, stride=c.stride, pad=c.pad, dil=c.dil, ws=self.wgrad_ws)
+        return 2
+
+    def _dgrad(self, c: _ConvT, dy, dx, residual=None) -> int:
+        """dx = conv_transpose(dy, W) (+ residual) through the forward kernel on the flipped weights."""
+        n = 1
+        if c.stride == 2:
+            up = self._buf("up", (self.B, c.H, c.W, c.cout))
+            ops.zero_insert2x(dy, out=up)
+            dy, n = up, 2
+        ops.conv_bn_act(dy, c.w_dgrad, c.one_in, c.zero_in, stride=1, pad=c.dil * (c.k - 1) - c.pad, dil=c.dil, relu=False,
+                        residual=residual, out=dx)
+        return n
+
+    # ------------------------------------------------------------------ the step
+    def _enqueue(self) -> int:
+        net, K = self.net, self.K
+        n = 0
+        # weights of this step (parameters change every optimizer step)
+        check(lib().hk_stem_pack_weights(ptr(net.conv1.weight.data), ptr(self.stem_w), stream_ptr()), "hk_stem_pack_weights")
+        n += 1 + self._pack(self.stem, with_dgrad=False)
+        for c in self.convs[1:]:
+            n += self._pack(c, with_dgrad=True)
+        # ---------------- forward (train mode) ----------------
+        st = self.stem
+        ops.stem_conv(self.x, self.stem_w, st.one_out, st.zero_out, relu=False, out=st.y)
+        bn = st.bn
+        ops.bn_train_stats(st.y, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.momentum, bn.eps, st.mean, st.invstd,
+                           st.scale, st.shift, self.bn_ws)
+        ops.bn_apply(st.y, st.scale, st.shift, relu=True, out=self.a0)
+        ops.maxpool3x3s2(self.a0, out=self.p0)
+        n += 5
+        x = self.p0
+        for (c1, c2, ds, a1, sc, out) in self.blocks:
+            n += self._conv_bn(c1, x, a1, relu=True)
+            if ds is not None:
+                n += self._conv_bn(ds, x, sc, relu=False)
+                shortcut = sc
+            else:
+                shortcut = x
+            n += self._conv_bn(c2, a1, out, relu=True, residual=shortcut)
+            x = out
+        feat = x
+        torch._foreach_add_(self._bn_counters, 1)
+        fc_w = net.fc.weight.data[:K].view(K, 512)
+        fc_b = net.fc.bias.data[:K]
+        ops.head_logits(feat, fc_w, fc_b, self.H, self.W, out=self.logits_up, logits_ws=self.logits_lr)
+        n += 3
+        # ---------------- loss: sigmoid + BCE(mean) forward and d/dlogits in one pass ----------------
+        tgt = self.target
+        tcode = 0 if tgt is None else ops.dtype_code(tgt.dtype)
+        check(lib().hk_bce_fwd_bwd(ptr(self.logits_up), 1, ptr(tgt), tcode, None if tgt is not None else ptr(self.uv), self.B, K, self.H,
+                                   self.W, C.c_float(self.sigma), ptr(self.loss), ptr(self.g_up), ptr(self.bce_ws), self.bce_ws.numel(),
+                                   stream_ptr()), "hk_bce_fwd_bwd")
+        n += 2
+        # ---------------- backward ----------------
+        d = self._buf("d0", feat.shape)
+        ops.head_bwd(self.g_up, feat, fc_w, d, self._g(net.fc.weight)[:K].view(K, 512), self._g(net.fc.bias)[:K],
+                     dlogits_ws=self.dlogits_lr, ws=self.head_ws)
+        n += 4
+        parity = 1
+        for bi in range(len(self.blocks) - 1, -1, -1):
+            c1, c2, ds, a1, sc, out = self.blocks[bi]
+            x_in = self.blocks[bi - 1][5] if bi > 0 else self.p0
+            dy2 = self._buf("dy", c2.y.shape)
+            dm = self._buf("dm", c2.y.shape)
+            n += self._bn_bwd(c2, d, out, dy2, dmasked=dm)            # d' = d*[out>0] also feeds the shortcut
+            n += self._wgrad(c2, a1, dy2)
+            da1 = self._buf("da1", a1.shape)
+            n += self._dgrad(c2, dy2, da1)
+            dy1 = self._buf("dy", c1.y.shape)
+            n += self._bn_bwd(c1, da1, a1, dy1)
+            n += self._wgrad(c1, x_in, dy1)
+            dx = self._buf(f"d{parity}", x_in.shape)
+            if ds is not None:
+                dyd = self._buf("dyd", ds.y.shape)
+                n += self._bn_bwd(ds, dm, None, dyd)
+                n += self._wgrad(ds, x_in, dyd)
+                dxd = self._buf("dxd", x_in.shape)
+                n += self._dgrad(ds, dyd, dxd)
+                n += self._dgrad(c1, dy1, dx, residual=dxd)
+            else:
+                n += self._dgrad(c1, dy1, dx, residual=dm)
+            d, parity = dx, parity ^ 1
+        da0 = self._buf("da0", self.a0.shape)
+        ops.maxpool3x3s2_bwd(d, self.a0, dx=da0)
+        dy0 = self._buf("dy", st.y.shape)
+        n += 1 + self._bn_bwd(st, da0, self.a0, dy0)
+        ops.stem_wgrad(self.x, dy0, self._g(net.conv1.weight), ws=self.wgrad_ws)
+        n += 2
+        return n
+
+    def _key(self):
+        return (tuple(p.data_ptr() for p in self.params), None if self.target is None else (self.target.data_ptr(), self.target.dtype))
+
+    def forward_backward(self, img: torch.Tensor, uv: Optional[torch.Tensor] = None, target: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """img (B,3,H,W) fp32 CUDA; labels uv (B,K,2) = (x,y) [Gaussian targets generated on the fly, dataset.py:36-44] or a
+        (B,K,H,W) fp64/fp32 target tensor (what KeypointsDataset returns).  Returns the fp64 mean-BCE loss (0-dim, a view of an
+        engine buffer); the gradients of all parameters are in `self.flat_grad` / `grad(p)`."""
+        if (uv is None) == (target is None):
+            raise ValueError("pass exactly one of uv / target")
+        if not img.is_cuda or tuple(img.shape) != (self.B, 3, self.H, self.W):
+            raise ValueError(f"expected a CUDA image batch of shape {(self.B, 3, self.H, self.W)}, got {tuple(img.shape)} on {img.device}")
+        with torch.no_grad():
+            self.x.copy_(img)
+            if uv is not None:
+                self.uv.copy_(uv.reshape(self.B, self.K, 2))
+                self.target = None
+            else:
+                if tuple(target.shape) != (self.B, self.K, self.H, self.W) or target.dtype not in (torch.float64, torch.float32):
+                    raise ValueError("target must be (B,K,H,W) float64 or float32")
+                if self.target is None or self.target.dtype != target.dtype:
+                    self.target = torch.empty_like(target, memory_format=torch.contiguous_format)
+                self.target.copy_(target)
+            if not self.use_cuda_graph:
+                self.launches = self._enqueue()
+                return self.loss
+            key = self._key()
+            if self.graph is None or key != self._graph_key:
+                # one eager step (lazy function attributes, scratch allocation), restoring the BN buffers it advanced
+                saved = [(c.bn.running_mean.clone(), c.bn.running_var.clone(), c.bn.num_batches_tracked.clone()) for c in self.convs]
+                self.launches = self._enqueue()
+                torch.cuda.current_stream().synchronize()
+                for c, (m, v, t) in zip(self.convs, saved):
+                    c.bn.running_mean.copy_(m); c.bn.running_var.copy_(v); c.bn.num_batches_tracked.copy_(t)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue()
+                self.graph, self._graph_key = g, key
+            self.graph.replay()
+        return self.loss
+
+    def grad(self, p: torch.nn.Parameter) -> torch.Tensor:
+        return self.grad_of[id(p)]
+
+    def grads_into_params(self) -> None:
+        """p.grad = the engine's gradient (views of the flat buffer) for every parameter."""
+        for p in self.params:
+            p.grad = self.grad_of[id(p)]

@@ -39,20 +39,66 @@ def sigmoid_bce_loss(logits: torch.Tensor, target: Optional[torch.Tensor] = None
     return _FusedSigmoidBCE.apply(logits, target, uv, float(sigma))
 
 
-def loss_from_batch(sample_batched, model, use_cuda: bool = True) -> torch.Tensor:
-    """Drop-in for reference train.py:18-26 `forward(sample_batched, model)`: (img, gt_gauss) -> float64 loss."""
+class _EngineStep(torch.autograd.Function):
+    """forward = TrainEngine.forward_backward (loss AND all parameter gradients in one pass of our kernels); backward hands the
+    stored gradients to autograd, so an unmodified `loss.backward(); optimizer.step()` (train.py:35-36) works."""
+
+    @staticmethod
+    def forward(ctx, engine, img, target, uv, *params):
+        loss = engine.forward_backward(img, uv=uv, target=target)
+        ctx.engine = engine
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        eng = ctx.engine
+        g = grad_out.to(torch.float32)
+        return (None, None, None, None) + tuple(eng.grad(p) * g for p in eng.params)
+
+
+def engine_loss(model, img: torch.Tensor, target: Optional[torch.Tensor] = None, uv: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Differentiable fp64 loss of one batch computed by the B200 TrainEngine (bf16 tensor-core forward/backward)."""
+    eng = model.train_engine(img.shape[0], img.shape[2], img.shape[3])
+    return _EngineStep.apply(eng, img, target, uv, *eng.params)
+
+
+def loss_from_batch(sample_batched, model, use_cuda: bool = True, backend: str = "hk") -> torch.Tensor:
+    """Drop-in for reference train.py:18-26 `forward(sample_batched, model)`: (img, gt_gauss) -> float64 loss.
+    backend "hk" (default): TrainEngine kernels; "autograd": torch autograd graph over the same parameters (fp32 checker)."""
     img, gt_gauss = sample_batched
     if use_cuda:
         img, gt_gauss = img.cuda(), gt_gauss.cuda()
+    if backend == "hk":
+        return engine_loss(model, img.float().contiguous(), target=gt_gauss.contiguous())
     return sigmoid_bce_loss(model.forward_logits(img), target=gt_gauss.contiguous())
 
 
-def train_step(model, optimizer, img: torch.Tensor, uv: torch.Tensor, sigma: float = 8.0, allreduce=None) -> torch.Tensor:
+def train_step(model, optimizer, img: torch.Tensor, uv: torch.Tensor, sigma: float = 8.0, allreduce=None,
+               backend: str = "hk") -> torch.Tensor:
     """One step of reference train.py:33-36 (zero_grad, forward, backward, step) with targets generated from
     labels on the fly.  `optimizer` is a `hulk_keypoints_b200.optim.FusedAdam` (flat buffers: one all-reduce, one
     update kernel) or any torch optimizer; `allreduce(params)` (data-parallel exchange) runs between backward and step
-    for torch optimizers, FusedAdam reduces its flat gradient buffer itself."""
+    for torch optimizers, FusedAdam reduces its flat gradient buffer itself.
+
+    backend "hk" (default): the whole forward + loss + backward runs on libhulk_sm100 kernels (TrainEngine, one CUDA graph);
+    with FusedAdam the engine writes the gradients straight into the optimiser's flat buffer.  backend "autograd": the
+    backbone runs on torch autograd (fp32 cuDNN) -- the checker of the parity tests, not a product path."""
     fused = hasattr(optimizer, "flat_grad")
+    if backend == "hk":
+        eng = model.train_engine(img.shape[0], img.shape[2], img.shape[3])
+        eng.sigma = float(sigma)
+        if fused:
+            if optimizer.flat_grad.data_ptr() != eng.flat_grad.data_ptr():
+                optimizer.adopt_grad_buffer(eng.flat_grad)
+        loss = eng.forward_backward(img, uv=uv)
+        if fused:
+            optimizer.all_reduce_grads()
+        else:
+            eng.grads_into_params()
+            if allreduce is not None:
+                allreduce(model.parameters())
+        optimizer.step()
+        return loss.detach().clone()
     if fused:
         optimizer.zero_grad()
     else:

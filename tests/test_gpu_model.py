@@ -51,8 +51,9 @@ def synth_batch(gen, B, H, W, K=4):
 
 @pytest.fixture(scope="module")
 def sd_trained():
-    """F-trn: a short training run on synthetic discs with OUR train step (fused sigmoid+BCE kernel on the loss
-    side, autograd backbone), so heatmaps are peaked and 'keypoints within 1 px' means something."""
+    """F-trn: a short fp32 training run on synthetic discs (fused sigmoid+BCE kernel on the loss side, torch-autograd backbone:
+    the checker path), so heatmaps are peaked and 'keypoints within 1 px' means something.  The bf16 TrainEngine has its own
+    convergence + gradient-parity tests in test_gpu_train_engine.py."""
     torch.manual_seed(0)
     m = hk.KeypointsGauss(4).cuda().train()
     opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-4)
@@ -61,7 +62,7 @@ def sd_trained():
     losses = []
     for step in range(200):
         img, uv = synth_batch(gen, 4, H, W)
-        losses.append(train_ops.train_step(m, opt, img.cuda(), uv.cuda(), sigma=6.0).item())
+        losses.append(train_ops.train_step(m, opt, img.cuda(), uv.cuda(), sigma=6.0, backend="autograd").item())
     assert losses[-1] < 0.25 * losses[0], (losses[0], losses[-1])
     return {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}, (H, W)
 
