@@ -98,7 +98,7 @@ def _declare(lib):
     lib.hk_stem_wgrad.restype = i
     lib.hk_stem_wgrad.argtypes = [vp, vp, vp, i, i, i, i, vp, sz, vp]
     lib.hk_maxpool3x3s2_bwd.restype = i
-    lib.hk_maxpool3x3s2_bwd.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp]
+    lib.hk_maxpool3x3s2_bwd.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp, sz, vp]
     lib.hk_head_logits_fwd.restype = i
     lib.hk_head_logits_fwd.argtypes = [vp, i, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
     lib.hk_head_bwd_workspace_bytes.restype = sz

@@ -123,14 +123,13 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_fwd_kernel(const __nv_bfl
                                                                  const float* __restrict__ shift,
                                                                  const __nv_bfloat16* __restrict__ residual, int relu,
                                                                  __nv_bfloat16* __restrict__ out, long long nvec, int C) {
-  const int CG = C >> 3;
+  // the grid stride (gridDim*256) is a multiple of C/8, so a thread keeps its 8 channels: coefficients live in registers
+  const int cg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % (C >> 3));
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + cg * 8 + j); sh[j] = __ldg(shift + cg * 8 + j); }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
     const Vec8 v = load8(y + i * 8);
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8 + 4));
-    const float4 t0 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8)), t1 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8 + 4));
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(v.v[j], sc[j], sh[j]);
@@ -193,16 +192,25 @@ __global__ void __launch_bounds__(BN_FIN_THREADS) bn_bwd_finalize_kernel(const f
   coef[2 * C + c] = (float)(s2 / (double)P);
 }
 
-// dy = coef0 * (d' - coef1 - xhat*coef2); optionally also writes d' (the gradient that flows into the shortcut branch)
+// dy = coef0 * (d' - coef1 - xhat*coef2) = k0*d' + k1*y + k2 per channel; optionally also writes d' (the gradient that flows
+// into the shortcut branch).  The thread's 8 channels are loop-invariant (see bn_apply_fwd_kernel): 24 coefficients in registers.
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout,
                                                                  const __nv_bfloat16* __restrict__ out_mask,
                                                                  const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                                                                  const float* __restrict__ invstd, const float* __restrict__ coef,
                                                                  __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dmasked,
                                                                  long long nvec, int C) {
-  const int CG = C >> 3;
+  const int c0 = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % (C >> 3)) * 8;
+  float k0[8], k1[8], k2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const float a = __ldg(coef + c), is = __ldg(invstd + c), mu = __ldg(mean + c);
+    k0[j] = a;
+    k1[j] = -a * __ldg(coef + 2 * C + c) * is;
+    k2[j] = -a * __ldg(coef + C + c) - k1[j] * mu;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % CG) * 8;
     Vec8 d = load8(dout + i * 8);
     if (out_mask) {
       const Vec8 m = load8(out_mask + i * 8);
@@ -213,11 +221,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const __nv_bfl
     const Vec8 v = load8(y + i * 8);
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const float xhat = (v.v[j] - __ldg(mean + c)) * __ldg(invstd + c);
-      o[j] = __ldg(coef + c) * (d.v[j] - __ldg(coef + C + c) - xhat * __ldg(coef + 2 * C + c));
-    }
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(k0[j], d.v[j], fmaf(k1[j], v.v[j], k2[j]));
     store8(dy + i * 8, o);
   }
 }

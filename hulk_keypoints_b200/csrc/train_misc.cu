@@ -20,10 +20,47 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
 
-// ---------------------------------------------------------------- maxpool backward (gather)
-// dx[b,iy,ix,c] = sum over the (<= 4) windows containing (iy,ix) of dout[window] * [argmax(window) == (iy,ix)],
-// argmax = first maximum in (r, s) scan order among in-bounds taps, as ATen's max_pool2d_with_indices picks it.
-__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
+// ---------------------------------------------------------------- maxpool backward (two deterministic passes)
+// pass 1: idx[b,oy,ox,c] = tap (r*3+s) of the first maximum of the window in (r, s) scan order among in-bounds taps -- the element
+//         ATen's max_pool2d_with_indices routes the gradient to;
+// pass 2: dx[b,iy,ix,c] = sum over the (<= 4) windows containing (iy,ix) of dout[window] * [idx[window] == my tap]   (gather).
+__global__ void __launch_bounds__(256) maxpool_argmax_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ idx, int B, int H, int W,
+                                                            int C, int Ho, int Wo) {
+  const int CG = C >> 3;
+  const long long total = (long long)B * Ho * Wo * CG;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    long long p = i / CG;
+    const int ox = (int)(p % Wo);
+    p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float best[8];
+    int who[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; who[j] = -1; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int yy = 2 * oy - 1 + r;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int xx = 2 * ox - 1 + s;
+        if (xx < 0 || xx >= W) continue;
+        float v[8];
+        ld8(x + (((long long)b * H + yy) * W + xx) * C + cg * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (v[j] > best[j] || who[j] < 0) { best[j] = v[j]; who[j] = r * 3 + s; }
+      }
+    }
+    uint2 packed;
+    packed.x = (uint32_t)who[0] | ((uint32_t)who[1] << 8) | ((uint32_t)who[2] << 16) | ((uint32_t)who[3] << 24);
+    packed.y = (uint32_t)who[4] | ((uint32_t)who[5] << 8) | ((uint32_t)who[6] << 16) | ((uint32_t)who[7] << 24);
+    *reinterpret_cast<uint2*>(idx + i * 8) = packed;
+  }
+}
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ idx,
                                                          __nv_bfloat16* __restrict__ dx, int B, int H, int W, int C, int Ho, int Wo) {
   const int CG = C >> 3;
   const long long total = (long long)B * H * W * CG;
@@ -39,31 +76,20 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
     const int ox_lo = max(0, ix / 2), ox_hi = min(Wo - 1, (ix + 1) / 2);
     for (int oy = oy_lo; oy <= oy_hi; ++oy) {
       for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-        float best[8];
-        int who[8];
+        const long long o = (((long long)b * Ho + oy) * Wo + ox) * C + cg * 8;
+        const uint2 w8 = __ldg(reinterpret_cast<const uint2*>(idx + o));
+        const uint32_t me = (uint32_t)((iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1)));
+        const uint32_t me4 = me * 0x01010101u;
+        const uint32_t e0 = w8.x ^ me4, e1 = w8.y ^ me4;   // a zero byte = this window routes its gradient here
+        if (((e0 - 0x01010101u) & ~e0 & 0x80808080u) | ((e1 - 0x01010101u) & ~e1 & 0x80808080u)) {
+          float g[8];
+          ld8(dout + o, g);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; who[j] = -1; }
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const int yy = 2 * oy - 1 + r;
-          if (yy < 0 || yy >= H) continue;
-#pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const int xx = 2 * ox - 1 + s;
-            if (xx < 0 || xx >= W) continue;
-            float v[8];
-            ld8(x + (((long long)b * H + yy) * W + xx) * C + cg * 8, v);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (v[j] > best[j] || who[j] < 0) { best[j] = v[j]; who[j] = r * 3 + s; }
+          for (int j = 0; j < 4; ++j) {
+            if (((e0 >> (8 * j)) & 0xffu) == 0) acc[j] += g[j];
+            if (((e1 >> (8 * j)) & 0xffu) == 0) acc[4 + j] += g[4 + j];
           }
         }
-        const int me = (iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1));
-        float g[8];
-        ld8(dout + (((long long)b * Ho + oy) * Wo + ox) * C + cg * 8, g);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (who[j] == me) acc[j] += g[j];
       }
     }
     st8(dx + i * 8, acc);
@@ -192,16 +218,30 @@ __global__ void __launch_bounds__(256) fc_bwd_dw_partial_kernel(const float* __r
     }
   }
 }
-// dw[k][c] = sum_blk partial;  db[k] = sum_p dl[b,k,pix]   (grid: K blocks)
-__global__ void __launch_bounds__(256) fc_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ dl,
-                                                             float* __restrict__ dw, float* __restrict__ db, int B, int K, int C, int hw,
-                                                             int accumulate) {
-  const int k = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+// dw[k][c] = sum_blk partial   (grid: (C/32, K); 256 threads = 32 channels x 8 slices of the blocks)
+__global__ void __launch_bounds__(256) fc_bwd_dw_finalize_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ dw, int K, int C,
+                                                                int accumulate) {
+  __shared__ double sh[8][32];
+  const int k = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+  float a0 = 0.f, a1 = 0.f;
+  int b = slice;
+  for (; b + 8 < nblk; b += 16) {
+    a0 += partial[((size_t)b * K + k) * C + c];
+    a1 += partial[((size_t)(b + 8) * K + k) * C + c];
+  }
+  if (b < nblk) a0 += partial[((size_t)b * K + k) * C + c];
+  sh[slice][threadIdx.x & 31] = (double)a0 + (double)a1;
+  __syncthreads();
+  if (threadIdx.x < 32) {
     double s = 0.0;
-    for (int b = 0; b < nblk; ++b) s += (double)partial[((size_t)b * K + k) * C + c];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sh[i][threadIdx.x];
     dw[(size_t)k * C + c] = (accumulate ? dw[(size_t)k * C + c] : 0.f) + (float)s;
   }
+}
+// db[k] = sum_p dl[b,k,pix]   (grid: K blocks)
+__global__ void __launch_bounds__(256) fc_bwd_db_kernel(const float* __restrict__ dl, float* __restrict__ db, int B, int K, int hw, int accumulate) {
+  const int k = blockIdx.x;
   __shared__ double red[256];
   double s = 0.0;
   for (int b = 0; b < B; ++b)
@@ -305,14 +345,20 @@ static int grid_for(long long n, int threads) {
 
 extern "C" {
 
-int hk_maxpool3x3s2_bwd(const void* dout, const void* x, void* dx, int B, int H, int W, int C, int Ho, int Wo, void* stream) {
+int hk_maxpool3x3s2_bwd(const void* dout, const void* x, void* dx, int B, int H, int W, int C, int Ho, int Wo, void* idx_ws,
+                        size_t idx_ws_bytes, void* stream) {
   using namespace hk;
-  HK_REQUIRE(dout && x && dx, "hk_maxpool3x3s2_bwd: null pointer");
+  HK_REQUIRE(dout && x && dx && idx_ws, "hk_maxpool3x3s2_bwd: null pointer");
+  HK_REQUIRE(idx_ws_bytes >= (size_t)B * Ho * Wo * C, "hk_maxpool3x3s2_bwd: index workspace too small (B*Ho*Wo*C bytes)");
   HK_REQUIRE(B > 0 && H > 0 && W > 0 && C >= 8 && (C & 7) == 0 && Ho == (H + 2 - 3) / 2 + 1 && Wo == (W + 2 - 3) / 2 + 1,
              "hk_maxpool3x3s2_bwd: bad shape");
+  maxpool_argmax_kernel<<<grid_for((long long)B * Ho * Wo * (C >> 3), 256), 256, 0, as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(idx_ws), B, H, W, C, Ho, Wo);
+  int rc = check_launch("maxpool_argmax_kernel");
+  if (rc) return rc;
   const long long total = (long long)B * H * W * (C >> 3);
   maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dout),
-                                                                         static_cast<const __nv_bfloat16*>(x),
+                                                                         static_cast<const uint8_t*>(idx_ws),
                                                                          static_cast<__nv_bfloat16*>(dx), B, H, W, C, Ho, Wo);
   return check_launch("maxpool_bwd_kernel");
 }
@@ -355,8 +401,12 @@ int hk_head_bwd(const float* g_up, const void* feat, const float* w_fc, float* d
   fc_bwd_dw_partial_kernel<<<nblk, 256, 0, s>>>(dlogits_ws, static_cast<const __nv_bfloat16*>(feat), static_cast<float*>(ws), B, K, C, hw);
   rc = check_launch("fc_bwd_dw_partial_kernel");
   if (rc) return rc;
-  fc_bwd_finalize_kernel<<<K, 256, 0, s>>>(static_cast<const float*>(ws), nblk, dlogits_ws, dw_fc, db_fc, B, K, C, hw, accumulate);
-  return check_launch("fc_bwd_finalize_kernel");
+  HK_REQUIRE(C % 32 == 0, "hk_head_bwd: C must be a multiple of 32");
+  fc_bwd_dw_finalize_kernel<<<dim3(C / 32, K), 256, 0, s>>>(static_cast<const float*>(ws), nblk, dw_fc, K, C, accumulate);
+  rc = check_launch("fc_bwd_dw_finalize_kernel");
+  if (rc) return rc;
+  fc_bwd_db_kernel<<<K, 256, 0, s>>>(dlogits_ws, db_fc, B, K, hw, accumulate);
+  return check_launch("fc_bwd_db_kernel");
 }
 
 size_t hk_stem_wgrad_workspace_bytes(void) { return (size_t)hk::sm_count() * 2 * 147 * 64 * sizeof(float); }

@@ -316,13 +316,17 @@ def stem_wgrad(x_nchw: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, ws: Opt
     return dw
 
 
-def maxpool3x3s2_bwd(dout: torch.Tensor, x: torch.Tensor, dx: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _need_cuda(dout, x, dx)
+def maxpool3x3s2_bwd(dout: torch.Tensor, x: torch.Tensor, dx: Optional[torch.Tensor] = None,
+                     idx_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(dout, x, dx, idx_ws)
     B, H, W, Cc = x.shape
     Ho, Wo = dout.shape[1], dout.shape[2]
     if dx is None:
         dx = torch.empty_like(x)
-    check(lib().hk_maxpool3x3s2_bwd(ptr(dout), ptr(x), ptr(dx), B, H, W, Cc, Ho, Wo, stream_ptr()), "hk_maxpool3x3s2_bwd")
+    if idx_ws is None:
+        idx_ws = torch.empty(B * Ho * Wo * Cc, device=x.device, dtype=torch.uint8)
+    check(lib().hk_maxpool3x3s2_bwd(ptr(dout), ptr(x), ptr(dx), B, H, W, Cc, Ho, Wo, ptr(idx_ws), idx_ws.numel(), stream_ptr()),
+          "hk_maxpool3x3s2_bwd")
     return dx
 
 

@@ -78,6 +78,7 @@ class TrainEngine:
         self.stem = _ConvT("stem", net.conv1, net.bn1, B, H, W, dev)
         self.a0 = torch.empty((B, h2, w2, 64), device=dev, dtype=bf)
         self.p0 = torch.empty((B, h4, w4, 64), device=dev, dtype=bf)
+        self.pool_idx = torch.empty(B * h4 * w4 * 64, device=dev, dtype=torch.uint8)
         self.blocks = []
         h, w = h4, w4
         for i, blk in enumerate(net.blocks()):
@@ -207,7 +208,7 @@ class TrainEngine:
         d = self._buf("d0", feat.shape)
         ops.head_bwd(self.g_up, feat, fc_w, d, self._g(net.fc.weight)[:K].view(K, 512), self._g(net.fc.bias)[:K],
                      dlogits_ws=self.dlogits_lr, ws=self.head_ws)
-        n += 4
+        n += 5
         parity = 1
         for bi in range(len(self.blocks) - 1, -1, -1):
             c1, c2, ds, a1, sc, out = self.blocks[bi]
@@ -233,9 +234,9 @@ class TrainEngine:
                 n += self._dgrad(c1, dy1, dx, residual=dm)
             d, parity = dx, parity ^ 1
         da0 = self._buf("da0", self.a0.shape)
-        ops.maxpool3x3s2_bwd(d, self.a0, dx=da0)
+        ops.maxpool3x3s2_bwd(d, self.a0, dx=da0, idx_ws=self.pool_idx)
         dy0 = self._buf("dy", st.y.shape)
-        n += 1 + self._bn_bwd(st, da0, self.a0, dy0)
+        n += 2 + self._bn_bwd(st, da0, self.a0, dy0)
         ops.stem_wgrad(self.x, dy0, self._g(net.conv1.weight), ws=self.wgrad_ws)
         n += 2
         return n

@@ -213,8 +213,10 @@ HK_API size_t hk_stem_wgrad_workspace_bytes(void);
 HK_API int hk_stem_wgrad(const float* x_nchw, const void* dy_nhwc, float* dw_oihw, int accumulate, int B, int H, int W, void* ws,
                          size_t ws_bytes, void* stream);
 
-/* MaxPool2d(3,2,1) backward (first-maximum routing, as ATen's indices). x = pool input (post-ReLU stem), NHWC bf16. */
-HK_API int hk_maxpool3x3s2_bwd(const void* dout, const void* x, void* dx, int B, int H, int W, int C, int Ho, int Wo, void* stream);
+/* MaxPool2d(3,2,1) backward (first-maximum routing, as ATen's indices). x = pool input (post-ReLU stem), NHWC bf16.
+ * idx_ws: B*Ho*Wo*C bytes (the per-window argmax taps computed in a first pass). */
+HK_API int hk_maxpool3x3s2_bwd(const void* dout, const void* x, void* dx, int B, int H, int W, int C, int Ho, int Wo, void* idx_ws,
+                               size_t idx_ws_bytes, void* stream);
 
 /* Head in training: K-row scoring conv + bilinear upsample WITHOUT the sigmoid (hk_bce_fwd_bwd takes logits), ATen's exact
  * operation order; and its backward: upsample-backward of g_up (B,K,H,W) to dlogits_ws (B,K,h,w), then
