@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--keypoints", type=int, default=4, help="K (config.py: 4; BASELINE config 5 also quotes 16 and 32)")
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default="", help="write the per-launch timing table to this JSON file")
@@ -155,7 +156,8 @@ def run_reference_arm(args, rank):
     if rank != 0:
         return
     ref = CpuReference(args.height, args.width)
-    n_per_step = 4
+    # bounded sample: ~0.2-0.5 s per image on the host cores; keep the whole run within a few minutes whatever --steps is
+    n_per_step = 4 if args.steps <= 30 else (2 if args.steps <= 100 else 1)
     for _ in range(max(args.warmup, 1)):
         ref.run(1)
     dt = 0.0
@@ -356,7 +358,10 @@ def run_ours(args, rank, world, local_rank):
         achieved = tc_flops / (tc_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops"]
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all launches of one step)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": ncu_conv_traffic_per_step(B, H, W, K_KEYPOINTS, args.precision),
+                "traffic_note": "DRAM bytes read+written by the 35 conv launches of one step (ncu, profiles/r01b_step_per_launch_dram.json); "
+                                "algorithmic activation traffic of those launches: in+out+residual of every conv",
                 "peak_source": f"{peaks['source']} burst bf16 ({peak}); sustained {peaks['bf16_tflops_sustained']}",
                 "launches": len(tc), "ms_in_step": tc_ms, "share_of_step": tc_ms / sum(r["ms"] for r in rows)}
     else:
@@ -405,8 +410,26 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def ncu_conv_traffic_per_step(B, H, W, K, precision):
+    """DRAM bytes (read + write) of the 35 tcgen05 conv launches of one step from the committed ncu capture
+    (profiles/r01b_step_per_launch_dram.json: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over bench.py's default
+    workload).  None for any other workload."""
+    if (B, H, W, K, precision) != (64, 480, 640, 4, "bf16"):
+        return None
+    p = os.path.join(ROOT, "profiles", "r01b_step_per_launch_dram.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        rows = [r for r in json.load(f) if "conv_tc" in r["kernel"]]
+    if len(rows) < 35:
+        return None
+    return float(sum(r["dram__bytes_read.sum"] + r["dram__bytes_write.sum"] for r in rows[:35]))  # any 35 consecutive = one step
+
+
 def main():
+    global K_KEYPOINTS
     args = parse_args()
+    K_KEYPOINTS = args.keypoints
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

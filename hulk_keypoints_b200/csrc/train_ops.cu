@@ -137,7 +137,41 @@ static int bce_blocks(long long n) {
 
 }  // namespace hk
 
+namespace hk {
+// sigmoid of model.py:21 and its autograd (sigmoid_backward: g_z = (g_p * (1 - p)) * p, ATen's operation order), for the split
+// train step where the loss is computed by the caller (an unmodified train.py: nn.BCELoss on model.forward(img).double()).
+__global__ void __launch_bounds__(256) sigmoid_fwd_kernel(const float* __restrict__ z, float* __restrict__ p, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = 1.0f / (1.0f + expf(-z[i]));
+}
+__global__ void __launch_bounds__(256) sigmoid_bwd_kernel(const float* __restrict__ p, const float* __restrict__ gp, float* __restrict__ gz,
+                                                         long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float pv = p[i];
+    gz[i] = __fmul_rn(__fmul_rn(gp[i], __fsub_rn(1.0f, pv)), pv);
+  }
+}
+}  // namespace hk
+
 extern "C" {
+
+int hk_sigmoid_fwd(const float* logits, float* heat, long long n, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(logits && heat && n > 0, "hk_sigmoid_fwd: bad argument");
+  long long blocks = ceil_div_ll(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sigmoid_fwd_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(logits, heat, n);
+  return check_launch("sigmoid_fwd_kernel");
+}
+
+int hk_sigmoid_bwd(const float* heat, const float* grad_heat, float* grad_logits, long long n, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(heat && grad_heat && grad_logits && n > 0, "hk_sigmoid_bwd: bad argument");
+  long long blocks = ceil_div_ll(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sigmoid_bwd_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(heat, grad_heat, grad_logits, n);
+  return check_launch("sigmoid_bwd_kernel");
+}
 
 int hk_gauss_targets(const float* uv, int B, int K, int H, int W, float sigma, void* out, int out_dtype, void* stream) {
   using namespace hk;

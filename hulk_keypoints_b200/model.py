@@ -186,6 +186,13 @@ class KeypointsGauss(nn.Module):
 
     def forward(self, x):
         if self.training:
+            # B200 path: bf16 tensor-core forward now, tcgen05 dgrad/wgrad when autograd calls back (train_ops._EngineForward).
+            # The torch-autograd graph remains for CPU tensors (CPU tests of the host logic), the fp32 mode, odd shapes, and
+            # train_backend="autograd" (the parity checker).
+            if (x.is_cuda and self.precision == "bf16" and getattr(self, "train_backend", "hk") == "hk" and x.dim() == 4
+                    and x.shape[2] % 8 == 0 and x.shape[3] % 8 == 0 and min(x.shape[2:]) >= 32 and torch.is_grad_enabled()):
+                from .train_ops import engine_forward
+                return engine_forward(self, x)
             return self._forward_autograd(x)
         if not x.is_cuda:
             raise RuntimeError("KeypointsGauss inference runs on CUDA (B200) only: there is no CPU fallback; "

@@ -165,6 +165,10 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ the step
     def _enqueue(self) -> int:
+        """pack + forward + fused loss + backward: the whole step."""
+        return self._enqueue_forward() + self._enqueue_loss() + self._enqueue_backward()
+
+    def _enqueue_forward(self) -> int:
         net, K = self.net, self.K
         n = 0
         # weights of this step (parameters change every optimizer step)
@@ -197,14 +201,24 @@ class TrainEngine:
         fc_b = net.fc.bias.data[:K]
         ops.head_logits(feat, fc_w, fc_b, self.H, self.W, out=self.logits_up, logits_ws=self.logits_lr)
         n += 3
-        # ---------------- loss: sigmoid + BCE(mean) forward and d/dlogits in one pass ----------------
+        return n
+
+    def _enqueue_loss(self) -> int:
+        """sigmoid + BCE(mean) forward and d/dlogits in one pass."""
+        K = self.K
         tgt = self.target
         tcode = 0 if tgt is None else ops.dtype_code(tgt.dtype)
         check(lib().hk_bce_fwd_bwd(ptr(self.logits_up), 1, ptr(tgt), tcode, None if tgt is not None else ptr(self.uv), self.B, K, self.H,
                                    self.W, C.c_float(self.sigma), ptr(self.loss), ptr(self.g_up), ptr(self.bce_ws), self.bce_ws.numel(),
                                    stream_ptr()), "hk_bce_fwd_bwd")
-        n += 2
-        # ---------------- backward ----------------
+        return 2
+
+    def _enqueue_backward(self) -> int:
+        """From self.g_up = dL/d(upsampled logits) to every parameter gradient."""
+        net, K, st = self.net, self.K, self.stem
+        n = 0
+        feat = self.blocks[-1][5]
+        fc_w = net.fc.weight.data[:K].view(K, 512)
         d = self._buf("d0", feat.shape)
         ops.head_bwd(self.g_up, feat, fc_w, d, self._g(net.fc.weight)[:K].view(K, 512), self._g(net.fc.bias)[:K],
                      dlogits_ws=self.dlogits_lr, ws=self.head_ws)
@@ -280,6 +294,60 @@ class TrainEngine:
                 self.graph, self._graph_key = g, key
             self.graph.replay()
         return self.loss
+
+    # ------------------------------------------------------------------ split step: the caller owns the loss (unmodified train.py)
+    def _run(self, name: str, fn) -> None:
+        """Eager, or capture-once / replay of one of the split graphs."""
+        if not self.use_cuda_graph:
+            fn()
+            return
+        key = self._key()
+        graphs = self.__dict__.setdefault("_split_graphs", {})
+        ent = graphs.get(name)
+        if ent is None or ent[1] != key:
+            if name == "fwd":  # the warm-up run advances the BN buffers once more than the captured replay: restore them
+                saved = [(c.bn.running_mean.clone(), c.bn.running_var.clone(), c.bn.num_batches_tracked.clone()) for c in self.convs]
+            fn()
+            torch.cuda.current_stream().synchronize()
+            if name == "fwd":
+                for c, (m, v, t) in zip(self.convs, saved):
+                    c.bn.running_mean.copy_(m); c.bn.running_var.copy_(v); c.bn.num_batches_tracked.copy_(t)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            graphs[name] = ent = (g, key)
+        ent[0].replay()
+
+    def forward_heatmaps(self, img: torch.Tensor) -> torch.Tensor:
+        """Train-mode forward only: (B,3,H,W) -> sigmoid heatmaps (B,K,H,W) fp32 (model.py:19-22 under model.train()); activations
+        are kept for backward_from_heatmap_grad().  Returns a view of an engine buffer."""
+        if not img.is_cuda or tuple(img.shape) != (self.B, 3, self.H, self.W):
+            raise ValueError(f"expected a CUDA image batch of shape {(self.B, 3, self.H, self.W)}, got {tuple(img.shape)} on {img.device}")
+        if "heat" not in self.__dict__:
+            self.heat = torch.empty_like(self.logits_up)
+            self.g_heat = torch.empty_like(self.logits_up)
+        n = self.logits_up.numel()
+
+        def fn():
+            self._enqueue_forward()
+            check(lib().hk_sigmoid_fwd(ptr(self.logits_up), ptr(self.heat), C.c_longlong(n), stream_ptr()), "hk_sigmoid_fwd")
+
+        with torch.no_grad():
+            self.x.copy_(img)
+            self._run("fwd", fn)
+        return self.heat
+
+    def backward_from_heatmap_grad(self, grad_heat: torch.Tensor) -> None:
+        """dL/dheat (B,K,H,W) fp32 -> all parameter gradients (self.flat_grad), through sigmoid, head and backbone."""
+        n = self.logits_up.numel()
+
+        def fn():
+            check(lib().hk_sigmoid_bwd(ptr(self.heat), ptr(self.g_heat), ptr(self.g_up), C.c_longlong(n), stream_ptr()), "hk_sigmoid_bwd")
+            self._enqueue_backward()
+
+        with torch.no_grad():
+            self.g_heat.copy_(grad_heat)
+            self._run("bwd", fn)
 
     def grad(self, p: torch.nn.Parameter) -> torch.Tensor:
         return self.grad_of[id(p)]

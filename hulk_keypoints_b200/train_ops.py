@@ -56,6 +56,29 @@ class _EngineStep(torch.autograd.Function):
         return (None, None, None, None) + tuple(eng.grad(p) * g for p in eng.params)
 
 
+class _EngineForward(torch.autograd.Function):
+    """KeypointsGauss.forward in train() mode on the B200 engine: returns the heatmaps; autograd hands dL/dheat back and the engine's
+    backward kernels produce every parameter gradient -- so an UNMODIFIED train.py (model.forward(img).double() -> nn.BCELoss ->
+    loss.backward() -> optimizer.step(), train.py:18-26,33-36) trains on tcgen05."""
+
+    @staticmethod
+    def forward(ctx, engine, img, *params):
+        ctx.engine = engine
+        return engine.forward_heatmaps(img).clone()
+
+    @staticmethod
+    def backward(ctx, grad_heat):
+        eng = ctx.engine
+        eng.backward_from_heatmap_grad(grad_heat.to(torch.float32).contiguous())
+        return (None, None) + tuple(eng.grad(p).clone() for p in eng.params)
+
+
+def engine_forward(model, img: torch.Tensor) -> torch.Tensor:
+    """Differentiable train-mode heatmaps (B,K,H,W) computed by the TrainEngine (see _EngineForward)."""
+    eng = model.train_engine(img.shape[0], img.shape[2], img.shape[3])
+    return _EngineForward.apply(eng, img.float().contiguous(), *eng.params)
+
+
 def engine_loss(model, img: torch.Tensor, target: Optional[torch.Tensor] = None, uv: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Differentiable fp64 loss of one batch computed by the B200 TrainEngine (bf16 tensor-core forward/backward)."""
     eng = model.train_engine(img.shape[0], img.shape[2], img.shape[3])

@@ -213,6 +213,11 @@ HK_API size_t hk_stem_wgrad_workspace_bytes(void);
 HK_API int hk_stem_wgrad(const float* x_nchw, const void* dy_nhwc, float* dw_oihw, int accumulate, int B, int H, int W, void* ws,
                          size_t ws_bytes, void* stream);
 
+/* Sigmoid of src/model.py:21 and its backward (g_z = (g_p*(1-p))*p), for the split train step in which the CALLER computes the
+ * loss on the heatmaps (unmodified train.py:21-25) and autograd hands dL/dheat back. */
+HK_API int hk_sigmoid_fwd(const float* logits, float* heat, long long n, void* stream);
+HK_API int hk_sigmoid_bwd(const float* heat, const float* grad_heat, float* grad_logits, long long n, void* stream);
+
 /* MaxPool2d(3,2,1) backward (first-maximum routing, as ATen's indices). x = pool input (post-ReLU stem), NHWC bf16.
  * idx_ws: B*Ho*Wo*C bytes (the per-window argmax taps computed in a first pass). */
 HK_API int hk_maxpool3x3s2_bwd(const void* dout, const void* x, void* dx, int B, int H, int W, int C, int Ho, int Wo, void* idx_ws,

@@ -147,3 +147,34 @@ def test_dropin_loss_backward_through_engine():
     # same loss as the on-the-fly-target path (targets are bit-equal to gauss_2d_batch)
     l_uv = eng.forward_backward(img, uv=uv).item()
     assert abs(l_uv - loss.item()) < 1e-12 * abs(l_uv)
+
+
+def test_unmodified_train_py_step_runs_on_the_engine():
+    """The literal sequence of reference train.py:18-26,33-36 -- pred = model.forward(img).double(); nn.BCELoss()(pred, gt);
+    loss.backward(); optimizer.step() -- goes through the TrainEngine (model.forward in train mode is engine-backed) and gives the
+    same loss and gradients as the fused path."""
+    torch.manual_seed(6)
+    m = hk.KeypointsGauss(4).cuda().train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4, weight_decay=1e-4)
+    img, uv = synth(torch.Generator().manual_seed(13), 2, 64, 96)
+    gt = torch.stack([hk.gauss_2d_batch(96, 64, 8, uv[b, :, 0], uv[b, :, 1]) for b in range(2)])
+    opt.zero_grad()
+    pred = m.forward(img).double()
+    assert pred.requires_grad and pred.shape == (2, 4, 64, 96)
+    loss = torch.nn.BCELoss()(pred, gt)
+    loss.backward()
+    eng = m.train_engine(2, 64, 96)
+    split = {n: p.grad.clone() for n, p in m.named_parameters()}
+    fused_loss = eng.forward_backward(img, uv=uv).item()
+    assert abs(fused_loss - loss.item()) < 1e-6 * abs(fused_loss)
+    for n, p in m.named_parameters():
+        g = eng.grad(p)
+        if g.norm() == 0:
+            assert split[n].norm() == 0, n
+        else:
+            assert cosine(split[n], g) > 0.9999, (n, cosine(split[n], g))
+    before = m.resnet.resnet34_8s.layer4[2].conv2.weight.detach().clone()
+    opt.step()
+    assert not torch.equal(before, m.resnet.resnet34_8s.layer4[2].conv2.weight)
+    # eval() still serves inference from the updated weights
+    assert m.eval()(img).shape == (2, 4, 64, 96)
