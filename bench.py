@@ -45,7 +45,11 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"],
+                    help="ours: libhulk_sm100 kernels; reference: the reference's CPU path (oracle port) on the host cores; torch_gpu: the "
+                         "same network through torch/cuDNN on this GPU (same-box competitor, SURVEY.md §8d; informational)")
+    ap.add_argument("--torch-dtype", default="fp32", choices=["fp32", "bf16"], help="torch_gpu arm: fp32 (TF32 off) or bf16 autocast + channels_last")
+    ap.add_argument("--as-written-head", action="store_true", help="torch_gpu arm: evaluate and upsample all 1000 fc channels, then slice (model.py:21)")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
@@ -178,6 +182,59 @@ def run_reference_arm(args, rank):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- same-box torch/cuDNN arm
+def run_torch_gpu(args, rank, world, local_rank):
+    """The same network evaluated by torch (cuDNN convs, ATen upsample/sigmoid, torch argmax) on this GPU: eval-mode BN, no_grad.
+    Uses the parameters of our KeypointsGauss through its torch graph (the one the parity tests check against) -- none of our kernels."""
+    import torch.nn.functional as F
+
+    import hulk_keypoints_b200 as hk
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    B, H, W, K = args.batch, args.height, args.width, K_KEYPOINTS
+    torch.manual_seed(0)
+    model = hk.KeypointsGauss(K, img_height=H, img_width=W).to(dev).eval()
+    net = model.resnet.resnet34_8s
+    bf16 = args.torch_dtype == "bf16"
+    if bf16:
+        net = net.to(memory_format=torch.channels_last)
+    x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(1000 + rank)).to(dev)
+    if bf16:
+        x = x.contiguous(memory_format=torch.channels_last)
+
+    def step():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+            feat = net.features(x)
+            if args.as_written_head:
+                up = F.interpolate(net.fc(feat), size=(H, W), mode="bilinear", align_corners=True)   # all 1000 channels
+                heat = torch.sigmoid(up[:, :K])
+            else:
+                heat = torch.sigmoid(F.interpolate(F.conv2d(feat, net.fc.weight[:K], net.fc.bias[:K]), size=(H, W), mode="bilinear",
+                                                   align_corners=True))
+            flat = heat.float().reshape(B, K, -1).argmax(-1)
+            return torch.stack([flat // W, flat % W], -1)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record(); e1.synchronize()
+    ms = e0.elapsed_time(e1)
+    if rank == 0:
+        print(json.dumps({"impl": "torch_gpu", "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                          "dtype": "bf16 autocast, channels_last" if bf16 else "f32 (TF32 off)", "data": "synthetic",
+                          "config": {"workload": f"torch/cuDNN eval forward + torch argmax, batch {B}, {H}x{W}, K={K}, "
+                                                 f"{'1000-channel head as written' if args.as_written_head else 'K-row head'}"}}), flush=True)
 
 
 # --------------------------------------------------------------------------------------------- our arm
@@ -438,6 +495,9 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    if args.impl == "torch_gpu":
+        run_torch_gpu(args, rank, 1, local_rank)
+        return
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

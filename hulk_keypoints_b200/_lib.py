@@ -28,7 +28,7 @@ EXPORTS = (
     "hk_stem_conv_fwd", "hk_bn_workspace_bytes", "hk_bn_train_stats", "hk_bn_apply_fwd", "hk_bn_train_bwd",
     "hk_pack_conv_weights_dgrad", "hk_zero_insert2x", "hk_conv_wgrad_workspace_bytes", "hk_conv_wgrad",
     "hk_stem_wgrad_workspace_bytes", "hk_stem_wgrad", "hk_maxpool3x3s2_bwd", "hk_head_logits_fwd",
-    "hk_head_bwd_workspace_bytes", "hk_head_bwd", "hk_sigmoid_fwd", "hk_sigmoid_bwd",
+    "hk_head_bwd_workspace_bytes", "hk_head_bwd", "hk_sigmoid_fwd", "hk_sigmoid_bwd", "hk_pack_conv_weights_many",
 )
 
 
@@ -105,6 +105,8 @@ def _declare(lib):
     lib.hk_head_bwd_workspace_bytes.argtypes = [i, i, i, i, i]
     lib.hk_head_bwd.restype = i
     lib.hk_head_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp, sz, vp]
+    lib.hk_pack_conv_weights_many.restype = i
+    lib.hk_pack_conv_weights_many.argtypes = [vp, i, ll, vp]
     lib.hk_sigmoid_fwd.restype = i
     lib.hk_sigmoid_fwd.argtypes = [vp, vp, ll, vp]
     lib.hk_sigmoid_bwd.restype = i

@@ -40,6 +40,31 @@ pack_weights_dgrad_kernel(const float* __restrict__ w_oihw, __nv_bfloat16* __res
   }
 }
 
+// All convolutions of the network in ONE launch (training repacks the weights every step): blockIdx.y = item, the x index space of an
+// item is [0, n) for the forward layout (cout, khw, cin) followed by [n, 2n) for the data-gradient layout (cin, khw flipped, cout).
+__global__ void __launch_bounds__(256) pack_weights_many_kernel(const HkPackItem* __restrict__ items) {
+  const HkPackItem it = items[blockIdx.y];
+  const long long n = (long long)it.cout * it.cin * it.khw;
+  const long long total = it.w_dgrad ? 2 * n : n;
+  const float* __restrict__ w = it.w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (i < n) {
+      const int c = (int)(i % it.cin);
+      const long long r = i / it.cin;
+      const int t = (int)(r % it.khw);
+      const int o = (int)(r / it.khw);
+      static_cast<__nv_bfloat16*>(it.w_fwd)[i] = __float2bfloat16_rn(__ldg(w + ((size_t)o * it.cin + c) * it.khw + t));
+    } else {
+      const long long j = i - n;
+      const int co = (int)(j % it.cout);
+      const long long r = j / it.cout;
+      const int t = (int)(r % it.khw);
+      const int ci = (int)(r / it.khw);
+      static_cast<__nv_bfloat16*>(it.w_dgrad)[j] = __float2bfloat16_rn(__ldg(w + ((size_t)co * it.cin + ci) * it.khw + (it.khw - 1 - t)));
+    }
+  }
+}
+
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                                const float* __restrict__ var, float eps, int cout, float* __restrict__ scale,
                                float* __restrict__ bias) {
@@ -92,4 +117,14 @@ extern "C" int hk_pack_conv_weights_dgrad(const float* w_oihw, int cout, int cin
   if (blocks > 148 * 8) blocks = 148 * 8;
   pack_weights_dgrad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_oihw, static_cast<__nv_bfloat16*>(w_out), cout, cin, kh, kw);
   return check_launch("pack_weights_dgrad_kernel");
+}
+
+extern "C" int hk_pack_conv_weights_many(const HkPackItem* items_dev, int n_items, long long max_elems, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(items_dev && n_items > 0 && max_elems > 0, "hk_pack_conv_weights_many: bad argument");
+  long long bx = ceil_div_ll(2 * max_elems, 256 * 8);  // 8 elements per thread for the largest item
+  if (bx > 1024) bx = 1024;
+  if (bx < 1) bx = 1;
+  pack_weights_many_kernel<<<dim3((unsigned)bx, (unsigned)n_items), 256, 0, as_stream(stream)>>>(items_dev);
+  return check_launch("pack_weights_many_kernel");
 }

@@ -105,6 +105,8 @@ class TrainEngine:
         self.wgrad_ws = torch.empty(max(wg, int(lib().hk_stem_wgrad_workspace_bytes())), device=dev, dtype=torch.uint8)
         self.head_ws = torch.empty(int(lib().hk_head_bwd_workspace_bytes(B, K, 512, h, w)), device=dev, dtype=torch.uint8)
         self._scratch: Dict[Tuple, torch.Tensor] = {}
+        self._pack_key = None
+        self._pack_items: Optional[torch.Tensor] = None
         self._bn_counters = [c.bn.num_batches_tracked for c in self.convs]
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_key = None
@@ -122,6 +124,25 @@ class TrainEngine:
 
     def _g(self, p) -> torch.Tensor:
         return self.grad_of[id(p)]
+
+    def _pack_all(self) -> int:
+        """Every conv weight -> bf16 forward + data-gradient layouts in one launch (hk_pack_conv_weights_many)."""
+        import numpy as np
+        key = tuple(c.conv.weight.data_ptr() for c in self.convs)
+        if self._pack_items is None or key != self._pack_key:
+            dt = np.dtype([("w", "<u8"), ("f", "<u8"), ("d", "<u8"), ("cout", "<i4"), ("cin", "<i4"), ("khw", "<i4"), ("r", "<i4")])
+            arr = np.zeros(len(self.convs) - 1, dtype=dt)
+            for i, c in enumerate(self.convs[1:]):
+                arr[i] = (c.conv.weight.data_ptr(), c.w_fwd.data_ptr(), c.w_dgrad.data_ptr(), c.cout, c.cin, c.k * c.k, 0)
+            self._pack_items = torch.from_numpy(arr.view(np.uint8).copy()).to(self.device)
+            self._pack_key = key
+            self._pack_max = max(c.cout * c.cin * c.k * c.k for c in self.convs[1:])
+            for c in self.convs:  # scale = 1 / bias = 0 of the raw convs: constant
+                c.one_out.fill_(1.0)
+                c.zero_out.zero_()
+        check(lib().hk_pack_conv_weights_many(ptr(self._pack_items), len(self.convs) - 1, C.c_longlong(self._pack_max), stream_ptr()),
+              "hk_pack_conv_weights_many")
+        return 1
 
     def _pack(self, c: _ConvT, with_dgrad: bool) -> int:
         w = c.conv.weight.data
@@ -173,9 +194,7 @@ class TrainEngine:
         n = 0
         # weights of this step (parameters change every optimizer step)
         check(lib().hk_stem_pack_weights(ptr(net.conv1.weight.data), ptr(self.stem_w), stream_ptr()), "hk_stem_pack_weights")
-        n += 1 + self._pack(self.stem, with_dgrad=False)
-        for c in self.convs[1:]:
-            n += self._pack(c, with_dgrad=True)
+        n += 1 + self._pack_all()
         # ---------------- forward (train mode) ----------------
         st = self.stem
         ops.stem_conv(self.x, self.stem_w, st.one_out, st.zero_out, relu=False, out=st.y)

@@ -195,6 +195,15 @@ HK_API int hk_bn_train_bwd(const void* dout, const void* out_mask_or_null, const
                            const float* gamma, long long P, int C, float* dgamma, float* dbeta, int accumulate, void* dy,
                            void* dmasked_or_null, void* ws, size_t ws_bytes, void* stream);
 
+/* All convs of the network repacked in ONE launch (the training step repacks every step).  items_dev: device array of HkPackItem;
+ * w_dgrad may be NULL (stem: no data gradient).  max_elems = max over items of cout*cin*khw. */
+typedef struct HkPackItem {
+  const float* w;   /* (cout, cin, kh, kw) fp32 */
+  void* w_fwd;      /* (cout, kh, kw, cin) bf16 */
+  void* w_dgrad;    /* (cin, kh, kw, cout) bf16, taps flipped; or NULL */
+  int32_t cout, cin, khw, reserved;
+} HkPackItem;
+HK_API int hk_pack_conv_weights_many(const HkPackItem* items_dev, int n_items, long long max_elems, void* stream);
 /* Conv weights for the data gradient: (cout,cin,kh,kw) fp32 -> (cin, kh, kw, cout) bf16 with the taps flipped. */
 HK_API int hk_pack_conv_weights_dgrad(const float* w_oihw, int cout, int cin, int kh, int kw, void* w_out, void* stream);
 /* (B,h,w,C) bf16 -> (B,2h,2w,C) with the values at even (y,x) and zeros elsewhere: the data gradient of a stride-2 conv is the
