@@ -66,6 +66,22 @@ class FusedAdam:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
             self.flat_grad.div_(dist.get_world_size())
 
+    def all_reduce_range_async(self, begin: int, end: int):
+        """Start the sum all-reduce of flat_grad[begin:end] on NCCL's stream (it waits for the work already enqueued on the current
+        stream); returns the work handle, or None outside a multi-rank job.  finish_all_reduce() waits and averages."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or end <= begin:
+            return None
+        return dist.all_reduce(self.flat_grad[begin:end], op=dist.ReduceOp.SUM, async_op=True)
+
+    def finish_all_reduce(self, works) -> None:
+        import torch.distributed as dist
+        works = [w for w in works if w is not None]
+        for w in works:
+            w.wait()
+        if works:
+            self.flat_grad.div_(dist.get_world_size())
+
     @torch.no_grad()
     def step(self) -> None:
         self.step_count += 1

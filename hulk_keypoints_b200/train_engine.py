@@ -104,6 +104,11 @@ class TrainEngine:
         wg = max(ops.conv_wgrad_workspace_bytes(B, c.H, c.W, c.cin, c.cout, c.k, c.stride, c.pad, c.dil) for c in self.convs[1:])
         self.wgrad_ws = torch.empty(max(wg, int(lib().hk_stem_wgrad_workspace_bytes())), device=dev, dtype=torch.uint8)
         self.head_ws = torch.empty(int(lib().hk_head_bwd_workspace_bytes(B, K, 512, h, w)), device=dev, dtype=torch.uint8)
+        # first block of layer3: everything from here to the end of the parameter list (layer3, layer4, fc) is the "late" part
+        self.split_block = 7
+        first_late = self.blocks[self.split_block][0].conv.weight
+        self.late_offset = next(o for p, o in zip(self.params, offs) if p is first_late)
+        self._bwd_state = None
         self._scratch: Dict[Tuple, torch.Tensor] = {}
         self._pack_key = None
         self._pack_items: Optional[torch.Tensor] = None
@@ -232,18 +237,25 @@ class TrainEngine:
                                    stream_ptr()), "hk_bce_fwd_bwd")
         return 2
 
-    def _enqueue_backward(self) -> int:
-        """From self.g_up = dL/d(upsampled logits) to every parameter gradient."""
+    def _enqueue_backward(self, part: str = "all") -> int:
+        """From self.g_up = dL/d(upsampled logits) to every parameter gradient.  part "late" = head + layers 4..3 (the tail of the
+        flat gradient buffer, 91 % of its bytes), part "early" = layers 2..1 + stem: the data-parallel step all-reduces the tail
+        while the early layers are still being differentiated."""
         net, K, st = self.net, self.K, self.stem
         n = 0
-        feat = self.blocks[-1][5]
-        fc_w = net.fc.weight.data[:K].view(K, 512)
-        d = self._buf("d0", feat.shape)
-        ops.head_bwd(self.g_up, feat, fc_w, d, self._g(net.fc.weight)[:K].view(K, 512), self._g(net.fc.bias)[:K],
-                     dlogits_ws=self.dlogits_lr, ws=self.head_ws)
-        n += 5
-        parity = 1
-        for bi in range(len(self.blocks) - 1, -1, -1):
+        nb = len(self.blocks)
+        if part in ("all", "late"):
+            feat = self.blocks[-1][5]
+            fc_w = net.fc.weight.data[:K].view(K, 512)
+            d = self._buf("d0", feat.shape)
+            ops.head_bwd(self.g_up, feat, fc_w, d, self._g(net.fc.weight)[:K].view(K, 512), self._g(net.fc.bias)[:K],
+                         dlogits_ws=self.dlogits_lr, ws=self.head_ws)
+            n += 5
+            parity, hi = 1, nb
+        else:
+            d, parity, hi = self._bwd_state
+        lo = self.split_block if part == "late" else 0
+        for bi in range(hi - 1, lo - 1, -1):
             c1, c2, ds, a1, sc, out = self.blocks[bi]
             x_in = self.blocks[bi - 1][5] if bi > 0 else self.p0
             dy2 = self._buf("dy", c2.y.shape)
@@ -266,6 +278,13 @@ class TrainEngine:
             else:
                 n += self._dgrad(c1, dy1, dx, residual=dm)
             d, parity = dx, parity ^ 1
+        if part == "late":
+            # the hand-off gradient gets its own buffer: the early graph is executed more than once per capture (warm-up, capture,
+            # replay) and its ping-pong scratch would otherwise overwrite its own input
+            dh = self._buf("dh", d.shape)
+            dh.copy_(d)
+            self._bwd_state = (dh, parity, lo)
+            return n + 1
         da0 = self._buf("da0", self.a0.shape)
         ops.maxpool3x3s2_bwd(d, self.a0, dx=da0, idx_ws=self.pool_idx)
         dy0 = self._buf("dy", st.y.shape)
@@ -315,14 +334,15 @@ class TrainEngine:
         return self.loss
 
     # ------------------------------------------------------------------ split step: the caller owns the loss (unmodified train.py)
-    def _run(self, name: str, fn) -> None:
-        """Eager, or capture-once / replay of one of the split graphs."""
+    def _run(self, name: str, fn, name_key: Optional[str] = None) -> None:
+        """Eager, or capture-once / replay of one of the split graphs.  `name` "fwd" marks graphs that advance the BN buffers."""
         if not self.use_cuda_graph:
             fn()
             return
         key = self._key()
         graphs = self.__dict__.setdefault("_split_graphs", {})
-        ent = graphs.get(name)
+        gname = name_key or name
+        ent = graphs.get(gname)
         if ent is None or ent[1] != key:
             if name == "fwd":  # the warm-up run advances the BN buffers once more than the captured replay: restore them
                 saved = [(c.bn.running_mean.clone(), c.bn.running_var.clone(), c.bn.num_batches_tracked.clone()) for c in self.convs]
@@ -334,7 +354,7 @@ class TrainEngine:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 fn()
-            graphs[name] = ent = (g, key)
+            graphs[gname] = ent = (g, key)
         ent[0].replay()
 
     def forward_heatmaps(self, img: torch.Tensor) -> torch.Tensor:
@@ -367,6 +387,27 @@ class TrainEngine:
         with torch.no_grad():
             self.g_heat.copy_(grad_heat)
             self._run("bwd", fn)
+
+    # ------------------------------------------------------------------ two-phase step for comm/compute overlap
+    def forward_backward_late(self, img: torch.Tensor, uv: torch.Tensor) -> torch.Tensor:
+        """Phase 1 of the data-parallel step: forward + loss + backward of head, layer4, layer3 (gradients flat_grad[late_offset:])."""
+        if not img.is_cuda or tuple(img.shape) != (self.B, 3, self.H, self.W):
+            raise ValueError(f"expected a CUDA image batch of shape {(self.B, 3, self.H, self.W)}")
+
+        def fn():
+            self._enqueue_forward(); self._enqueue_loss(); self._enqueue_backward("late")
+
+        with torch.no_grad():
+            self.x.copy_(img)
+            self.uv.copy_(uv.reshape(self.B, self.K, 2))
+            self.target = None
+            self._run("fwd", fn, name_key="late")
+        return self.loss
+
+    def backward_early(self) -> None:
+        """Phase 2: backward of layer2, layer1 and the stem (gradients flat_grad[:late_offset])."""
+        with torch.no_grad():
+            self._run("bwd_early", lambda: self._enqueue_backward("early"))
 
     def grad(self, p: torch.nn.Parameter) -> torch.Tensor:
         return self.grad_of[id(p)]

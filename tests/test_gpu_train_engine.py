@@ -178,3 +178,19 @@ def test_unmodified_train_py_step_runs_on_the_engine():
     assert not torch.equal(before, m.resnet.resnet34_8s.layer4[2].conv2.weight)
     # eval() still serves inference from the updated weights
     assert m.eval()(img).shape == (2, 4, 64, 96)
+
+
+def test_two_phase_step_equals_single_phase(pair):
+    """The data-parallel step runs backward in two graphs (head+layer4+layer3, then layer2+layer1+stem) so the all-reduce of the
+    first part overlaps the second; gradients and loss are bit-identical to the one-graph step."""
+    m, _, eng, img, uv, loss, grads, _ = pair
+    ref_flat = eng.flat_grad.clone()
+    eng.flat_grad.zero_()
+    l = eng.forward_backward_late(img, uv).clone()
+    assert eng.flat_grad[: eng.late_offset].abs().sum().item() == 0.0        # early gradients not produced yet
+    assert torch.equal(eng.flat_grad[eng.late_offset:], ref_flat[eng.late_offset:])
+    eng.backward_early()
+    assert l.item() == loss.item() and torch.equal(eng.flat_grad, ref_flat)
+    names = [n for n, _ in m.named_parameters()]
+    first_late = names.index("resnet.resnet34_8s.layer3.0.conv1.weight")
+    assert eng.late_offset == sum((p.numel() + 3) // 4 * 4 for p in list(m.parameters())[:first_late])
