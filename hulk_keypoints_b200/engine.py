@@ -77,7 +77,7 @@ class InferenceEngine:
         self.stem_on_tensor_cores = True  # bf16 mode: tcgen05 stem; False keeps the fp32 CUDA-core stem
         self._packed: Optional[Dict[str, _PackedConv]] = None
         self._packed_key = None
-        self._plans: Dict[Tuple[int, int, int], _Plan] = {}
+        self._plans: Dict[Tuple[int, int, int, int], _Plan] = {}
         self.device = None
 
     # ---- weights ----
@@ -161,8 +161,10 @@ class InferenceEngine:
             ops.argmax_decode(plan.heat, yx=plan.yx, maxval=plan.maxval, ws=plan.argmax_ws, want_max=True); n += 2
         return n
 
-    def plan_for(self, B: int, H: int, W: int) -> _Plan:
-        key = (B, H, W)
+    def plan_for(self, B: int, H: int, W: int, slot: int = 0) -> _Plan:
+        """Buffers + CUDA graph for one input shape.  `slot` selects an independent copy (own input / output buffers and graph) so a
+        caller can fill slot 1's input while slot 0 computes (double-buffered serving, see KeypointsGauss.staging_input)."""
+        key = (B, H, W, slot)
         p = self._plans.get(key)
         if p is None:
             if H < 32 or W < 32:
@@ -170,6 +172,17 @@ class InferenceEngine:
             p = _Plan(self, B, H, W)
             self._plans[key] = p
         return p
+
+    def staging_input(self, B: int, H: int, W: int, slot: int = 0, uint8: bool = False) -> torch.Tensor:
+        """The plan's own input buffer ((B,3,H,W) fp32, or (B,H,W,3) uint8): copy host images straight into it and pass it to
+        forward() -- no device-to-device copy on the serving path."""
+        self._ensure_packed()
+        plan = self.plan_for(B, H, W, slot)
+        if not uint8:
+            return plan.x
+        if plan.x_u8 is None:
+            plan.x_u8 = torch.empty((B, H, W, 3), device=self.device, dtype=torch.uint8)
+        return plan.x_u8
 
     def run_plan(self, plan: _Plan, decode: bool) -> None:
         """Run the forward on `plan.x` (already filled) into plan.heat / plan.yx."""
@@ -186,8 +199,10 @@ class InferenceEngine:
             plan.graph, plan.graph_decode = g, (decode, plan.input_is_u8)
         plan.graph.replay()
 
-    def forward(self, x: torch.Tensor, decode: bool = False, clone: bool = True):
-        """(B,3,H,W) / (3,H,W) fp32, or (B,H,W,3) / (H,W,3) uint8 (cv2 layout), CUDA -> heat (B,K,H,W) fp32 [, yx (B,K,2)]."""
+    def forward(self, x: torch.Tensor, decode: bool = False, clone: bool = True, slot: int = 0):
+        """(B,3,H,W) / (3,H,W) fp32, or (B,H,W,3) / (H,W,3) uint8 (cv2 layout), CUDA -> heat (B,K,H,W) fp32 [, yx (B,K,2)].
+        clone=False returns views of the plan's buffers (valid until the next call on the same slot); when `x` IS the plan's own
+        input buffer (staging_input) no copy is made."""
         u8 = x.dtype == torch.uint8
         if x.dim() == 3:
             x = x.unsqueeze(0)
@@ -200,13 +215,16 @@ class InferenceEngine:
             B, H, W, _ = x.shape
         else:
             B, _, H, W = x.shape
-        plan = self.plan_for(B, H, W)
+        plan = self.plan_for(B, H, W, slot)
         with torch.no_grad():
             if u8 and self._stem_w_tc is not None:
                 if plan.x_u8 is None:
                     plan.x_u8 = torch.empty((B, H, W, 3), device=self.device, dtype=torch.uint8)
-                plan.x_u8.copy_(x)
+                if x.data_ptr() != plan.x_u8.data_ptr():
+                    plan.x_u8.copy_(x)
                 plan.input_is_u8 = True
+            elif not u8 and x.data_ptr() == plan.x.data_ptr():
+                plan.input_is_u8 = False
             else:
                 # fp32 path (and the fp32 correctness mode for uint8 input: ToTensor semantics, dataset.py:16)
                 # (tensor / tensor keeps IEEE division on the GPU; tensor / python-scalar would multiply by 1/255)

@@ -213,6 +213,24 @@ class KeypointsGauss(nn.Module):
     def _forward_autograd(self, x):
         return self.sigmoid(self.forward_logits(x))
 
+    def keypoints(self, x, slot: int = 0):
+        """Additive serving API: eval-mode forward + argmax decode -> (yx int32 (B,K,2) as (row, col), peak value fp32 (B,K)), without
+        copying the heatmaps out.  The results are views of engine buffers, valid until the next call on the same `slot`."""
+        if self.training:
+            raise RuntimeError("keypoints() is an inference call; use model.eval() first")
+        eng = self.engine()
+        _, yx = eng.forward(x, decode=True, clone=False, slot=slot)
+        B = yx.shape[0]
+        H, W = (x.shape[1], x.shape[2]) if x.dtype == torch.uint8 else (x.shape[-2], x.shape[-1])
+        return yx, eng.plan_for(B, H, W, slot).maxval
+
+    def staging_input(self, batch: int, height: int, width: int, slot: int = 0, uint8: bool = False):
+        """Device input buffer of serving slot `slot`: `buf.copy_(pinned_host_images, non_blocking=True)` then `keypoints(buf, slot)`;
+        two slots give H2D / compute double buffering with no device-to-device copy."""
+        if self.training:
+            raise RuntimeError("staging_input() is an inference call; use model.eval() first")
+        return self.engine().staging_input(batch, height, width, slot, uint8)
+
     def heatmaps_and_keypoints(self, x):
         """Additive API: eval-mode forward + argmax decode of every batch element -> (heat, yx int32 (B,K,2))."""
         if self.training:

@@ -281,3 +281,27 @@ def test_fused_adam_training_tracks_torch_adam():
                 assert torch.allclose(sa[k], sb[k], rtol=1e-3, atol=2 * 1e-4 * 3 + 1e-5), k
     # the model still serves inference after its parameters became views of the flat buffer
     assert a.eval()(rand_img(1, 1, 64, 96).cuda()).shape == (1, 4, 64, 96)
+
+
+def test_serving_api_staging_slots_match_forward(sd_cal):
+    """model.staging_input / model.keypoints (no device-to-device copy, no heatmap copy, two independent slots) give the same
+    keypoints and peak values as heatmaps_and_keypoints, for fp32 and uint8 inputs."""
+    m = make_model(sd_cal, "bf16")
+    x0, x1 = rand_img(31, 2, 96, 128), rand_img(32, 2, 96, 128)
+    ref = []
+    for x in (x0, x1):
+        heat, yx = m.heatmaps_and_keypoints(x.cuda())
+        ref.append((yx.clone(), heat.flatten(2).max(-1).values.clone()))
+    bufs = [m.staging_input(2, 96, 128, slot=j) for j in range(2)]
+    assert bufs[0].data_ptr() != bufs[1].data_ptr()
+    bufs[0].copy_(x0.pin_memory(), non_blocking=True)
+    bufs[1].copy_(x1.pin_memory(), non_blocking=True)
+    out = [m.keypoints(bufs[j], slot=j) for j in range(2)]        # slot 1 must not disturb slot 0's results
+    for j in range(2):
+        assert torch.equal(out[j][0], ref[j][0]) and torch.equal(out[j][1], ref[j][1])
+    u8 = torch.randint(0, 256, (2, 96, 128, 3), dtype=torch.uint8)
+    b8 = m.staging_input(2, 96, 128, slot=0, uint8=True)
+    b8.copy_(u8)
+    yx8, _ = m.keypoints(b8, slot=0)
+    _, yx_ref = m.heatmaps_and_keypoints(u8.cuda())
+    assert torch.equal(yx8, yx_ref)
