@@ -194,3 +194,30 @@ def test_two_phase_step_equals_single_phase(pair):
     names = [n for n, _ in m.named_parameters()]
     first_late = names.index("resnet.resnet34_8s.layer3.0.conv1.weight")
     assert eng.late_offset == sum((p.numel() + 3) // 4 * 4 for p in list(m.parameters())[:first_late])
+
+
+def test_engine_odd_shape_more_keypoints():
+    """B=3, 72x104 (multiples of 8 only: ragged 4x16 / 8x16 tiles everywhere, TMA clipping and zero fill), K=7 (two head groups)."""
+    torch.manual_seed(8)
+    m = hk.KeypointsGauss(7).cuda().train()
+    ref = hk.KeypointsGauss(7).cuda().train()
+    ref.load_state_dict(m.state_dict())
+    # a few steps so the weights are not the hostile raw init
+    from hulk_keypoints_b200.optim import FusedAdam
+    opt = FusedAdam(m.parameters(), lr=1e-3, weight_decay=1e-4)
+    gen = torch.Generator().manual_seed(21)
+    for _ in range(40):
+        img, uv = discs(gen, 3, 72, 104, K=4)
+        uv7 = torch.cat([uv, uv[:, :3]], 1)
+        train_ops.train_step(m, opt, img, uv7, sigma=8.0)
+    ref.load_state_dict(m.state_dict())
+    img, uv = discs(gen, 3, 72, 104, K=4)
+    uv7 = torch.cat([uv, uv[:, :3]], 1)
+    eng = m.train_engine(3, 72, 104)
+    loss = eng.forward_backward(img, uv=uv7).item()
+    loss_ref = train_ops.sigmoid_bce_loss(ref.forward_logits(img), uv=uv7, sigma=8.0)
+    loss_ref.backward()
+    assert abs(loss - loss_ref.item()) < 2e-3 * abs(loss_ref.item()), (loss, loss_ref.item())
+    cs = [cosine(eng.grad(q), p.grad) for (n, p), (_, q) in zip(ref.named_parameters(), m.named_parameters()) if p.grad.norm() > 0]
+    assert min(cs) > 0.95 and sum(cs) / len(cs) > 0.99, (min(cs), sum(cs) / len(cs))
+    assert eng.grad(m.resnet.resnet34_8s.fc.weight)[7:].abs().sum().item() == 0.0
