@@ -183,6 +183,74 @@ head_upsample_sigmoid_kernel(const float* __restrict__ logits, float* __restrict
   }
 }
 
+// ---- throughput-mode upsample: ROWS output rows per CTA, the x interpolation set-up amortised over them, optional fused argmax ----
+constexpr int kHeadRows = 8;
+// grid (ceil(H / kHeadRows), B*K); each thread owns 4 consecutive output x (loops when W/4 > blockDim).  The source rows touched by the
+// CTA's output rows are staged once; per row three vertical lerps (the 4 outputs of a thread read at most 3 consecutive source columns)
+// and one horizontal lerp + sigmoid per output (the separable form of the kernel above).  (Fusing the argmax into this kernel was
+// measured and dropped: the kernel is instruction-bound and the compare cost more than the stand-alone decode's HBM read.)
+__global__ void __launch_bounds__(256)
+head_upsample_rows_kernel(const float* __restrict__ logits, float* __restrict__ heat, int h, int w, int H, int W, int wq, float ry, float rx,
+                          int nsrc) {
+  extern __shared__ float srows[];  // nsrc x w
+  const int map = blockIdx.y;
+  const int Y0 = blockIdx.x * kHeadRows;
+  const int Yend = min(H, Y0 + kHeadRows);
+  const int ybase = min((int)(ry * (float)Y0), h - 1);
+  const float* src = logits + (size_t)map * h * w;
+  for (int i = threadIdx.x; i < nsrc * w; i += blockDim.x) {
+    const int r = i / w, c = i - r * w;
+    srows[i] = __ldg(src + (size_t)min(ybase + r, h - 1) * w + c);
+  }
+  __syncthreads();
+  for (int xq = threadIdx.x; xq < wq; xq += blockDim.x) {
+    // x set-up once per thread, reused by all rows: the 4 outputs read at most 3 consecutive source columns c0, c0+1, c0+2
+    float lx[4], hx[4];
+    bool a1[4], b1[4], b2[4];   // left tap = column c0 + a1; right tap = column c0 + b1 + b2  (b2 implies b1)
+    int c0 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int X = min(xq * 4 + j, W - 1);
+      const float sx = rx * (float)X;
+      const int x0 = min((int)sx, w - 1);
+      const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+      if (j == 0) c0 = x0;
+      lx[j] = sx - (float)x0;
+      hx[j] = 1.0f - lx[j];
+      a1[j] = x0 - c0 >= 1;        // x0 - c0 in {0, 1}: 3*rx < 1 is checked on the host
+      b1[j] = x1 - c0 >= 1;        // x1 - c0 in {0, 1, 2}
+      b2[j] = x1 - c0 >= 2;
+    }
+    const int c1 = min(c0 + 1, w - 1), c2 = min(c0 + 2, w - 1);
+    for (int Y = Y0; Y < Yend; ++Y) {
+      const float sy = ry * (float)Y;
+      const int y0 = min((int)sy, h - 1);
+      const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+      const float ly = sy - (float)y0, hy = 1.0f - ly;
+      const float* r0 = srows + (y0 - ybase) * w;
+      const float* r1 = srows + (y1 - ybase) * w;
+      const float t0 = hy * r0[c0] + ly * r1[c0];
+      const float t1 = hy * r0[c1] + ly * r1[c1];
+      const float t2 = hy * r0[c2] + ly * r1[c2];
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float ta = a1[j] ? t1 : t0;
+        const float tb = b2[j] ? t2 : (b1[j] ? t1 : t0);
+        o[j] = sigmoid_f<true>(hx[j] * ta + lx[j] * tb);
+      }
+      float* dst = heat + ((size_t)map * H + Y) * W + xq * 4;
+      if ((W & 3) == 0) {
+        __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (xq * 4 + j < W) dst[j] = o[j];
+      }
+    }
+  }
+}
+
 template <typename FeatT>
 static void launch_logits(const void* feat, const float* w_fc, const float* b_fc, float* logits, int pixels, int hw, int K, int C,
                           cudaStream_t s) {
@@ -239,7 +307,14 @@ static int head_fwd_impl(const void* feat, int feat_dtype, const float* w_fc, co
   // bf16 features = throughput mode: separable lerp + ex2/rcp-approx sigmoid; fp32 features = correctness mode
   if (!sigmoid)  // training: upsampled logits in ATen's exact operation order; the sigmoid lives in hk_bce_fwd_bwd
     head_upsample_sigmoid_kernel<false, false><<<grid, threads, (size_t)2 * w * sizeof(float), s>>>(logits_ws, heat, h, w, H, W, wq, ry, rx);
-  else if (feat_dtype == HK_BF16)
+  else if (feat_dtype == HK_BF16 && 3.0f * rx < 1.0f) {   // (the rows kernel assumes <= 3 source columns per 4 outputs)
+    const int nsrc = (int)(ry * (float)kHeadRows) + 3;
+    const dim3 grid2(ceil_div(H, kHeadRows), B * K);
+    const size_t smem = (size_t)nsrc * w * sizeof(float);
+    HK_REQUIRE(smem <= 48 * 1024, "hk_head_fwd: low-res row too wide for the staging buffer");
+    head_upsample_rows_kernel<<<grid2, threads, smem, s>>>(logits_ws, heat, h, w, H, W, wq, ry, rx, nsrc);
+    return check_launch("head_upsample_rows_kernel");
+  } else if (feat_dtype == HK_BF16)
     head_upsample_sigmoid_kernel<true><<<grid, threads, (size_t)w * sizeof(float), s>>>(logits_ws, heat, h, w, H, W, wq, ry, rx);
   else
     head_upsample_sigmoid_kernel<false><<<grid, threads, (size_t)2 * w * sizeof(float), s>>>(logits_ws, heat, h, w, H, W, wq, ry, rx);
