@@ -284,6 +284,9 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const ConvTcA
 bool conv_tc2_applicable(const HkConvDesc& d);
 int conv_tc2_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
                     const void* residual, void* y, cudaStream_t s);
+bool conv_tc2h_applicable(const HkConvDesc& d);
+int conv_tc2h_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
+                     const void* residual, void* y, cudaStream_t s);
 bool conv_tc_c64_applicable(const HkConvDesc& d);
 int conv_tc_c64_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
                        const void* residual, void* y, cudaStream_t s);
@@ -303,6 +306,8 @@ int conv_tc_launch(const HkConvDesc& d, const void* x, const void* w, const floa
   // layer1 shape (3x3, 64 -> 64, stride 1): resident weights + haloed boxes, 3.6x less L2->SM traffic
   const bool specialised = d.algo != HK_CONV_TCGEN05_1CTA;
   if (specialised && conv_tc_c64_applicable(d)) return conv_tc_c64_launch(d, x, w, scale, bias, residual, y, s);
+  // operand-traffic-bound 3x3 shapes: CTA-pair kernel with one haloed activation box per horizontal tap
+  if (specialised && conv_tc2_applicable(d) && conv_tc2h_applicable(d)) return conv_tc2h_launch(d, x, w, scale, bias, residual, y, s);
   // Cout >= 128: CTA-pair kernel (cta_group::2, M=256), half the weight tile per SM
   if (specialised && conv_tc2_applicable(d)) return conv_tc2_launch(d, x, w, scale, bias, residual, y, s);
 

@@ -365,3 +365,25 @@ def test_fused_adam_matches_torch_adam():
     for p, q in zip(ref_params, our_params):
         assert torch.allclose(p, q, rtol=2e-6, atol=2e-7), (p - q).abs().max().item()
     assert our_params[0].grad.data_ptr() == ours.flat_grad.data_ptr()
+
+
+HALO_CASES = [
+    (2, 60, 80, 128, 128, 3, 1, 1, True, True),     # layer2 shape (default route), height 60: half-empty last patch row
+    (2, 60, 80, 128, 128, 3, 1, 1, False, False),
+    (1, 64, 80, 256, 256, 3, 1, 2, True, True),     # layer3-like, dilation 2, height multiple of 8 (default route)
+    (2, 60, 80, 128, 256, 3, 1, 2, False, True),    # layer3.0.conv1 (forced)
+    (1, 60, 80, 512, 512, 3, 1, 4, True, True),     # layer4 shape, dilation 4, 2 N tiles (forced)
+    (3, 21, 37, 128, 128, 3, 1, 1, True, True),     # ragged patches in both directions, odd patch count -> padding patch
+    (5, 120, 160, 128, 128, 3, 1, 1, False, True),  # more tiles than clusters: ring wrap-around over many tiles
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv_tcgen05_haloed_operand_kernel(case):
+    """conv_tc2h (one haloed activation box per horizontal tap) against the oracle, forced on for every eligible shape."""
+    import os
+    os.environ["HK_CONV_HALO"] = "1"
+    try:
+        test_conv_tcgen05_vs_oracle(case)
+    finally:
+        os.environ.pop("HK_CONV_HALO", None)
