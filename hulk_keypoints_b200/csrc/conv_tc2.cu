@@ -346,7 +346,8 @@ int conv_tc2_launch(const HkConvDesc& d, const void* x, const void* w, const flo
                     const void* residual, void* y, cudaStream_t s) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled entry point not available");
-  const int block_n = d.out_c % 256 == 0 ? 256 : 128;
+  const long long boxes_all = (long long)ceil_div(d.out_w, T2_BOX_W) * ceil_div(d.out_h, T2_BOX_H) * d.batch;
+  const int block_n = pick_block_n_pair(d.out_c, (boxes_all + 3) / 4);
   const int ktot = d.kh * d.kw * d.in_c;
   CUtensorMap mx, mw;
   {

@@ -324,7 +324,8 @@ int conv_tc2h_launch(const HkConvDesc& d, const void* x, const void* w, const fl
                      void* y, cudaStream_t s) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return fail(HK_ERR_CUDA, "conv(tcgen05,halo): cuTensorMapEncodeTiled entry point not available");
-  const int block_n = d.out_c % 256 == 0 ? 256 : 128;
+  const long long patches_all = (long long)ceil_div(d.out_w, TH_TILE_W) * ceil_div(d.out_h, TH_TILE_H) * d.batch;
+  const int block_n = pick_block_n_pair(d.out_c, (patches_all + 1) / 2);
   const int ktot = 9 * d.in_c;
   const int box_rows = TH_TILE_H + 2 * d.dil;
   CUtensorMap mx, mw, my, mres;

@@ -24,6 +24,18 @@ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b;
 // Number of SMs of the current device (cached).
 int sm_count();
 
+// N tile of the CTA-pair conv kernels.  256 columns amortise the activation tile best, but with few tiles the last wave of the
+// persistent grid is mostly idle (batch 4 of 60x80 maps: 75 tiles on 74 CTA pairs = 2 waves for 1.01 waves of work); 128-column tiles
+// halve the quantum at ~10 % lower per-tile efficiency.  m_tiles = number of 256-pixel tiles.
+inline int pick_block_n_pair(int out_c, long long m_tiles) {
+  if (out_c % 256 != 0) return 128;
+  const long long clusters = sm_count() / 2;
+  const long long t256 = m_tiles * (out_c / 256);
+  const double cost256 = (double)ceil_div_ll(t256, clusters);
+  const double cost128 = (double)ceil_div_ll(2 * t256, clusters) * 0.55;
+  return cost128 < cost256 ? 128 : 256;
+}
+
 #define HK_REQUIRE(cond, ...)                                  \
   do {                                                         \
     if (!(cond)) return ::hk::fail(HK_ERR_BAD_ARG, __VA_ARGS__); \
