@@ -462,7 +462,7 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_cpu_baseline and world >= 1:
         ref = CpuReference(H, W)
         ref.run(2)
-        n = args.cpu_images or 40
+        n = args.cpu_images or 120
         secs = ref.run(n)
         v, cores = n / secs, ref.cores
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

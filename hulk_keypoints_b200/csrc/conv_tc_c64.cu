@@ -26,7 +26,8 @@ constexpr int C64_TILE_H = 8, C64_TILE_W = 16;   // 128 output pixels = UMMA M
 constexpr int C64_C = 64;
 constexpr int C64_ROW_BYTES = C64_TILE_W * 128;  // one image row of a box: 16 px x 64 ch bf16 = 2048 B
 constexpr int C64_W_BYTES = 9 * C64_C * 128;     // 72 KB resident weights
-constexpr int C64_THREADS = 256;
+constexpr int C64_THREADS = 384;   // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare; warps 4-11: epilogue
+constexpr int C64_EPI_THREADS = 256;
 constexpr int C64_MAX_SLOTS = 8;  // patch slots (one haloed box each); the host picks as many as fit in shared memory
 
 struct ConvC64Args {
@@ -61,6 +62,8 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   uint64_t* w_bar = tmem_empty_bar + 2;
   uint64_t* res_bar = w_bar + 1;   // [2]: residual tile landed in staging buffer i
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 2);
+  float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // [64] scale, [64] bias: broadcast reads in the epilogue
+  float* s_bias = s_scale + C64_C;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp: provably uniform
 
@@ -77,7 +80,7 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
-      ptx::mbar_init(&tmem_empty_bar[i], 128);
+      ptx::mbar_init(&tmem_empty_bar[i], C64_EPI_THREADS);
     }
     ptx::mbar_init(w_bar, 1);
     ptx::mbar_init(&res_bar[0], 1);
@@ -87,6 +90,9 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   if (warp == 2) {
     ptx::tmem_alloc(tmem_ptr_smem, 128);
     ptx::tmem_relinquish();
+  }
+  if (warp == 3) {
+    for (int i = lane; i < C64_C; i += 32) { s_scale[i] = a.scale[i]; s_bias[i] = a.bias[i]; }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -159,8 +165,10 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (128 threads, named barrier 1) =====================
-    const int q = warp & 3;
+    // ===================== epilogue (8 warps = 256 threads, named barrier 1) =====================
+    // warp % 4 = TMEM lane quarter (32 pixels), (warp - 4) / 4 = channel half (32 of the 64 accumulator columns): the drain of one
+    // tile takes half as long as with 4 warps, which were the slowest stage of the pipeline (2.4k clocks per tile against 2.0k of MMAs)
+    const int q = warp & 3, half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const bool leader = (warp == 4 && lane == 0);
     const int sw = row & 7;
@@ -185,8 +193,6 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const uint32_t buf = it & 1;
       uint8_t* stage_buf = sOut + buf * C64_STAGING_BYTES;
       uint8_t* my_row = stage_buf + row * 128;
-      int b, y0, x0;
-      tile_origin(tile, b, y0, x0);
       if (leader) C64_STAMP(2, (int)it, 0);
       if (leader) {
         ptx::bulk_wait_group_read0();  // every earlier TMA store has finished reading its staging buffer
@@ -198,54 +204,53 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           ptx::tma_load_4d(sOut + (buf ^ 1) * C64_STAGING_BYTES, &map_res, &res_bar[buf ^ 1], 0, nx0, ny0, nb);
         }
       }
-      ptx::named_bar_sync(1, 128);     // this tile's staging buffer is free of stores (the next tile's residual is in flight)
+      ptx::named_bar_sync(1, C64_EPI_THREADS);  // this tile's staging buffer is free of stores (the next tile's residual is in flight)
       if (leader) C64_STAMP(2, (int)it, 1);
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 25);
       ptx::tc_fence_after();
       if (leader) C64_STAMP(2, (int)it, 2);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C64_C + half * 32;
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(taddr, r);
       if (a.has_residual) ptx::mbar_wait(&res_bar[buf], (it >> 1) & 1, 26);
       if (leader) C64_STAMP(2, (int)it, 3);
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C64_C;
-#pragma unroll
-      for (int c0 = 0; c0 < C64_C; c0 += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(taddr + c0, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int c = c0 + g * 8;
-          const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.scale + c));
-          const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.scale + c + 4));
-          const float4 t0 = __ldg(reinterpret_cast<const float4*>(a.bias + c));
-          const float4 t1 = __ldg(reinterpret_cast<const float4*>(a.bias + c + 4));
-          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[g * 8 + j]), sc[j], bi[j]);
-          uint4* slot = reinterpret_cast<uint4*>(my_row + ((((c >> 3) ^ sw) & 7) << 4));  // 128-byte swizzle, as TMA expects
-          if (a.has_residual) {
-            const uint4 rr = *slot;
-            float lo, hi;
-            unpack_bf16x2(rr.x, lo, hi); v[0] += lo; v[1] += hi;
-            unpack_bf16x2(rr.y, lo, hi); v[2] += lo; v[3] += hi;
-            unpack_bf16x2(rr.z, lo, hi); v[4] += lo; v[5] += hi;
-            unpack_bf16x2(rr.w, lo, hi); v[6] += lo; v[7] += hi;
-          }
-          if (a.relu) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          *slot = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        }
-      }
+      ptx::tmem_ld_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained: the MMA warp may start tile it+2
+      ptx::mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained into registers: the MMA warp may start tile it+2
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c = half * 32 + g * 8;
+        const float4 s0 = *reinterpret_cast<const float4*>(s_scale + c);
+        const float4 s1 = *reinterpret_cast<const float4*>(s_scale + c + 4);
+        const float4 t0 = *reinterpret_cast<const float4*>(s_bias + c);
+        const float4 t1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[g * 8 + j]), sc[j], bi[j]);
+        uint4* slot = reinterpret_cast<uint4*>(my_row + ((((c >> 3) ^ sw) & 7) << 4));  // 128-byte swizzle, as TMA expects
+        if (a.has_residual) {
+          const uint4 rr = *slot;
+          float lo, hi;
+          unpack_bf16x2(rr.x, lo, hi); v[0] += lo; v[1] += hi;
+          unpack_bf16x2(rr.y, lo, hi); v[2] += lo; v[3] += hi;
+          unpack_bf16x2(rr.z, lo, hi); v[4] += lo; v[5] += hi;
+          unpack_bf16x2(rr.w, lo, hi); v[6] += lo; v[7] += hi;
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        *slot = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      }
       if (leader) C64_STAMP(2, (int)it, 4);
       ptx::fence_proxy_async_smem();           // my smem writes -> visible to the TMA store
-      ptx::named_bar_sync(1, 128);
+      ptx::named_bar_sync(1, C64_EPI_THREADS);
       if (leader) C64_STAMP(2, (int)it, 5);
       if (leader) {
+        int b, y0, x0;
+        tile_origin(tile, b, y0, x0);
         ptx::tma_store_4d(&map_y, stage_buf, 0, x0, y0, b);  // rows / columns beyond the image are clipped
         ptx::bulk_commit_group();
       }
@@ -274,7 +279,7 @@ bool conv_tc_c64_applicable(const HkConvDesc& d) {
   if (disabled) return false;
   if (!(d.kh == 3 && d.kw == 3 && d.stride == 1 && d.in_c == 64 && d.out_c == 64 && d.pad == d.dil)) return false;
   const int box_rows = C64_TILE_H + 2 * d.dil;
-  const int smem_min = 1024 + C64_W_BYTES + 3 * box_rows * C64_ROW_BYTES + 2 * C64_STAGING_BYTES + 256;  // at least one tile in flight
+  const int smem_min = 1024 + C64_W_BYTES + 3 * box_rows * C64_ROW_BYTES + 2 * C64_STAGING_BYTES + 1024;  // at least one tile in flight
   return box_rows <= 256 && smem_min <= 227 * 1024;
 }
 
@@ -335,7 +340,7 @@ int conv_tc_c64_launch(const HkConvDesc& d, const void* x, const void* w, const 
   a.num_tiles = (int)nt;
   a.box_rows = box_rows;
   a.patch_bytes = box_rows * C64_ROW_BYTES;
-  const int fixed = 1024 + C64_W_BYTES + 2 * C64_STAGING_BYTES + 256;
+  const int fixed = 1024 + C64_W_BYTES + 2 * C64_STAGING_BYTES + 1024;  // alignment slack, weights, staging, barriers + scale/bias
   int slots = (227 * 1024 - fixed) / a.patch_bytes;
   if (slots > C64_MAX_SLOTS) slots = C64_MAX_SLOTS;
   a.slots = slots;

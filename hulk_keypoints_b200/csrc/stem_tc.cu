@@ -290,6 +290,217 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ stem weight gradient
+// dW[co][c][r][s] = sum_{b,oy,ox} dY[b,oy,ox,co] * X[b,c,2oy-3+r,2ox-3+s]   (autograd of the stem conv, reference
+// src/resnet.py:137 under train.py:35), as a tcgen05 GEMM whose reduction runs over the output pixels:
+//   D[M = co (64, duplicated to 128), N = k (192)] += dY_tile^T[co, 128 px] * im2col_tile[128 px, k]
+// The im2col tile is built exactly like the forward kernel's A tile ([128 px][192 k], 128-byte-swizzled); here it is the
+// B operand read MN-major (k contiguous, pixels = GEMM-K strided: 8-pixel groups 1024 B apart, 64-wide k groups 16 KB apart).
+// The dY tile (128 px x 64 co bf16) is one SWIZZLE_128B TMA box, loaded twice so the A operand has 128 rows (rows 64..127 of
+// the accumulator repeat rows 0..63 and are never read).  The fp32 accumulator (128 lanes x 192 columns of TMEM) lives across
+// ALL tiles of the persistent CTA; one epilogue at the end writes the CTA's partial [64 co][192 k], summed in a fixed order by
+// stem_wgrad_tc_finalize_kernel (deterministic, no atomics).  x is rounded to bf16 exactly as in the forward kernel.
+constexpr int SWG_DY_TILE_BYTES = 128 * 128;                           // 128 px x 64 co bf16
+constexpr int SWG_DY_BYTES = 2 * SWG_DY_TILE_BYTES;                     // two copies: accumulator rows 0..63 and 64..127
+constexpr int SWG_SMEM_BYTES = 1024 + ST_A_BYTES + SWG_DY_BYTES + ((ST_PATCH_ELEMS * 2 + 15) & ~15) + 64;
+constexpr int SWG_TMEM_COLS = 256;
+
+struct StemWgradArgs {
+  const float* x;     // (B,3,H,W) fp32 NCHW
+  float* partial;     // [grid][64 co][192 k] fp32
+  int B, H, W, Ho, Wo;
+  int tiles_x, tiles_per_img, num_tiles;
+};
+
+// MN-major SWIZZLE_128B operand made of [128 px][128 B] blocks: LBO = 16 KB between 64-element groups along M/N,
+// SBO = 1024 B between 8-pixel groups along K
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128_16k(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(16384 >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 2)
+stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const StemWgradArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                   // im2col: 3 k blocks x [128 px][128 B]
+  uint8_t* sDy = smem + ST_A_BYTES;                     // 2 x [128 px][128 B]
+  __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(sDy + SWG_DY_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + ((ST_PATCH_ELEMS * 2 + 15) & ~15));
+  uint64_t* dy_bar = bars;       // dY tile landed
+  uint64_t* mma_bar = bars + 1;  // this tile's MMAs done: sA / sDy may be overwritten
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+  if (tid == 0) {
+    ptx::prefetch_tensormap(&map_dy);
+    ptx::mbar_init(dy_bar, 1);
+    ptx::mbar_init(mma_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_smem, SWG_TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  for (int i = tid; i < 128 * 3; i += ST_THREADS) {  // k in [168,192): zero once (meets zero... never written again)
+    const int row = i / 3, chunk = 5 + i % 3;
+    *reinterpret_cast<uint4*>(sA + 2 * 16384 + sw128_off(row, chunk)) = make_uint4(0, 0, 0, 0);
+  }
+  for (int i = tid; i < 8; i += ST_THREADS) patch[ST_PATCH_H * ST_PATCH_W * 3 + i] = __float2bfloat16(0.f);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, ST_K) | (1u << 15) | (1u << 16);  // A and B MN-major
+  uint32_t phase = 0;   // parity of dy_bar / mma_bar for the current tile (each completes once per tile)
+  bool first = true;
+
+  constexpr int PATCH_ROWS = 3 * ST_PATCH_H;                       // 63 (channel, row) segments of 38 floats
+  constexpr int ROWS_PER_WARP = (PATCH_ROWS + 7) / 8;              // 8
+  float pre[ROWS_PER_WARP][2];
+  auto prefetch_patch = [&](int t) {
+    const int pb = t / a.tiles_per_img;
+    const int prem = t - pb * a.tiles_per_img;
+    const int pty = prem / a.tiles_x, ptx_ = prem - pty * a.tiles_x;
+    const int piy0 = 2 * pty * ST_TILE_H - 3, pix0 = 2 * ptx_ * ST_TILE_W - 3;
+    const float* xb = a.x + (size_t)pb * 3 * a.H * a.W;
+    const int ix_a = pix0 + lane, ix_b = pix0 + lane + 32;
+    const bool ok_a = ix_a >= 0 && ix_a < a.W;
+    const bool ok_b = lane < ST_PATCH_W - 32 && ix_b >= 0 && ix_b < a.W;
+#pragma unroll
+    for (int j = 0; j < ROWS_PER_WARP; ++j) {
+      const int seg = warp + 8 * j;                                // warp-uniform
+      const int c = seg / ST_PATCH_H, py = seg - c * ST_PATCH_H;
+      const int iy = piy0 + py;
+      const bool ok_row = seg < PATCH_ROWS && iy >= 0 && iy < a.H;
+      const float* rowp = xb + ((size_t)c * a.H + (ok_row ? iy : 0)) * a.W;
+      pre[j][0] = (ok_row && ok_a) ? __ldg(rowp + ix_a) : 0.f;
+      pre[j][1] = (ok_row && ok_b) ? __ldg(rowp + ix_b) : 0.f;
+    }
+  };
+  if ((int)blockIdx.x < a.num_tiles) prefetch_patch(blockIdx.x);
+
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    const int b = tile / a.tiles_per_img;
+    const int rem = tile - b * a.tiles_per_img;
+    const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+    const int oy0 = ty * ST_TILE_H, ox0 = tx * ST_TILE_W;
+
+    // ---- 1. prefetched input patch -> smem, bf16, [y][x][c] (the patch buffer is not an MMA operand) ----
+#pragma unroll
+    for (int j = 0; j < ROWS_PER_WARP; ++j) {
+      const int seg = warp + 8 * j;
+      if (seg < PATCH_ROWS) {
+        const int c = seg / ST_PATCH_H, py = seg - c * ST_PATCH_H;
+        __nv_bfloat16* dstp = patch + (py * ST_PATCH_W) * 3 + c;
+        dstp[lane * 3] = __float2bfloat16_rn(pre[j][0]);
+        if (lane < ST_PATCH_W - 32) dstp[(lane + 32) * 3] = __float2bfloat16_rn(pre[j][1]);
+      }
+    }
+    // ---- 2. previous tile's MMAs have finished reading sA / sDy; fetch this tile's dY ----
+    if (!first) ptx::mbar_wait(mma_bar, phase ^ 1, 14);
+    if (tid == 0) {
+      ptx::mbar_arrive_expect_tx(dy_bar, SWG_DY_BYTES);
+      ptx::tma_load_4d(sDy, &map_dy, dy_bar, 0, ox0, oy0, b);                      // pixels beyond the image arrive as zeros
+      ptx::tma_load_4d(sDy + SWG_DY_TILE_BYTES, &map_dy, dy_bar, 0, ox0, oy0, b);
+    }
+    __syncthreads();  // patch complete
+
+    // ---- 3. im2col rows into the swizzled tile (same layout as the forward kernel's A tile) ----
+    for (int sidx = tid; sidx < 128 * 7; sidx += ST_THREADS) {
+      const int row = sidx & 127, r = sidx >> 7;
+      const int py = row >> 4, px = row & 15;
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(patch + ((2 * py + r) * ST_PATCH_W + 2 * px) * 3);
+      uint32_t v[12];
+#pragma unroll
+      for (int j = 0; j < 12; ++j) v[j] = src[j];
+#pragma unroll
+      for (int cidx = 0; cidx < 3; ++cidx) {
+        const int gchunk = r * 3 + cidx;
+        uint8_t* dst = sA + (gchunk >> 3) * 16384 + sw128_off(row, gchunk & 7);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(v[4 * cidx], v[4 * cidx + 1], v[4 * cidx + 2], v[4 * cidx + 3]);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    ptx::tc_fence_before();
+    __syncthreads();
+
+    // ---- 4. MMA: 8 steps of 16 pixels ----
+    if (warp_u == 0) {
+      ptx::mbar_wait(dy_bar, phase, 15);
+      ptx::tc_fence_after();
+      if (ptx::elect_one_sync()) {
+        const uint64_t adesc = make_smem_desc_mn_sw128_16k(ptx::smem_u32(sDy));
+        const uint64_t bdesc = make_smem_desc_mn_sw128_16k(ptx::smem_u32(sA));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // 16 pixels = 2048 bytes further along the reduction: +128 in the (addr >> 4) field
+          ptx::umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (!first || k != 0) ? 1u : 0u);
+        ptx::umma_commit(mma_bar);
+      }
+      __syncwarp();
+    }
+    first = false;
+    phase ^= 1;
+    if (tile + (int)gridDim.x < a.num_tiles) prefetch_patch(tile + gridDim.x);
+  }
+
+  // ---- epilogue: the CTA's accumulated [64 co][192 k] -> partial (warp%4 = TMEM lane quarter, warp/4 = column half) ----
+  if (!first) {
+    ptx::mbar_wait(mma_bar, phase ^ 1, 16);
+    ptx::tc_fence_after();
+    const int q = warp & 3, c0 = (warp >> 2) * (ST_K / 2);
+    if (q < 2) {  // rows 64..127 duplicate rows 0..63
+      const int co = q * 32 + lane;
+      float* dst = a.partial + ((size_t)blockIdx.x * ST_COUT + co) * ST_K + c0;
+#pragma unroll 1
+      for (int cc = 0; cc < ST_K / 2; cc += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0 + cc, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(dst + cc + g * 4) = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
+                                                                      __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, SWG_TMEM_COLS);
+  }
+}
+
+// dw (64,3,7,7) OIHW (+)= sum over CTAs of partial[cta][co][r*24 + s*3 + c]; fixed order, double accumulation
+__global__ void __launch_bounds__(256) stem_wgrad_tc_finalize_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ dw,
+                                                                    int accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;   // co * 147 + (c*7 + r)*7 + s
+  if (j >= 64 * 147) return;
+  const int co = j / 147, t = j - co * 147;
+  const int c = t / 49, rs = t - c * 49, r = rs / 7, sft = rs - r * 7;
+  const float* p = partial + (size_t)co * ST_K + r * ST_SEG + sft * 3 + c;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int b = 0;
+  for (; b + 4 <= nblk; b += 4) {
+    s0 += (double)p[(size_t)(b + 0) * (ST_COUT * ST_K)];
+    s1 += (double)p[(size_t)(b + 1) * (ST_COUT * ST_K)];
+    s2 += (double)p[(size_t)(b + 2) * (ST_COUT * ST_K)];
+    s3 += (double)p[(size_t)(b + 3) * (ST_COUT * ST_K)];
+  }
+  for (; b < nblk; ++b) s0 += (double)p[(size_t)b * (ST_COUT * ST_K)];
+  dw[j] = (accumulate ? dw[j] : 0.f) + (float)((s0 + s1) + (s2 + s3));
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -398,6 +609,56 @@ int hk_stem_conv_fwd(const float* x_nchw, const void* w_packed, const float* sca
 int hk_stem_fwd_u8(const uint8_t* x_nhwc_u8, const void* w_packed, const float* scale, const float* bias, void* y_nhwc, int B,
                    int H, int W, void* stream) {
   return stem_launch(x_nhwc_u8, true, w_packed, scale, bias, y_nhwc, B, H, W, stream);
+}
+
+size_t hk_stem_wgrad_workspace_bytes(void) { return (size_t)hk::sm_count() * 2 * hk::ST_COUT * hk::ST_K * sizeof(float); }
+
+int hk_stem_wgrad(const float* x_nchw, const void* dy_nhwc, float* dw_oihw, int accumulate, int B, int H, int W, void* ws,
+                  size_t ws_bytes, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(x_nchw && dy_nhwc && dw_oihw && ws, "hk_stem_wgrad: null pointer");
+  HK_REQUIRE(B > 0 && H >= 7 && W >= 7, "hk_stem_wgrad: bad shape");
+  HK_REQUIRE(ws_bytes >= hk_stem_wgrad_workspace_bytes(), "hk_stem_wgrad: workspace too small");
+  HK_REQUIRE((reinterpret_cast<uintptr_t>(dy_nhwc) & 15) == 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
+             "hk_stem_wgrad: buffers must be 16-byte aligned");
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return fail(HK_ERR_CUDA, "hk_stem_wgrad: cuTensorMapEncodeTiled entry point not available");
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  CUtensorMap mdy;
+  {
+    const cuuint64_t dims[4] = {64, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {128, (cuuint64_t)Wo * 128, (cuuint64_t)Ho * Wo * 128};
+    const cuuint32_t box[4] = {64, (cuuint32_t)ST_TILE_W, (cuuint32_t)ST_TILE_H, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&mdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy_nhwc), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "hk_stem_wgrad: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  }
+  StemWgradArgs a;
+  a.x = x_nchw; a.partial = static_cast<float*>(ws);
+  a.B = B; a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo;
+  a.tiles_x = ceil_div(Wo, ST_TILE_W);
+  a.tiles_per_img = a.tiles_x * ceil_div(Ho, ST_TILE_H);
+  const long long nt = (long long)a.tiles_per_img * B;
+  HK_REQUIRE(nt < 0x7fffffffLL, "hk_stem_wgrad: too many tiles");
+  a.num_tiles = (int)nt;
+  static int attr_dev_mask = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_dev_mask & (1 << dev))) {
+    cudaError_t e = cudaFuncSetAttribute(stem_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWG_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(HK_ERR_CUDA, "hk_stem_wgrad: smem attribute: %s", cudaGetErrorString(e));
+    attr_dev_mask |= (1 << dev);
+  }
+  int grid = 2 * sm_count();
+  if (grid > a.num_tiles) grid = a.num_tiles;
+  stem_wgrad_tc_kernel<<<grid, ST_THREADS, SWG_SMEM_BYTES, as_stream(stream)>>>(mdy, a);
+  int rc = check_launch("stem_wgrad_tc_kernel");
+  if (rc) return rc;
+  stem_wgrad_tc_finalize_kernel<<<ceil_div(64 * 147, 256), 256, 0, as_stream(stream)>>>(static_cast<const float*>(ws), grid, dw_oihw,
+                                                                                       accumulate);
+  return check_launch("stem_wgrad_tc_finalize_kernel");
 }
 
 }  // extern "C"

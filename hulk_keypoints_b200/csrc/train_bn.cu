@@ -63,33 +63,39 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_partial_kernel(const __nv
   block_reduce_2x8(s, q, C, partial);
 }
 
-// Finalize kernels: 256 threads = 32 channels x 8 slices of the per-block partials (coalesced across channels, 8-way parallel and
-// unrolled along the blocks -- a single thread per channel walking ~1000 partials serially cost 170 us per launch).
-constexpr int BN_FIN_THREADS = 256;
+// Finalize kernels: 1024 threads = 32 channels x 32 slices of the per-block partials (coalesced across channels; every thread has
+// up to 8 independent loads in flight and walks <= 19 of the 592 partials -- one thread per channel walking them serially cost
+// 170 us per launch, 8 slices with 2-deep unrolling still 15 us: the loop is pure L2 latency).  Fixed order => deterministic.
+constexpr int BN_FIN_SLICES = 32;
+constexpr int BN_FIN_THREADS = 32 * BN_FIN_SLICES;
 __device__ __forceinline__ void bn_sum_partials(const float* __restrict__ partial, int nblocks, int C, int c, double& s, double& q) {
-  __shared__ double sh[2][8][32];
+  __shared__ double sh[2][BN_FIN_SLICES][33];
   const int lane_c = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
   if (c < C) {
-    int b = slice;
-    for (; b + 8 < nblocks; b += 16) {
-      a0 += partial[(size_t)b * 2 * C + c];
-      b0 += partial[(size_t)b * 2 * C + C + c];
-      a1 += partial[(size_t)(b + 8) * 2 * C + c];
-      b1 += partial[(size_t)(b + 8) * 2 * C + C + c];
+    int blk = slice;
+    for (; blk + 3 * BN_FIN_SLICES < nblocks; blk += 4 * BN_FIN_SLICES) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] += partial[(size_t)(blk + u * BN_FIN_SLICES) * 2 * C + c];
+        b[u] += partial[(size_t)(blk + u * BN_FIN_SLICES) * 2 * C + C + c];
+      }
     }
-    if (b < nblocks) {
-      a0 += partial[(size_t)b * 2 * C + c];
-      b0 += partial[(size_t)b * 2 * C + C + c];
+    for (; blk < nblocks; blk += BN_FIN_SLICES) {
+      a[0] += partial[(size_t)blk * 2 * C + c];
+      b[0] += partial[(size_t)blk * 2 * C + C + c];
     }
   }
-  sh[0][slice][lane_c] = (double)a0 + (double)a1;
-  sh[1][slice][lane_c] = (double)b0 + (double)b1;
+  sh[0][slice][lane_c] = ((double)a[0] + (double)a[1]) + ((double)a[2] + (double)a[3]);
+  sh[1][slice][lane_c] = ((double)b[0] + (double)b[1]) + ((double)b[2] + (double)b[3]);
   __syncthreads();
-  s = 0.0;
-  q = 0.0;
+  double s4[4] = {0.0, 0.0, 0.0, 0.0}, q4[4] = {0.0, 0.0, 0.0, 0.0};
+  if (threadIdx.x < 32) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { s += sh[0][i][lane_c]; q += sh[1][i][lane_c]; }
+    for (int i = 0; i < BN_FIN_SLICES; ++i) { s4[i & 3] += sh[0][i][lane_c]; q4[i & 3] += sh[1][i][lane_c]; }
+  }
+  s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
 }
 
 // mean / invstd, the fused affine (scale, shift) of the apply pass, running statistics

@@ -239,98 +239,32 @@ __global__ void __launch_bounds__(256) fc_bwd_dw_finalize_kernel(const float* __
     dw[(size_t)k * C + c] = (accumulate ? dw[(size_t)k * C + c] : 0.f) + (float)s;
   }
 }
-// db[k] = sum_p dl[b,k,pix]   (grid: K blocks)
-__global__ void __launch_bounds__(256) fc_bwd_db_kernel(const float* __restrict__ dl, float* __restrict__ db, int B, int K, int hw, int accumulate) {
-  const int k = blockIdx.x;
+// db[k] = sum_{b,pix} dl[b,k,pix] in two fixed-order stages: one block per (k, b) map, then one thread per k over the B partials
+// (a single block per k walking all B*hw elements serially cost 0.29 ms at B = 32)
+__global__ void __launch_bounds__(256) fc_bwd_db_partial_kernel(const float* __restrict__ dl, double* __restrict__ partial, int K, int hw) {
+  const int k = blockIdx.x, b = blockIdx.y;
+  const float* src = dl + ((size_t)b * K + k) * hw;
   __shared__ double red[256];
-  double s = 0.0;
-  for (int b = 0; b < B; ++b)
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) s += (double)dl[((size_t)b * K + k) * hw + i];
-  red[threadIdx.x] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int i = threadIdx.x;
+  for (; i + 3 * 256 < hw; i += 4 * 256) {
+    s0 += src[i]; s1 += src[i + 256]; s2 += src[i + 512]; s3 += src[i + 768];
+  }
+  for (; i < hw; i += 256) s0 += src[i];
+  red[threadIdx.x] = ((double)s0 + (double)s1) + ((double)s2 + (double)s3);
   __syncthreads();
   for (int st = 128; st > 0; st >>= 1) {
     if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
     __syncthreads();
   }
-  if (threadIdx.x == 0) db[k] = (accumulate ? db[k] : 0.f) + (float)red[0];
+  if (threadIdx.x == 0) partial[(size_t)b * K + k] = red[0];
 }
-
-// ---------------------------------------------------------------- stem weight gradient
-// dw[co][c][r][s] = sum_{b,oy,ox} dy[b,oy,ox,co] * x[b,c,2oy-3+r,2ox-3+s]      (x fp32 NCHW, dy bf16 NHWC)
-// One CTA per 8x16 output tile (persistent): input patch (3 x 21 x 37) and the dy tile (128 px x 64 co) in shared memory.  Thread t
-// owns the 4 output channels co = 4*(t&15).. and the taps k = (t>>4) + 16*i (k = (c*7 + r)*7 + s, i < 10): per pixel one float4 of dy
-// and 10 broadcast patch loads feed 40 FMAs; the 40 accumulators stay in registers over all tiles of the CTA.
-constexpr int SW_TH = 8, SW_TW = 16, SW_PH = 2 * SW_TH + 5, SW_PW = 2 * SW_TW + 5;  // 21 x 37
-constexpr int SW_KPT = 10;                                                          // ceil(147 / 16)
-__global__ void __launch_bounds__(256) stem_wgrad_partial_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                                                                float* __restrict__ partial, int B, int H, int W, int Ho, int Wo,
-                                                                int tiles_x, int tiles_per_img, int num_tiles) {
-  __shared__ float sx[3 * SW_PH * SW_PW];
-  __shared__ __align__(16) float sdy[SW_TH * SW_TW][64 + 4];
-  const int quad = threadIdx.x & 15, kg = threadIdx.x >> 4;
-  int koff[SW_KPT];
-#pragma unroll
-  for (int i = 0; i < SW_KPT; ++i) {
-    const int k = min(kg + 16 * i, 146);
-    const int c = k / 49, rs = k - c * 49, r = rs / 7, sft = rs - r * 7;
-    koff[i] = c * (SW_PH * SW_PW) + r * SW_PW + sft;
-  }
-  float acc[SW_KPT][4];
-#pragma unroll
-  for (int i = 0; i < SW_KPT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
-    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-    const int oy0 = ty * SW_TH, ox0 = tx * SW_TW;
-    const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
-    __syncthreads();
-    for (int t = threadIdx.x; t < 3 * SW_PH * SW_PW; t += blockDim.x) {
-      const int c = t / (SW_PH * SW_PW), r2 = t - c * (SW_PH * SW_PW);
-      const int py = r2 / SW_PW, px = r2 - py * SW_PW;
-      const int iy = iy0 + py, ix = ix0 + px;
-      sx[t] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + (((size_t)b * 3 + c) * H + iy) * W + ix) : 0.f;
-    }
-    for (int t = threadIdx.x; t < SW_TH * SW_TW * 8; t += blockDim.x) {
-      const int pix = t >> 3, cg = t & 7;
-      const int oy = oy0 + pix / SW_TW, ox = ox0 + pix % SW_TW;
-      float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (oy < Ho && ox < Wo) ld8(dy + (((size_t)b * Ho + oy) * Wo + ox) * 64 + cg * 8, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sdy[pix][cg * 8 + j] = v[j];
-    }
-    __syncthreads();
-#pragma unroll 2
-    for (int pix = 0; pix < SW_TH * SW_TW; ++pix) {
-      const float4 d = *reinterpret_cast<const float4*>(&sdy[pix][quad * 4]);
-      const int pbase = 2 * (pix / SW_TW) * SW_PW + 2 * (pix % SW_TW);
-#pragma unroll
-      for (int i = 0; i < SW_KPT; ++i) {
-        const float xv = sx[koff[i] + pbase];
-        acc[i][0] = fmaf(d.x, xv, acc[i][0]);
-        acc[i][1] = fmaf(d.y, xv, acc[i][1]);
-        acc[i][2] = fmaf(d.z, xv, acc[i][2]);
-        acc[i][3] = fmaf(d.w, xv, acc[i][3]);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < SW_KPT; ++i) {
-    const int k = kg + 16 * i;
-    if (k < 147) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) partial[(size_t)blockIdx.x * (147 * 64) + k * 64 + quad * 4 + j] = acc[i][j];
-    }
-  }
-}
-// dw (64,3,7,7) OIHW: index co*147 + k
-__global__ void stem_wgrad_finalize_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ dw, int accumulate) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= 147 * 64) return;
+__global__ void fc_bwd_db_final_kernel(const double* __restrict__ partial, float* __restrict__ db, int B, int K, int accumulate) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += (double)partial[(size_t)b * (147 * 64) + j];
-  const int k = j >> 6, co = j & 63;
-  float* dst = dw + co * 147 + k;
-  *dst = (accumulate ? *dst : 0.f) + (float)s;
+  for (int b = 0; b < B; ++b) s += partial[(size_t)b * K + k];
+  db[k] = (accumulate ? db[k] : 0.f) + (float)s;
 }
 
 static int grid_for(long long n, int threads) {
@@ -405,30 +339,13 @@ int hk_head_bwd(const float* g_up, const void* feat, const float* w_fc, float* d
   fc_bwd_dw_finalize_kernel<<<dim3(C / 32, K), 256, 0, s>>>(static_cast<const float*>(ws), nblk, dw_fc, K, C, accumulate);
   rc = check_launch("fc_bwd_dw_finalize_kernel");
   if (rc) return rc;
-  fc_bwd_db_kernel<<<K, 256, 0, s>>>(dlogits_ws, db_fc, B, K, hw, accumulate);
-  return check_launch("fc_bwd_db_kernel");
-}
-
-size_t hk_stem_wgrad_workspace_bytes(void) { return (size_t)hk::sm_count() * 2 * 147 * 64 * sizeof(float); }
-
-int hk_stem_wgrad(const float* x_nchw, const void* dy_nhwc, float* dw_oihw, int accumulate, int B, int H, int W, void* ws,
-                  size_t ws_bytes, void* stream) {
-  using namespace hk;
-  HK_REQUIRE(x_nchw && dy_nhwc && dw_oihw && ws, "hk_stem_wgrad: null pointer");
-  HK_REQUIRE(B > 0 && H >= 7 && W >= 7, "hk_stem_wgrad: bad shape");
-  HK_REQUIRE(ws_bytes >= hk_stem_wgrad_workspace_bytes(), "hk_stem_wgrad: workspace too small");
-  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
-  const int tiles_x = ceil_div(Wo, SW_TW), tiles_y = ceil_div(Ho, SW_TH);
-  const int num_tiles = B * tiles_x * tiles_y;
-  int blocks = sm_count() * 2;
-  if (blocks > num_tiles) blocks = num_tiles;
-  stem_wgrad_partial_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x_nchw, static_cast<const __nv_bfloat16*>(dy_nhwc),
-                                                                  static_cast<float*>(ws), B, H, W, Ho, Wo, tiles_x, tiles_x * tiles_y,
-                                                                  num_tiles);
-  int rc = check_launch("stem_wgrad_partial_kernel");
+  // the dw partials in `ws` are consumed: its head is reused for the B x K double partials of db
+  HK_REQUIRE(ws_bytes >= (size_t)B * K * sizeof(double) && (reinterpret_cast<uintptr_t>(ws) & 7) == 0, "hk_head_bwd: workspace too small for db");
+  fc_bwd_db_partial_kernel<<<dim3(K, B), 256, 0, s>>>(dlogits_ws, static_cast<double*>(ws), K, hw);
+  rc = check_launch("fc_bwd_db_partial_kernel");
   if (rc) return rc;
-  stem_wgrad_finalize_kernel<<<ceil_div(147 * 64, 256), 256, 0, as_stream(stream)>>>(static_cast<const float*>(ws), blocks, dw_oihw, accumulate);
-  return check_launch("stem_wgrad_finalize_kernel");
+  fc_bwd_db_final_kernel<<<ceil_div(K, 64), 64, 0, s>>>(static_cast<const double*>(ws), db_fc, B, K, accumulate);
+  return check_launch("fc_bwd_db_final_kernel");
 }
 
 }  // extern "C"
