@@ -1,17 +1,23 @@
-// tcgen05 stem: conv 7x7 stride 2 pad 3 (3 -> 64) + folded BN + ReLU  (SURVEY.md k1), bf16 operands, fp32 accumulate.
+// tcgen05 stem: conv 7x7 stride 2 pad 3 (3 -> 64) + folded BN + ReLU  (SURVEY.md k1), bf16 operands, fp32 accumulate,
+// and its weight gradient.
 //
 // Replaces nn.Conv2d(3,64,7,2,3) -> BatchNorm2d -> ReLU of reference src/resnet.py:137-139,199-201 in the bf16
-// inference mode.  Cin = 3 is too thin for a TMA im2col, so the CTA builds the im2col tile itself:
-//   1. the fp32 NCHW input patch that feeds an 8x16 tile of stem outputs (21 rows x 37 cols x 3 ch) is loaded
-//      with coalesced reads, rounded to bf16 and stored pixel-major [y][x][c] in shared memory;
-//   2. for one output pixel and one filter row r the 7x3 = 21 taps are CONTIGUOUS in that layout, so the A tile
-//      (128 pixels x K) is 7 segments of 24 bf16 per row (21 taps + 3 that meet zero weights), K = 7*24 = 168,
-//      padded to 192 = three 64-wide K blocks; rows are written straight into the 128-byte-swizzled K-major
-//      layout tcgen05 expects (16-byte chunk index XOR row%8);
-//   3. one thread issues 12 tcgen05.mma (M=128, N=64, K=16) against the weights (64 x 192 bf16, TMA-loaded once
-//      per CTA), accumulator in TMEM;
-//   4. warps 0-3 read TMEM, apply scale/bias/ReLU and store 64 bf16 channels (128 contiguous bytes) per pixel.
-// Two CTAs per SM (77 KB smem each) overlap one CTA's global loads/stores with the other's build/MMA.
+// inference mode (and autograd's weight gradient of that conv under train.py:35).  Cin = 3 is too thin for a TMA
+// im2col, so the CTA builds the im2col tile itself:
+//   1. the input patch that feeds an 8x16 tile of stem outputs (21 rows x 38 cols x 3 ch; fp32 NCHW, or uint8 HWC) is
+//      loaded with coalesced reads one tile ahead into registers, rounded to bf16 and stored pixel-major in shared
+//      memory with FOUR channels per pixel (the fourth is zero): one pixel = 8 bytes;
+//   2. for one output pixel and one filter row r the 7 taps x 3 channels are then 8 px x 4 ch = 32 contiguous bf16 =
+//      64 bytes starting on a 16-byte boundary (2*px pixels in), so an im2col row segment is FOUR 16-byte chunks copied
+//      verbatim (LDS.128 -> STS.128, conflict-free) into the 128-byte-swizzled K-major layout tcgen05 expects;
+//      K = 7 * 32 = 224, padded to 256 = four 64-wide K blocks.  The eighth pixel / fourth channel of a segment meet
+//      zero weights.  (The previous layout, 24 bf16 per filter row with 12 LDS.32 + repacking per segment and per-element
+//      index arithmetic in the loads, made the kernel instruction-issue-bound: 1.6k instructions per warp per tile.)
+//   3. one thread issues 16 tcgen05.mma (M=128, N=64, K=16) against the weights (64 x 256 bf16, TMA-loaded once per
+//      CTA), accumulator in TMEM;
+//   4. all 8 warps read TMEM, apply scale/bias(/ReLU) from shared memory and write the bf16 tile into the first K block
+//      of the (now idle) A tile, from where one TMA store writes it out.
+// Two CTAs per SM (~104 KB smem each) overlap one CTA's global loads/stores with the other's build/MMA.
 #include <cuda.h>
 
 #include "hk_common.cuh"
@@ -21,17 +27,19 @@ namespace hk {
 
 constexpr int ST_TILE_H = 8, ST_TILE_W = 16;            // stem-output pixels per tile (128 = UMMA M)
 constexpr int ST_PATCH_H = 2 * ST_TILE_H + 5;           // 21 input rows
-constexpr int ST_PATCH_W = 2 * ST_TILE_W + 6;           // 38 columns (37 used + 1 so segment reads stay in range)
-constexpr int ST_SEG = 24;                              // bf16 per filter row in the A tile (21 taps + 3 pad)
-constexpr int ST_K = 192;                               // 7*24 = 168 padded to 3 K blocks of 64
+constexpr int ST_PATCH_W = 2 * ST_TILE_W + 6;           // 38 columns (37 used + 1 so 8-pixel segment reads stay in range)
+constexpr int ST_PCH = 4;                               // bf16 per patch pixel: 3 channels + one zero
+constexpr int ST_SEG = 32;                              // bf16 per filter row in the A tile: 8 px x 4 ch (7 x 3 real taps)
+constexpr int ST_K = 256;                               // 7*32 = 224 padded to 4 K blocks of 64
 constexpr int ST_KBLOCKS = ST_K / 64;
 constexpr int ST_COUT = 64;
 constexpr int ST_THREADS = 256;
-constexpr int ST_A_BYTES = 128 * 128 * ST_KBLOCKS;      // 48 KB
-constexpr int ST_B_BYTES = ST_COUT * 128 * ST_KBLOCKS;  // 24 KB
-constexpr int ST_PATCH_ELEMS = ST_PATCH_H * ST_PATCH_W * 3 + 8;
-constexpr int ST_OUT_BYTES = 128 * 128;                 // output tile staging: 128 px x 64 ch bf16, swizzled for the TMA store
-constexpr int ST_SMEM_BYTES = 1024 + ST_A_BYTES + ST_B_BYTES + ST_OUT_BYTES + ((ST_PATCH_ELEMS * 2 + 15) & ~15) + 64;
+constexpr int ST_A_BYTES = 128 * 128 * ST_KBLOCKS;      // 64 KB; K block 0 doubles as the output staging tile
+constexpr int ST_B_BYTES = ST_COUT * 128 * ST_KBLOCKS;  // 32 KB
+constexpr int ST_PATCH_BYTES = (ST_PATCH_H * ST_PATCH_W * ST_PCH * 2 + 15) & ~15;
+constexpr int ST_TAIL_BYTES = 64 + 2 * ST_COUT * 4;     // barriers + TMEM pointer, scale[64], bias[64]
+constexpr int ST_SMEM_BYTES = 1024 + ST_A_BYTES + ST_B_BYTES + ST_PATCH_BYTES + ST_TAIL_BYTES;
+constexpr int ST_ROW_SLOTS = 3;                         // patch rows per warp: w, w+8, w+16 (< 21)
 
 struct StemTcArgs {
   const void* x;    // (B,3,H,W) fp32 NCHW, or (B,H,W,3) uint8 (cv2 layout) in the U8 instantiation
@@ -43,27 +51,156 @@ struct StemTcArgs {
   int relu;         // 1: ReLU in the epilogue (inference / folded BN); 0: raw affine output (train-mode BN follows)
   long long* dbg;  // optional phase timeline of CTA 0 (tools/diag_stem_timeline.py); null in production
 };
+constexpr int ST_DBG_FIRST = 36;  // first tile (of CTA 0) recorded in the diagnostic timeline: steady state, L2 full of dirty lines
 #define ST_STAMP(slot)                                                                            \
   do {                                                                                            \
-    if (a.dbg && blockIdx.x == 0 && tid == 0 && dbg_tile < 24) a.dbg[dbg_tile * 8 + (slot)] = clock64(); \
+    if (a.dbg && blockIdx.x == 0 && tid == 0 && dbg_tile >= ST_DBG_FIRST && dbg_tile < ST_DBG_FIRST + 24) a.dbg[(dbg_tile - ST_DBG_FIRST) * 8 + (slot)] = clock64(); \
   } while (0)
 
 // byte offset of (row, 16-byte chunk) inside one 128-row x 128-byte K block, SWIZZLE_128B
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
+
+// ---- the input patch of one tile: registers <- global (one tile ahead), shared <- registers ----
+// Warp w owns patch rows w, w+8, w+16; lane l owns columns l and l+32 (the latter for l < 6).  fp32 NCHW: three coalesced
+// channel loads per pixel; uint8 HWC: three byte loads per pixel (a warp covers 96 contiguous bytes), packed in one register.
+template <bool U8>
+struct StemPatch {
+  uint32_t v[ST_ROW_SLOTS][2][U8 ? 1 : 3];
+};
+__device__ __forceinline__ void stem_tile_origin(int tile, int tiles_per_img, int tiles_x, int& b, int& ty, int& tx) {
+  b = tile / tiles_per_img;
+  const int rem = tile - b * tiles_per_img;
+  ty = rem / tiles_x;
+  tx = rem - ty * tiles_x;
+}
+template <bool U8>
+__device__ __forceinline__ void stem_prefetch_patch(StemPatch<U8>& p, const void* x, int H, int W, int b, int ty, int tx, int warp,
+                                                    int lane) {
+  const int iy0 = 2 * ty * ST_TILE_H - 3, ix0 = 2 * tx * ST_TILE_W - 3 + lane;
+  const bool interior = iy0 >= 0 && iy0 + ST_PATCH_H <= H && ix0 - lane >= 0 && ix0 - lane + ST_PATCH_W <= W;  // CTA-uniform
+  const bool has_b = lane < ST_PATCH_W - 32;
+  if constexpr (U8) {
+    const uint8_t* base = static_cast<const uint8_t*>(x) + ((size_t)b * H * W) * 3;
+#pragma unroll
+    for (int j = 0; j < ST_ROW_SLOTS; ++j) {
+      const int py = warp + 8 * j, iy = iy0 + py;
+      const bool row_ok = py < ST_PATCH_H && (interior || (iy >= 0 && iy < H));
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int ix = ix0 + 32 * t;
+        const bool ok = row_ok && (t == 0 || has_b) && (interior || (ix >= 0 && ix < W));
+        uint32_t v = 0;
+        if (ok) {
+          const uint8_t* q = base + ((size_t)iy * W + ix) * 3;
+          v = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
+        }
+        p.v[j][t][0] = v;
+      }
+    }
+  } else {
+    const size_t HW = (size_t)H * W;
+    const float* base = static_cast<const float*>(x) + (size_t)b * 3 * HW;
+    if (interior) {  // CTA-uniform fast path (all but the border tiles): no per-element bounds logic, strength-reduced addresses
+      const float* q0 = base + (size_t)(iy0 + warp) * W + ix0;
+#pragma unroll
+      for (int j = 0; j < ST_ROW_SLOTS; ++j) {
+        const float* q = q0 + (size_t)(8 * j) * W;
+        const bool row_ok = warp + 8 * j < ST_PATCH_H;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          p.v[j][0][c] = row_ok ? __float_as_uint(__ldg(q + c * HW)) : 0u;
+          p.v[j][1][c] = (row_ok && has_b) ? __float_as_uint(__ldg(q + c * HW + 32)) : 0u;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < ST_ROW_SLOTS; ++j) {
+        const int py = warp + 8 * j, iy = iy0 + py;
+        const bool row_ok = py < ST_PATCH_H && iy >= 0 && iy < H;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int ix = ix0 + 32 * t;
+          const bool ok = row_ok && (t == 0 || has_b) && ix >= 0 && ix < W;
+          const float* q = base + (size_t)(ok ? iy : 0) * W + (ok ? ix : 0);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) p.v[j][t][c] = ok ? __float_as_uint(__ldg(q + c * HW)) : 0u;
+        }
+      }
+    }
+  }
+}
+template <bool U8>
+__device__ __forceinline__ void stem_store_patch(const StemPatch<U8>& p, __nv_bfloat16* patch, int warp, int lane) {
+#pragma unroll
+  for (int j = 0; j < ST_ROW_SLOTS; ++j) {
+    const int py = warp + 8 * j;
+    if (py < ST_PATCH_H) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (t == 0 || lane < ST_PATCH_W - 32) {
+          float f0, f1, f2;
+          if constexpr (U8) {
+            // ToTensor semantics (reference dataset.py:16): uint8 / 255 in fp32, then the bf16 operand rounding
+            const uint32_t v = p.v[j][t][0];
+            f0 = __fdiv_rn((float)(v & 0xffu), 255.0f);
+            f1 = __fdiv_rn((float)((v >> 8) & 0xffu), 255.0f);
+            f2 = __fdiv_rn((float)((v >> 16) & 0xffu), 255.0f);
+          } else {
+            f0 = __uint_as_float(p.v[j][t][0]);
+            f1 = __uint_as_float(p.v[j][t][1]);
+            f2 = __uint_as_float(p.v[j][t][2]);
+          }
+          *reinterpret_cast<uint2*>(patch + (py * ST_PATCH_W + lane + 32 * t) * ST_PCH) = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, 0.f));
+        }
+      }
+    }
+  }
+}
+// im2col rows into the swizzled A tile: 128 pixels x 7 filter rows = 896 segments of 32 bf16 = four 16-byte chunks each;
+// filter row r occupies chunks 4r .. 4r+3 along K, i.e. K block r/2, chunks 4*(r&1) .. +3
+__device__ __forceinline__ void stem_build_im2col(const __nv_bfloat16* patch, uint8_t* sA, int tid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int sidx = tid + i * ST_THREADS;
+    if (sidx < 128 * 7) {
+      const int row = sidx & 127, r = sidx >> 7;
+      const int py = row >> 4, px = row & 15;
+      const uint4* src = reinterpret_cast<const uint4*>(patch + ((2 * py + r) * ST_PATCH_W + 2 * px) * ST_PCH);
+      const uint4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
+      uint8_t* blk = sA + (r >> 1) * 16384 + row * 128;
+      const int c0 = (r & 1) * 4, sw = row & 7;
+      *reinterpret_cast<uint4*>(blk + (((c0 + 0) ^ sw) << 4)) = v0;
+      *reinterpret_cast<uint4*>(blk + (((c0 + 1) ^ sw) << 4)) = v1;
+      *reinterpret_cast<uint4*>(blk + (((c0 + 2) ^ sw) << 4)) = v2;
+      *reinterpret_cast<uint4*>(blk + (((c0 + 3) ^ sw) << 4)) = v3;
+    }
+  }
+}
+// k in [224,256) = chunks 4..7 of K block 3 never receive data: zero them once (they meet zero weights, but must be finite)
+__device__ __forceinline__ void stem_zero_k_padding(uint8_t* sA, __nv_bfloat16* patch, int tid) {
+  for (int i = tid; i < 128 * 4; i += ST_THREADS) {
+    const int row = i >> 2, chunk = 4 + (i & 3);
+    *reinterpret_cast<uint4*>(sA + 3 * 16384 + sw128_off(row, chunk)) = make_uint4(0, 0, 0, 0);
+  }
+  // the patch is fully rewritten for every tile (all 21 x 38 pixels, zeros outside the image)
+  (void)patch;
+}
 
 template <bool U8>
 __global__ void __launch_bounds__(ST_THREADS, 2)
 stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y, const StemTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem;                                   // 3 K blocks x [128 rows][128 B]
-  uint8_t* sB = smem + ST_A_BYTES;                      // 3 K blocks x [64 rows][128 B]
-  uint8_t* sOut = sB + ST_B_BYTES;                      // [128 rows][128 B], 1024-aligned
-  __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(sOut + ST_OUT_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + ((ST_PATCH_ELEMS * 2 + 15) & ~15));
+  uint8_t* sA = smem;                                   // 4 K blocks x [128 rows][128 B]
+  uint8_t* sB = smem + ST_A_BYTES;                      // 4 K blocks x [64 rows][128 B]
+  uint8_t* sOut = sA;                                   // [128 rows][128 B]: the epilogue reuses K block 0 once the MMAs are done
+  __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(sB + ST_B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + ST_PATCH_BYTES);
   uint64_t* w_bar = bars;       // weights landed
   uint64_t* mma_bar = bars + 1; // accumulator ready / A tile free
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2);
+  float* s_scale = reinterpret_cast<float*>(bars + 8);  // 64 bytes in: 16-byte aligned
+  float* s_bias = s_scale + ST_COUT;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);  // same value, provably warp-uniform for the compiler
@@ -79,18 +216,14 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     ptx::tmem_alloc(tmem_ptr_smem, 64);
     ptx::tmem_relinquish();
   }
-  // zero the K padding of the A tile once: k in [168,192) = chunks 5..7 of K block 2, every row
-  for (int i = tid; i < 128 * 3; i += ST_THREADS) {
-    const int row = i / 3, chunk = 5 + i % 3;
-    *reinterpret_cast<uint4*>(sA + 2 * 16384 + sw128_off(row, chunk)) = make_uint4(0, 0, 0, 0);
-  }
-  for (int i = tid; i < 8; i += ST_THREADS) patch[ST_PATCH_H * ST_PATCH_W * 3 + i] = __float2bfloat16(0.f);
+  if (tid >= 64 && tid < 64 + ST_COUT) { s_scale[tid - 64] = a.scale[tid - 64]; s_bias[tid - 64] = a.bias[tid - 64]; }
+  stem_zero_k_padding(sA, patch, tid);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (tid == 0) {  // weights: three (64 k x 64 cout) boxes, once per CTA
+  if (tid == 0) {  // weights: four (64 k x 64 cout) boxes, once per CTA
     ptx::mbar_arrive_expect_tx(w_bar, ST_B_BYTES);
     for (int kb = 0; kb < ST_KBLOCKS; ++kb) ptx::tma_load_2d(sB + kb * 8192, &map_w, w_bar, kb * 64, 0);
   }
@@ -99,123 +232,31 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   uint32_t mma_phase = 0;
   bool first = true;
 
-  // Software pipeline: the NEXT tile's input patch is fetched into registers (PATCH_PER_THREAD independent global
-  // loads in flight per thread) while the current tile is built, multiplied and stored.
-  // Work split: the patch is 3*21 = 63 (channel, row) segments of 38 floats; warp w owns segments w, w+8, ...
-  // (warp-uniform row arithmetic, no per-element div/mod), lane l loads columns l and l+32 (the latter for l < 6).
-  constexpr int PATCH_ROWS = 3 * ST_PATCH_H;                       // 63
-  constexpr int ROWS_PER_WARP = (PATCH_ROWS + 7) / 8;              // 8
-  // U8 input (B,H,W,3): a patch row is 38 px * 3 = 114 contiguous BYTES already in [x][c] order; warp w owns patch rows
-  // w, w+8, w+16 and lane l loads bytes l, l+32, l+64, l+96 of each.
-  constexpr int U8_ROW_BYTES = ST_PATCH_W * 3;                     // 114
-  constexpr int U8_ROWS_PER_WARP = (ST_PATCH_H + 7) / 8;           // 3
-  float pre[U8 ? 1 : ROWS_PER_WARP][2];
-  uint32_t pre8[U8 ? U8_ROWS_PER_WARP : 1];
-  auto prefetch_patch = [&](int t) {
-    const int pb = t / a.tiles_per_img;
-    const int prem = t - pb * a.tiles_per_img;
-    const int pty = prem / a.tiles_x, ptx_ = prem - pty * a.tiles_x;
-    const int piy0 = 2 * pty * ST_TILE_H - 3, pix0 = 2 * ptx_ * ST_TILE_W - 3;
-    if constexpr (U8) {
-      const uint8_t* xb = static_cast<const uint8_t*>(a.x) + (size_t)pb * a.H * a.W * 3;
-      bool ok[4];
-#pragma unroll
-      for (int t4 = 0; t4 < 4; ++t4) {
-        const int j = lane + 32 * t4;
-        const int ix = pix0 + j / 3;
-        ok[t4] = j < U8_ROW_BYTES && ix >= 0 && ix < a.W;
-      }
-#pragma unroll
-      for (int jr = 0; jr < U8_ROWS_PER_WARP; ++jr) {
-        const int py = warp + 8 * jr;                              // warp-uniform
-        const int iy = piy0 + py;
-        const bool ok_row = py < ST_PATCH_H && iy >= 0 && iy < a.H;
-        const uint8_t* rowp = xb + ((size_t)(ok_row ? iy : 0) * a.W + pix0) * 3;  // may point before the row start; guarded
-        uint32_t packed = 0;
-#pragma unroll
-        for (int t4 = 0; t4 < 4; ++t4) {
-          const uint32_t v = (ok_row && ok[t4]) ? (uint32_t)__ldg(rowp + lane + 32 * t4) : 0u;
-          packed |= v << (8 * t4);
-        }
-        pre8[jr] = packed;
-      }
-    } else {
-      const float* xb = static_cast<const float*>(a.x) + (size_t)pb * 3 * a.H * a.W;
-      const int ix_a = pix0 + lane, ix_b = pix0 + lane + 32;
-      const bool ok_a = ix_a >= 0 && ix_a < a.W;
-      const bool ok_b = lane < ST_PATCH_W - 32 && ix_b >= 0 && ix_b < a.W;
-#pragma unroll
-      for (int j = 0; j < ROWS_PER_WARP; ++j) {
-        const int seg = warp + 8 * j;                                // warp-uniform
-        const int c = seg / ST_PATCH_H, py = seg - c * ST_PATCH_H;
-        const int iy = piy0 + py;
-        const bool ok_row = seg < PATCH_ROWS && iy >= 0 && iy < a.H;
-        const float* rowp = xb + ((size_t)c * a.H + (ok_row ? iy : 0)) * a.W;
-        pre[j][0] = (ok_row && ok_a) ? __ldg(rowp + ix_a) : 0.f;
-        pre[j][1] = (ok_row && ok_b) ? __ldg(rowp + ix_b) : 0.f;
-      }
-    }
-  };
-  if ((int)blockIdx.x < a.num_tiles) prefetch_patch(blockIdx.x);
+  // Software pipeline: the NEXT tile's input patch is fetched into registers while the current tile is built, multiplied and stored.
+  StemPatch<U8> pre;
+  int b, ty, tx;
+  if ((int)blockIdx.x < a.num_tiles) {
+    stem_tile_origin(blockIdx.x, a.tiles_per_img, a.tiles_x, b, ty, tx);
+    stem_prefetch_patch<U8>(pre, a.x, a.H, a.W, b, ty, tx, warp_u, lane);
+  }
 
   int dbg_tile = 0;
+  if (a.dbg && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) a.dbg[192 + (blockIdx.x ? 4 : 0)] = clock64();
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++dbg_tile) {
     ST_STAMP(0);
-    if (tid == 0) ptx::bulk_wait_group_read0();  // previous tile's TMA store has drained the staging buffer
-    const int b = tile / a.tiles_per_img;
-    const int rem = tile - b * a.tiles_per_img;
-    const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-    const int oy0 = ty * ST_TILE_H, ox0 = tx * ST_TILE_W;
+    const int oy0 = ty * ST_TILE_H, ox0 = tx * ST_TILE_W, ob = b;
 
-    // ---- 1. prefetched input patch -> smem, bf16, [y][x][c] ----
-    if constexpr (U8) {
-#pragma unroll
-      for (int jr = 0; jr < U8_ROWS_PER_WARP; ++jr) {
-        const int py = warp + 8 * jr;
-        if (py < ST_PATCH_H) {
-          __nv_bfloat16* dstp = patch + py * U8_ROW_BYTES;
-#pragma unroll
-          for (int t4 = 0; t4 < 4; ++t4) {
-            const int j = lane + 32 * t4;
-            // ToTensor semantics (reference dataset.py:16): uint8 / 255 in fp32, then the bf16 operand rounding
-            if (j < U8_ROW_BYTES) dstp[j] = __float2bfloat16_rn(__fdiv_rn((float)((pre8[jr] >> (8 * t4)) & 0xffu), 255.0f));
-          }
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < ROWS_PER_WARP; ++j) {
-        const int seg = warp + 8 * j;
-        if (seg < PATCH_ROWS) {
-          const int c = seg / ST_PATCH_H, py = seg - c * ST_PATCH_H;
-          __nv_bfloat16* dstp = patch + (py * ST_PATCH_W) * 3 + c;
-          dstp[lane * 3] = __float2bfloat16_rn(pre[j][0]);
-          if (lane < ST_PATCH_W - 32) dstp[(lane + 32) * 3] = __float2bfloat16_rn(pre[j][1]);
-        }
-      }
-    }
+    // ---- 1. prefetched input patch -> smem, bf16, [y][x][4] ----
+    stem_store_patch<U8>(pre, patch, warp_u, lane);
+    if (tid == 0) ptx::bulk_wait_group_read0();  // previous tile's TMA store has drained the staging buffer (= K block 0 of sA)
     ST_STAMP(1);
-    __syncthreads();  // patch complete; also: previous tile's epilogue has drained TMEM (all warps passed it)
+    __syncthreads();  // patch complete; staging free; previous tile's epilogue has drained TMEM (all warps passed it)
     ST_STAMP(2);
 
     // ---- 2. im2col rows into the swizzled A tile ----
-    // 128 pixels x 7 filter rows = 896 segments of 24 bf16 (48 B = 3 chunks); k0 = r*24 -> chunk index r*3 overall
-    for (int sidx = tid; sidx < 128 * 7; sidx += ST_THREADS) {
-      const int row = sidx & 127, r = sidx >> 7;
-      const int py = row >> 4, px = row & 15;
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(patch + ((2 * py + r) * ST_PATCH_W + 2 * px) * 3);
-      uint32_t v[12];
-#pragma unroll
-      for (int j = 0; j < 12; ++j) v[j] = src[j];
-#pragma unroll
-      for (int cidx = 0; cidx < 3; ++cidx) {
-        const int gchunk = r * 3 + cidx;  // 16-byte chunk index along K (0..20)
-        uint8_t* dst = sA + (gchunk >> 3) * 16384 + sw128_off(row, gchunk & 7);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(v[4 * cidx], v[4 * cidx + 1], v[4 * cidx + 2], v[4 * cidx + 3]);
-      }
-    }
+    stem_build_im2col(patch, sA, tid);
     ST_STAMP(3);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to tcgen05
+    ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to tcgen05
     ptx::tc_fence_before();
     __syncthreads();
     ST_STAMP(4);
@@ -230,13 +271,18 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         const uint64_t adesc = ptx::make_smem_desc_sw128(a0 + kb * 16384);
         const uint64_t bdesc = ptx::make_smem_desc_sw128(b0 + kb * 8192);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k)
+          if (kb * 64 + k * 16 < 7 * ST_SEG)  // k >= 224 is zero padding on both operands: those two K steps are skipped
+            ptx::umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
       }
       ptx::umma_commit(mma_bar);
     }
     first = false;
     // next tile's input patch -> registers while the tensor core works on this one
-    if (tile + (int)gridDim.x < a.num_tiles) prefetch_patch(tile + gridDim.x);
+    if (tile + (int)gridDim.x < a.num_tiles) {
+      stem_tile_origin(tile + gridDim.x, a.tiles_per_img, a.tiles_x, b, ty, tx);
+      stem_prefetch_patch<U8>(pre, a.x, a.H, a.W, b, ty, tx, warp_u, lane);
+    }
     ST_STAMP(5);
 
     // ---- 4. epilogue (all 8 warps: warp%4 = TMEM lane quarter, warp/4 = channel half) ----
@@ -255,10 +301,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int c = c0 + g * 8;
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.scale + c));
-        const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.scale + c + 4));
-        const float4 t0 = __ldg(reinterpret_cast<const float4*>(a.bias + c));
-        const float4 t1 = __ldg(reinterpret_cast<const float4*>(a.bias + c + 4));
+        const float4 s0 = *reinterpret_cast<const float4*>(s_scale + c);
+        const float4 s1 = *reinterpret_cast<const float4*>(s_scale + c + 4);
+        const float4 t0 = *reinterpret_cast<const float4*>(s_bias + c);
+        const float4 t1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
         const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
         float v[8];
@@ -275,13 +321,18 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     }
     __syncthreads();
     if (tid == 0) {  // one coalesced tile store; rows / columns beyond the image are clipped by the TMA unit
-      ptx::tma_store_4d(&map_y, sOut, 0, ox0, oy0, b);
+      ptx::tma_store_4d(&map_y, sOut, 0, ox0, oy0, ob);
       ptx::bulk_commit_group();
     }
     ST_STAMP(7);
   }
 
+  if (a.dbg && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) a.dbg[193 + (blockIdx.x ? 4 : 0)] = clock64();
   if (tid == 0) ptx::bulk_wait_group0();
+  if (a.dbg && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+    a.dbg[194 + (blockIdx.x ? 4 : 0)] = clock64();
+    a.dbg[195 + (blockIdx.x ? 4 : 0)] = dbg_tile;
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -290,25 +341,24 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   }
 }
 
-
 // ------------------------------------------------------------------------------------------------ stem weight gradient
 // dW[co][c][r][s] = sum_{b,oy,ox} dY[b,oy,ox,co] * X[b,c,2oy-3+r,2ox-3+s]   (autograd of the stem conv, reference
 // src/resnet.py:137 under train.py:35), as a tcgen05 GEMM whose reduction runs over the output pixels:
-//   D[M = co (64, duplicated to 128), N = k (192)] += dY_tile^T[co, 128 px] * im2col_tile[128 px, k]
-// The im2col tile is built exactly like the forward kernel's A tile ([128 px][192 k], 128-byte-swizzled); here it is the
+//   D[M = co (64, duplicated to 128), N = k (256)] += dY_tile^T[co, 128 px] * im2col_tile[128 px, k]
+// The im2col tile is built exactly like the forward kernel's A tile ([128 px][256 k], 128-byte-swizzled); here it is the
 // B operand read MN-major (k contiguous, pixels = GEMM-K strided: 8-pixel groups 1024 B apart, 64-wide k groups 16 KB apart).
 // The dY tile (128 px x 64 co bf16) is one SWIZZLE_128B TMA box, loaded twice so the A operand has 128 rows (rows 64..127 of
-// the accumulator repeat rows 0..63 and are never read).  The fp32 accumulator (128 lanes x 192 columns of TMEM) lives across
-// ALL tiles of the persistent CTA; one epilogue at the end writes the CTA's partial [64 co][192 k], summed in a fixed order by
+// the accumulator repeat rows 0..63 and are never read).  The fp32 accumulator (128 lanes x 256 columns of TMEM) lives across
+// ALL tiles of the persistent CTA; one epilogue at the end writes the CTA's partial [64 co][256 k], summed in a fixed order by
 // stem_wgrad_tc_finalize_kernel (deterministic, no atomics).  x is rounded to bf16 exactly as in the forward kernel.
 constexpr int SWG_DY_TILE_BYTES = 128 * 128;                           // 128 px x 64 co bf16
 constexpr int SWG_DY_BYTES = 2 * SWG_DY_TILE_BYTES;                     // two copies: accumulator rows 0..63 and 64..127
-constexpr int SWG_SMEM_BYTES = 1024 + ST_A_BYTES + SWG_DY_BYTES + ((ST_PATCH_ELEMS * 2 + 15) & ~15) + 64;
+constexpr int SWG_SMEM_BYTES = 1024 + ST_A_BYTES + SWG_DY_BYTES + ST_PATCH_BYTES + 64;
 constexpr int SWG_TMEM_COLS = 256;
 
 struct StemWgradArgs {
   const float* x;     // (B,3,H,W) fp32 NCHW
-  float* partial;     // [grid][64 co][192 k] fp32
+  float* partial;     // [grid][64 co][256 k] fp32
   int B, H, W, Ho, Wo;
   int tiles_x, tiles_per_img, num_tiles;
 };
@@ -329,10 +379,10 @@ __global__ void __launch_bounds__(ST_THREADS, 2)
 stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const StemWgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem;                                   // im2col: 3 k blocks x [128 px][128 B]
+  uint8_t* sA = smem;                                   // im2col: 4 k blocks x [128 px][128 B]
   uint8_t* sDy = smem + ST_A_BYTES;                     // 2 x [128 px][128 B]
   __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(sDy + SWG_DY_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + ((ST_PATCH_ELEMS * 2 + 15) & ~15));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + ST_PATCH_BYTES);
   uint64_t* dy_bar = bars;       // dY tile landed
   uint64_t* mma_bar = bars + 1;  // this tile's MMAs done: sA / sDy may be overwritten
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2);
@@ -350,11 +400,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const StemWgrad
     ptx::tmem_alloc(tmem_ptr_smem, SWG_TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  for (int i = tid; i < 128 * 3; i += ST_THREADS) {  // k in [168,192): zero once (meets zero... never written again)
-    const int row = i / 3, chunk = 5 + i % 3;
-    *reinterpret_cast<uint4*>(sA + 2 * 16384 + sw128_off(row, chunk)) = make_uint4(0, 0, 0, 0);
-  }
-  for (int i = tid; i < 8; i += ST_THREADS) patch[ST_PATCH_H * ST_PATCH_W * 3 + i] = __float2bfloat16(0.f);
+  stem_zero_k_padding(sA, patch, tid);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -364,73 +410,30 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const StemWgrad
   uint32_t phase = 0;   // parity of dy_bar / mma_bar for the current tile (each completes once per tile)
   bool first = true;
 
-  constexpr int PATCH_ROWS = 3 * ST_PATCH_H;                       // 63 (channel, row) segments of 38 floats
-  constexpr int ROWS_PER_WARP = (PATCH_ROWS + 7) / 8;              // 8
-  float pre[ROWS_PER_WARP][2];
-  auto prefetch_patch = [&](int t) {
-    const int pb = t / a.tiles_per_img;
-    const int prem = t - pb * a.tiles_per_img;
-    const int pty = prem / a.tiles_x, ptx_ = prem - pty * a.tiles_x;
-    const int piy0 = 2 * pty * ST_TILE_H - 3, pix0 = 2 * ptx_ * ST_TILE_W - 3;
-    const float* xb = a.x + (size_t)pb * 3 * a.H * a.W;
-    const int ix_a = pix0 + lane, ix_b = pix0 + lane + 32;
-    const bool ok_a = ix_a >= 0 && ix_a < a.W;
-    const bool ok_b = lane < ST_PATCH_W - 32 && ix_b >= 0 && ix_b < a.W;
-#pragma unroll
-    for (int j = 0; j < ROWS_PER_WARP; ++j) {
-      const int seg = warp + 8 * j;                                // warp-uniform
-      const int c = seg / ST_PATCH_H, py = seg - c * ST_PATCH_H;
-      const int iy = piy0 + py;
-      const bool ok_row = seg < PATCH_ROWS && iy >= 0 && iy < a.H;
-      const float* rowp = xb + ((size_t)c * a.H + (ok_row ? iy : 0)) * a.W;
-      pre[j][0] = (ok_row && ok_a) ? __ldg(rowp + ix_a) : 0.f;
-      pre[j][1] = (ok_row && ok_b) ? __ldg(rowp + ix_b) : 0.f;
-    }
-  };
-  if ((int)blockIdx.x < a.num_tiles) prefetch_patch(blockIdx.x);
+  StemPatch<false> pre;
+  int b, ty, tx;
+  if ((int)blockIdx.x < a.num_tiles) {
+    stem_tile_origin(blockIdx.x, a.tiles_per_img, a.tiles_x, b, ty, tx);
+    stem_prefetch_patch<false>(pre, a.x, a.H, a.W, b, ty, tx, warp_u, lane);
+  }
 
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-    const int b = tile / a.tiles_per_img;
-    const int rem = tile - b * a.tiles_per_img;
-    const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-    const int oy0 = ty * ST_TILE_H, ox0 = tx * ST_TILE_W;
+    const int oy0 = ty * ST_TILE_H, ox0 = tx * ST_TILE_W, ob = b;
 
-    // ---- 1. prefetched input patch -> smem, bf16, [y][x][c] (the patch buffer is not an MMA operand) ----
-#pragma unroll
-    for (int j = 0; j < ROWS_PER_WARP; ++j) {
-      const int seg = warp + 8 * j;
-      if (seg < PATCH_ROWS) {
-        const int c = seg / ST_PATCH_H, py = seg - c * ST_PATCH_H;
-        __nv_bfloat16* dstp = patch + (py * ST_PATCH_W) * 3 + c;
-        dstp[lane * 3] = __float2bfloat16_rn(pre[j][0]);
-        if (lane < ST_PATCH_W - 32) dstp[(lane + 32) * 3] = __float2bfloat16_rn(pre[j][1]);
-      }
-    }
+    // ---- 1. prefetched input patch -> smem (the patch buffer is not an MMA operand) ----
+    stem_store_patch<false>(pre, patch, warp_u, lane);
     // ---- 2. previous tile's MMAs have finished reading sA / sDy; fetch this tile's dY ----
     if (!first) ptx::mbar_wait(mma_bar, phase ^ 1, 14);
     if (tid == 0) {
       ptx::mbar_arrive_expect_tx(dy_bar, SWG_DY_BYTES);
-      ptx::tma_load_4d(sDy, &map_dy, dy_bar, 0, ox0, oy0, b);                      // pixels beyond the image arrive as zeros
-      ptx::tma_load_4d(sDy + SWG_DY_TILE_BYTES, &map_dy, dy_bar, 0, ox0, oy0, b);
+      ptx::tma_load_4d(sDy, &map_dy, dy_bar, 0, ox0, oy0, ob);                      // pixels beyond the image arrive as zeros
+      ptx::tma_load_4d(sDy + SWG_DY_TILE_BYTES, &map_dy, dy_bar, 0, ox0, oy0, ob);
     }
     __syncthreads();  // patch complete
 
     // ---- 3. im2col rows into the swizzled tile (same layout as the forward kernel's A tile) ----
-    for (int sidx = tid; sidx < 128 * 7; sidx += ST_THREADS) {
-      const int row = sidx & 127, r = sidx >> 7;
-      const int py = row >> 4, px = row & 15;
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(patch + ((2 * py + r) * ST_PATCH_W + 2 * px) * 3);
-      uint32_t v[12];
-#pragma unroll
-      for (int j = 0; j < 12; ++j) v[j] = src[j];
-#pragma unroll
-      for (int cidx = 0; cidx < 3; ++cidx) {
-        const int gchunk = r * 3 + cidx;
-        uint8_t* dst = sA + (gchunk >> 3) * 16384 + sw128_off(row, gchunk & 7);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(v[4 * cidx], v[4 * cidx + 1], v[4 * cidx + 2], v[4 * cidx + 3]);
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    stem_build_im2col(patch, sA, tid);
+    ptx::fence_proxy_async_smem();
     ptx::tc_fence_before();
     __syncthreads();
 
@@ -450,10 +453,13 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const StemWgrad
     }
     first = false;
     phase ^= 1;
-    if (tile + (int)gridDim.x < a.num_tiles) prefetch_patch(tile + gridDim.x);
+    if (tile + (int)gridDim.x < a.num_tiles) {
+      stem_tile_origin(tile + gridDim.x, a.tiles_per_img, a.tiles_x, b, ty, tx);
+      stem_prefetch_patch<false>(pre, a.x, a.H, a.W, b, ty, tx, warp_u, lane);
+    }
   }
 
-  // ---- epilogue: the CTA's accumulated [64 co][192 k] -> partial (warp%4 = TMEM lane quarter, warp/4 = column half) ----
+  // ---- epilogue: the CTA's accumulated [64 co][256 k] -> partial (warp%4 = TMEM lane quarter, warp/4 = column half) ----
   if (!first) {
     ptx::mbar_wait(mma_bar, phase ^ 1, 16);
     ptx::tc_fence_after();
@@ -481,14 +487,14 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const StemWgrad
   }
 }
 
-// dw (64,3,7,7) OIHW (+)= sum over CTAs of partial[cta][co][r*24 + s*3 + c]; fixed order, double accumulation
+// dw (64,3,7,7) OIHW (+)= sum over CTAs of partial[cta][co][r*32 + s*4 + c]; fixed order, double accumulation
 __global__ void __launch_bounds__(256) stem_wgrad_tc_finalize_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ dw,
                                                                     int accumulate) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;   // co * 147 + (c*7 + r)*7 + s
   if (j >= 64 * 147) return;
   const int co = j / 147, t = j - co * 147;
   const int c = t / 49, rs = t - c * 49, r = rs / 7, sft = rs - r * 7;
-  const float* p = partial + (size_t)co * ST_K + r * ST_SEG + sft * 3 + c;
+  const float* p = partial + (size_t)co * ST_K + r * ST_SEG + sft * ST_PCH + c;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   int b = 0;
   for (; b + 4 <= nblk; b += 4) {
@@ -506,17 +512,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_fn();
 
-// OIHW (64,3,7,7) fp32 -> (64, 192) bf16 with k = r*24 + s*3 + c, zeros elsewhere
+// OIHW (64,3,7,7) fp32 -> (64, 256) bf16 with k = r*32 + s*4 + c, zeros elsewhere
 __global__ void stem_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ST_COUT * ST_K) return;
   const int o = i / ST_K, k = i - o * ST_K;
   const int r = k / ST_SEG, j = k - r * ST_SEG;
+  const int s = j / ST_PCH, c = j - s * ST_PCH;
   float v = 0.f;
-  if (r < 7 && j < 21) {
-    const int s = j / 3, c = j - s * 3;
-    v = w[((o * 3 + c) * 7 + r) * 7 + s];
-  }
+  if (r < 7 && s < 7 && c < 3) v = w[((o * 3 + c) * 7 + r) * 7 + s];
   out[i] = __float2bfloat16_rn(v);
 }
 

@@ -74,7 +74,7 @@ def conv_bn_act(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, bi
 
 
 def stem_pack_weights(w_oihw: torch.Tensor) -> torch.Tensor:
-    """conv1.weight (64,3,7,7) fp32 -> the (64,192) bf16 K layout of the tensor-core stem."""
+    """conv1.weight (64,3,7,7) fp32 -> the (64,256) bf16 K layout of the tensor-core stem (k = r*32 + s*4 + c)."""
     _need_cuda(w_oihw)
     if tuple(w_oihw.shape) != (64, 3, 7, 7):
         raise ValueError("stem weight must be (64,3,7,7)")

@@ -101,7 +101,7 @@ HK_API int hk_conv_bn_act_fwd(const HkConvDesc* desc, const void* x, const void*
 /* Stem on the tensor cores (bf16 mode): conv 7x7 s2 p3 (3->64) + folded BN + ReLU.
  * Replaces src/resnet.py:137-139,199-201.  x (B,3,H,W) fp32 NCHW -- the reference's input tensor -- is rounded to
  * bf16 on the fly; y (B,H/2,W/2,64) bf16 NHWC.  w_packed comes from hk_stem_pack_weights (conv1.weight (64,3,7,7)
- * fp32 -> (64,192) bf16, K laid out filter-row-major with zero padding); scale/bias from hk_pack_conv_weights. */
+ * fp32 -> (64,256) bf16, k = r*32 + s*4 + c, zero padding elsewhere); scale/bias from hk_pack_conv_weights. */
 HK_API size_t hk_stem_packed_weight_bytes(void);
 HK_API int hk_stem_pack_weights(const float* w_oihw, void* w_out, void* stream);
 HK_API int hk_stem_fwd(const float* x_nchw, const void* w_packed, const float* scale, const float* bias,
