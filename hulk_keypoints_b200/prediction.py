@@ -50,11 +50,13 @@ class Prediction:
         return e_x / e_x.sum()
 
     def expectation(self, d):
-        """Soft-argmax (x, y) of one (H, W) map, truncated to int like the reference."""
+        """Soft-argmax of one (H, W) map, as written in reference prediction.py:31-38: the map is flattened in the order of
+        `d.T.ravel()` while the index arrays assume row-major order (x = i % W, y = i // W), so for H != W rows and columns mix;
+        kept as is for result parity (the reference computes it in `plot` and discards it).  Truncated to int."""
         d = np.asarray(d)
-        height, width = d.shape
-        p = self.softmax(d.ravel())
-        flat = np.arange(height * width)
+        width, height = d.T.shape
+        p = self.softmax(d.T.ravel())
+        flat = np.arange(width * height)
         return [int(np.dot(p, flat % width)), int(np.dot(p, flat // width))]
 
     def plot(self, img, heatmap, image_id=0, cls=None, classes=None):

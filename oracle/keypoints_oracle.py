@@ -258,6 +258,20 @@ def argmax_decode(heat: np.ndarray) -> np.ndarray:
     return np.stack([flat // W, flat % W], axis=-1).astype(np.int64)
 
 
+def soft_expectation(d: np.ndarray) -> List[int]:
+    """Soft-argmax of one (H, W) map exactly as written in reference src/prediction.py:26-38: softmax over the map, flattened in
+    the order of `d.T.ravel()` (column-major), against x = i % W and y = i // W with W = d.shape[1] -- the index arrays assume
+    row-major order, so for H != W the "expectation" mixes rows and columns; the quirk is part of the reference's result and is
+    kept.  Truncated to int like the reference."""
+    d = np.asarray(d)
+    width, height = d.T.shape
+    flat = d.T.ravel()
+    e = np.exp(flat - np.max(flat))
+    p = e / e.sum()
+    idx = np.arange(width * height)
+    return [int(np.dot(p, idx % width)), int(np.dot(p, idx // width))]
+
+
 def gauss_targets(uv: np.ndarray, height: int, width: int, sigma: float) -> np.ndarray:
     """`gauss_2d_batch` (dataset.py:36-44) for a batch: uv (B,K,2)=(x,y) -> (B,K,H,W) float64.
 

@@ -145,3 +145,36 @@ def test_bilinear_restatement_corners():
     mine = O.bilinear_upsample_ac(lo.numpy(), 48, 64)
     assert np.abs(up - mine).max() < 1e-6
     assert mine[0, 0, 0, 0] == lo[0, 0, 0, 0] and mine[0, 1, 47, 63] == lo[0, 1, 5, 7]
+
+
+def _prediction_golden_maps():
+    """The seeded maps of oracle/make_golden_prediction.py (same generator, same order)."""
+    rng = np.random.RandomState(7)
+    out = []
+    for h, w in ((5, 7), (12, 12), (48, 64), (33, 17)):
+        d = rng.rand(h, w).astype(np.float32)
+        d[rng.randint(h), rng.randint(w)] += 6.0
+        out.append(d)
+    out.append((np.eye(9, 13, dtype=np.float32) * 3).astype(np.float32))
+    return out
+
+
+def test_soft_expectation_matches_reference_golden():
+    """oracle.soft_expectation and the product's Prediction.expectation / softmax against outputs of the unmodified reference class
+    (tests/golden/prediction_v1.json; reference src/prediction.py:26-38, transposed-ravel quirk included)."""
+    import json
+    import os
+
+    import hulk_keypoints_b200 as hk
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "prediction_v1.json")) as f:
+        cases = json.load(f)["cases"]
+    pred = hk.Prediction(hk.KeypointsGauss(4), 4, 480, 640, use_cuda=False)
+    maps = _prediction_golden_maps()
+    assert len(maps) == len(cases)
+    for d, c in zip(maps, cases):
+        assert list(d.shape) == c["shape"]
+        assert O.soft_expectation(d) == c["expectation"]
+        assert pred.expectation(d) == c["expectation"]
+        sm = pred.softmax(d.ravel().astype(np.float64))
+        assert abs(sm.max() - c["softmax_max"]) < 1e-15 and abs(sm.sum() - c["softmax_sum"]) < 1e-15
