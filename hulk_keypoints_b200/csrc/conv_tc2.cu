@@ -99,6 +99,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int total_tiles = a.num_m_tiles * a.num_n_tiles;
   const int num_kb = a.kh * a.kw * a.cblocks;
 
+  ptx::griddep_launch_dependents();  // the next kernel's CTAs may take over SMs as ours exit (its prologue overlaps our tail)
   ptx::cluster_sync_all();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_x);
@@ -130,6 +131,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   if (warp == 0) {
     {
       // ===================== TMA producer (both CTAs; whole warp waits, one elected lane issues) =====================
+      ptx::griddep_wait();  // the previous kernel's output (our input) is complete and visible
       uint32_t stage = 0, phase = 0, pit = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++pit) {
         const int m_tile = tile / a.num_n_tiles, n_tile = tile - m_tile * a.num_n_tiles;
@@ -204,6 +206,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const int sw = row & 7;
     constexpr int CHUNKS = BLOCK_N / 64;
     const bool has_res = a.residual != nullptr;
+    ptx::griddep_wait();  // before the first residual load / output store
     uint32_t it = 0, chunk_ctr = 0;      // chunk_ctr selects the staging buffer and the res_bar phase
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -338,7 +341,8 @@ static int launch_tc2(const CUtensorMap& mx, const CUtensorMap& mw, const CUtens
   const int total = a.num_m_tiles * a.num_n_tiles;
   int clusters = sm_count() / 2;
   if (clusters > total) clusters = total;
-  conv_tc2_kernel<BLOCK_N><<<2 * clusters, T2_THREADS, Cfg::SMEM_BYTES, s>>>(mx, mw, my, mres, a);
+  cudaError_t le = launch_pdl(conv_tc2_kernel<BLOCK_N>, dim3(2 * clusters), dim3(T2_THREADS), (size_t)Cfg::SMEM_BYTES, s, mx, mw, my, mres, a);
+  if (le != cudaSuccess) return fail(HK_ERR_CUDA, "conv_tc2_kernel: %s", cudaGetErrorString(le));
   return check_launch("conv_tc2_kernel");
 }
 

@@ -78,6 +78,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int total_tiles = a.num_m_tiles * a.num_n_tiles;
 
+  ptx::griddep_launch_dependents();  // the next kernel's CTAs may take over SMs as ours exit (its prologue overlaps our tail)
   ptx::cluster_sync_all();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_x);
@@ -112,6 +113,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; whole warp waits, one elected lane issues) =====================
+    ptx::griddep_wait();  // the previous kernel's output (our input) is complete and visible
     uint32_t as = 0, aph = 0, bs = 0, bph = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int m_tile = tile / a.num_n_tiles, n_tile = tile - m_tile * a.num_n_tiles;
@@ -188,6 +190,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int sw = row & 7;
     constexpr int CHUNKS = BLOCK_N / 64;
     const bool has_res = a.residual != nullptr;
+    ptx::griddep_wait();  // before the first residual load / output store
     uint32_t it = 0, chunk_ctr = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -316,7 +319,8 @@ static int launch_tc2h(const CUtensorMap& mx, const CUtensorMap& mw, const CUten
   const int total = a.num_m_tiles * a.num_n_tiles;
   int clusters = sm_count() / 2;
   if (clusters > total) clusters = total;
-  conv_tc2h_kernel<BLOCK_N><<<2 * clusters, TH_THREADS, smem, s>>>(mx, mw, my, mres, a);
+  cudaError_t le = launch_pdl(conv_tc2h_kernel<BLOCK_N>, dim3(2 * clusters), dim3(TH_THREADS), (size_t)smem, s, mx, mw, my, mres, a);
+  if (le != cudaSuccess) return fail(HK_ERR_CUDA, "conv_tc2h_kernel: %s", cudaGetErrorString(le));
   return check_launch("conv_tc2h_kernel");
 }
 

@@ -67,6 +67,7 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp: provably uniform
 
+  ptx::griddep_launch_dependents();  // the next kernel's CTAs may take over SMs as ours exit (its prologue overlaps our tail)
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_x);
     ptx::prefetch_tensormap(&map_w);
@@ -92,6 +93,7 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     ptx::tmem_relinquish();
   }
   if (warp == 3) {
+    ptx::griddep_wait();  // scale / bias may have been written by the previous kernel (weight packing)
     for (int i = lane; i < C64_C; i += 32) { s_scale[i] = a.scale[i]; s_bias[i] = a.bias[i]; }
   }
   ptx::tc_fence_before();
@@ -102,6 +104,7 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   if (warp == 0) {
     {
       // ===================== TMA producer (whole warp waits, one elected lane issues) =====================
+      ptx::griddep_wait();  // no global read (weights included) before the previous kernel has completed
       if (lane == 0) {
         ptx::mbar_arrive_expect_tx(w_bar, C64_W_BYTES);
         for (int t = 0; t < 9; ++t) ptx::tma_load_2d(sW + t * (C64_C * 128), &map_w, w_bar, t * C64_C, 0);
@@ -170,6 +173,7 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     // tile takes half as long as with 4 warps, which were the slowest stage of the pipeline (2.4k clocks per tile against 2.0k of MMAs)
     const int q = warp & 3, half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
+    ptx::griddep_wait();  // before the first residual load / output store
     const bool leader = (warp == 4 && lane == 0);
     const int sw = row & 7;
     uint32_t it = 0;
@@ -355,7 +359,8 @@ int conv_tc_c64_launch(const HkConvDesc& d, const void* x, const void* w, const 
   }
   int grid = sm_count();
   if (grid > a.num_tiles) grid = a.num_tiles;
-  conv_tc_c64_kernel<<<grid, C64_THREADS, smem, s>>>(mx, mw, my, mres, a);
+  cudaError_t le = launch_pdl(conv_tc_c64_kernel, dim3(grid), dim3(C64_THREADS), (size_t)smem, s, mx, mw, my, mres, a);
+  if (le != cudaSuccess) return fail(HK_ERR_CUDA, "conv_tc_c64_kernel: %s", cudaGetErrorString(le));
   return check_launch("conv_tc_c64_kernel");
 }
 

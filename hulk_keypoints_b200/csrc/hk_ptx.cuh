@@ -68,6 +68,13 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// ---------------- programmatic dependent launch ----------------
+// launch_dependents: the next kernel in the stream (if it was launched with the programmatic-serialization attribute) may start
+// occupying SMs as this grid's CTAs exit; griddep_wait: block until every prerequisite grid has completed and its memory is
+// visible.  A kernel launched normally sees both as no-ops.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------- TMA ----------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
