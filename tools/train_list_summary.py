@@ -1,0 +1,17 @@
+"""Aggregate a train-step ncu launch list (tools/gpu_train_lists.sh) by kernel: last step only.  usage: train_list_summary.py csv"""
+import collections, csv, sys
+rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) >= 15 and r[0].isdigit()]
+by = collections.OrderedDict()
+for r in rows:
+    by.setdefault(r[0], {"k": r[4].split('(')[0].replace('void ', '').replace('hk::', '')})[r[12]] = float(r[14].replace(',', ''))
+L = list(by.values())
+idx = [i for i, l in enumerate(L) if l['k'] == 'stem_pack_kernel']
+step = L[idx[-1]:]
+agg = {}
+for l in step:
+    a = agg.setdefault(l['k'], [0, 0, 0]); a[0] += l['gpu__time_duration.sum']; a[1] += 1
+    a[2] += l.get('dram__bytes_read.sum', 0) + l.get('dram__bytes_write.sum', 0)
+tot = sum(a[0] for a in agg.values())
+print("step ms", round(tot / 1e6, 3), "launches", len(step))
+for k, (t, n, b) in sorted(agg.items(), key=lambda x: -x[1][0])[: int(sys.argv[2]) if len(sys.argv) > 2 else 40]:
+    print(f"{k[:48]:48s} {n:4d} {t/1e6:8.3f} ms {100*t/tot:5.1f}%  avg {t/n/1e3:7.1f} us  {b/1e9:7.2f} GB {b/t if t else 0:6.0f} GB/s")
