@@ -82,9 +82,9 @@ def _declare(lib):
     lib.hk_bn_train_stats.restype = i
     lib.hk_bn_train_stats.argtypes = [vp, ll, i, vp, vp, vp, vp, f, f, vp, vp, vp, vp, vp, sz, vp]
     lib.hk_bn_apply_fwd.restype = i
-    lib.hk_bn_apply_fwd.argtypes = [vp, vp, vp, vp, i, vp, ll, i, vp]
+    lib.hk_bn_apply_fwd.argtypes = [vp, vp, vp, vp, i, vp, vp, ll, i, vp]
     lib.hk_bn_train_bwd.restype = i
-    lib.hk_bn_train_bwd.argtypes = [vp, vp, vp, vp, vp, vp, ll, i, vp, vp, i, vp, vp, vp, sz, vp]
+    lib.hk_bn_train_bwd.argtypes = [vp, vp, i, vp, vp, vp, vp, ll, i, vp, vp, i, vp, vp, vp, sz, vp]
     lib.hk_pack_conv_weights_dgrad.restype = i
     lib.hk_pack_conv_weights_dgrad.argtypes = [vp, i, i, i, i, vp, vp]
     lib.hk_zero_insert2x.restype = i

@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(BN_FIN_THREADS) bn_stats_finalize_kernel(const
 __global__ void __launch_bounds__(BN_THREADS) bn_apply_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                                                  const float* __restrict__ shift,
                                                                  const __nv_bfloat16* __restrict__ residual, int relu,
-                                                                 __nv_bfloat16* __restrict__ out, long long nvec, int C) {
+                                                                 __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ relu_bits,
+                                                                 long long nvec, int C) {
   // the grid stride (gridDim*256) is a multiple of C/8, so a thread keeps its 8 channels: coefficients live in registers
   const int cg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % (C >> 3));
   float sc[8], sh[8];
@@ -145,6 +146,12 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_fwd_kernel(const __nv_bfl
       for (int j = 0; j < 8; ++j) o[j] += r.v[j];
     }
     if (relu) {
+      if (relu_bits) {  // bit j = [out_j > 0]: the ReLU mask of the backward pass at 1/16 of the bytes of `out`
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m |= (o[j] > 0.f ? 1u : 0u) << j;
+        relu_bits[i] = (uint8_t)m;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
     }
@@ -153,8 +160,9 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_fwd_kernel(const __nv_bfl
 }
 
 // ---- backward reduce: s1 = sum d', s2 = sum d'*xhat with d' = dout*[out>0] ----
+template <bool BITS>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dout,
-                                                                   const __nv_bfloat16* __restrict__ out_mask,
+                                                                   const void* __restrict__ out_mask,
                                                                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                                                                    const float* __restrict__ invstd, long long P, int C,
                                                                    float* __restrict__ partial) {
@@ -167,9 +175,15 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_partial_kernel(const __nv_b
     const long long off = r * C + cg * 8;
     Vec8 d = load8(dout + off);
     if (out_mask) {
-      const Vec8 m = load8(out_mask + off);
+      if constexpr (BITS) {
+        const uint32_t m = static_cast<const uint8_t*>(out_mask)[off >> 3];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d.v[j] = m.v[j] > 0.f ? d.v[j] : 0.f;
+        for (int j = 0; j < 8; ++j) d.v[j] = (m >> j) & 1u ? d.v[j] : 0.f;
+      } else {
+        const Vec8 m = load8(static_cast<const __nv_bfloat16*>(out_mask) + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d.v[j] = m.v[j] > 0.f ? d.v[j] : 0.f;
+      }
     }
     const Vec8 v = load8(y + off);
 #pragma unroll
@@ -200,8 +214,9 @@ __global__ void __launch_bounds__(BN_FIN_THREADS) bn_bwd_finalize_kernel(const f
 
 // dy = coef0 * (d' - coef1 - xhat*coef2) = k0*d' + k1*y + k2 per channel; optionally also writes d' (the gradient that flows
 // into the shortcut branch).  The thread's 8 channels are loop-invariant (see bn_apply_fwd_kernel): 24 coefficients in registers.
+template <bool BITS>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout,
-                                                                 const __nv_bfloat16* __restrict__ out_mask,
+                                                                 const void* __restrict__ out_mask,
                                                                  const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                                                                  const float* __restrict__ invstd, const float* __restrict__ coef,
                                                                  __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dmasked,
@@ -219,9 +234,15 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const __nv_bfl
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     Vec8 d = load8(dout + i * 8);
     if (out_mask) {
-      const Vec8 m = load8(out_mask + i * 8);
+      if constexpr (BITS) {
+        const uint32_t m = static_cast<const uint8_t*>(out_mask)[i];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d.v[j] = m.v[j] > 0.f ? d.v[j] : 0.f;
+        for (int j = 0; j < 8; ++j) d.v[j] = (m >> j) & 1u ? d.v[j] : 0.f;
+      } else {
+        const Vec8 m = load8(static_cast<const __nv_bfloat16*>(out_mask) + i * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d.v[j] = m.v[j] > 0.f ? d.v[j] : 0.f;
+      }
     }
     if (dmasked) store8(dmasked + i * 8, d.v);
     const Vec8 v = load8(y + i * 8);
@@ -272,18 +293,18 @@ int hk_bn_train_stats(const void* y, long long P, int C, const float* gamma, con
 }
 
 int hk_bn_apply_fwd(const void* y, const float* scale, const float* shift, const void* residual_or_null, int relu, void* out,
-                    long long P, int C, void* stream) {
+                    void* relu_bits_or_null, long long P, int C, void* stream) {
   using namespace hk;
   HK_REQUIRE(y && scale && shift && out, "hk_bn_apply_fwd: null pointer");
   HK_REQUIRE(P > 0 && C >= 8 && (C & 7) == 0, "hk_bn_apply_fwd: bad shape");
   const long long nvec = P * (C >> 3);
   bn_apply_fwd_kernel<<<bn_grid_elems(nvec), BN_THREADS, 0, as_stream(stream)>>>(
       static_cast<const __nv_bfloat16*>(y), scale, shift, static_cast<const __nv_bfloat16*>(residual_or_null), relu,
-      static_cast<__nv_bfloat16*>(out), nvec, C);
+      static_cast<__nv_bfloat16*>(out), static_cast<uint8_t*>(relu_bits_or_null), nvec, C);
   return check_launch("bn_apply_fwd_kernel");
 }
 
-int hk_bn_train_bwd(const void* dout, const void* out_mask_or_null, const void* y, const float* mean, const float* invstd,
+int hk_bn_train_bwd(const void* dout, const void* out_mask_or_null, int mask_is_bits, const void* y, const float* mean, const float* invstd,
                     const float* gamma, long long P, int C, float* dgamma, float* dbeta, int accumulate, void* dy,
                     void* dmasked_or_null, void* ws, size_t ws_bytes, void* stream) {
   using namespace hk;
@@ -294,17 +315,22 @@ int hk_bn_train_bwd(const void* dout, const void* out_mask_or_null, const void* 
   float* partial = static_cast<float*>(ws);
   float* coef = partial + (size_t)BN_MAX_BLOCKS * 2 * C;
   const __nv_bfloat16* d = static_cast<const __nv_bfloat16*>(dout);
-  const __nv_bfloat16* m = static_cast<const __nv_bfloat16*>(out_mask_or_null);
+  const void* m = out_mask_or_null;
   const __nv_bfloat16* yy = static_cast<const __nv_bfloat16*>(y);
-  bn_bwd_partial_kernel<<<blocks, BN_THREADS, 0, as_stream(stream)>>>(d, m, yy, mean, invstd, P, C, partial);
+  if (mask_is_bits) bn_bwd_partial_kernel<true><<<blocks, BN_THREADS, 0, as_stream(stream)>>>(d, m, yy, mean, invstd, P, C, partial);
+  else bn_bwd_partial_kernel<false><<<blocks, BN_THREADS, 0, as_stream(stream)>>>(d, m, yy, mean, invstd, P, C, partial);
   int rc = check_launch("bn_bwd_partial_kernel");
   if (rc) return rc;
   bn_bwd_finalize_kernel<<<ceil_div(C, 32), BN_FIN_THREADS, 0, as_stream(stream)>>>(partial, blocks, P, C, gamma, invstd, dgamma, dbeta, accumulate, coef);
   rc = check_launch("bn_bwd_finalize_kernel");
   if (rc) return rc;
   const long long nvec = P * (C >> 3);
-  bn_bwd_apply_kernel<<<bn_grid_elems(nvec), BN_THREADS, 0, as_stream(stream)>>>(d, m, yy, mean, invstd, coef, static_cast<__nv_bfloat16*>(dy),
-                                                                               static_cast<__nv_bfloat16*>(dmasked_or_null), nvec, C);
+  if (mask_is_bits)
+    bn_bwd_apply_kernel<true><<<bn_grid_elems(nvec), BN_THREADS, 0, as_stream(stream)>>>(d, m, yy, mean, invstd, coef, static_cast<__nv_bfloat16*>(dy),
+                                                                                       static_cast<__nv_bfloat16*>(dmasked_or_null), nvec, C);
+  else
+    bn_bwd_apply_kernel<false><<<bn_grid_elems(nvec), BN_THREADS, 0, as_stream(stream)>>>(d, m, yy, mean, invstd, coef, static_cast<__nv_bfloat16*>(dy),
+                                                                                        static_cast<__nv_bfloat16*>(dmasked_or_null), nvec, C);
   return check_launch("bn_bwd_apply_kernel");
 }
 

@@ -234,14 +234,17 @@ def bn_train_stats(y: torch.Tensor, gamma, beta, running_mean, running_var, mome
 
 
 def bn_apply(y: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, relu: bool, residual: Optional[torch.Tensor] = None,
-             out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _need_cuda(y, scale, shift, residual, out)
+             out: Optional[torch.Tensor] = None, relu_bits: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = relu?(y*scale + shift [+ residual]); relu_bits (uint8, numel/8): receives the ReLU mask as one bit per element."""
+    _need_cuda(y, scale, shift, residual, out, relu_bits)
     Cc = y.shape[-1]
     P = y.numel() // Cc
     if out is None:
         out = torch.empty_like(y)
-    check(lib().hk_bn_apply_fwd(ptr(y), ptr(scale), ptr(shift), ptr(residual), int(relu), ptr(out), C.c_longlong(P), Cc, stream_ptr()),
-          "hk_bn_apply_fwd")
+    if relu_bits is not None and (relu_bits.dtype != torch.uint8 or relu_bits.numel() < y.numel() // 8):
+        raise ValueError("relu_bits must be a uint8 tensor of numel/8 bytes")
+    check(lib().hk_bn_apply_fwd(ptr(y), ptr(scale), ptr(shift), ptr(residual), int(relu), ptr(out), ptr(relu_bits), C.c_longlong(P), Cc,
+                                stream_ptr()), "hk_bn_apply_fwd")
     return out
 
 
@@ -251,7 +254,8 @@ def bn_train_bwd(dout: torch.Tensor, out_mask: Optional[torch.Tensor], y: torch.
     _need_cuda(dout, out_mask, y, mean, invstd, dy, ws, dmasked)
     Cc = y.shape[-1]
     P = y.numel() // Cc
-    check(lib().hk_bn_train_bwd(ptr(dout), ptr(out_mask), ptr(y), ptr(mean), ptr(invstd), ptr(gamma), C.c_longlong(P), Cc, ptr(dgamma),
+    bits = out_mask is not None and out_mask.dtype == torch.uint8   # bit array from bn_apply(relu_bits=...) instead of the bf16 output
+    check(lib().hk_bn_train_bwd(ptr(dout), ptr(out_mask), int(bits), ptr(y), ptr(mean), ptr(invstd), ptr(gamma), C.c_longlong(P), Cc, ptr(dgamma),
                                 ptr(dbeta), int(accumulate), ptr(dy), ptr(dmasked), ptr(ws), ws.numel(), stream_ptr()), "hk_bn_train_bwd")
     return dy
 

@@ -45,6 +45,7 @@ class _ConvT:
         self.zero_in = torch.zeros(self.cin, device=dev)
         self.y = torch.empty((B, self.Ho, self.Wo, self.cout), device=dev, dtype=bf)   # raw conv output (saved for BN backward)
         self.mean, self.invstd, self.scale, self.shift = (torch.empty(self.cout, device=dev) for _ in range(4))
+        self.relu_bits = torch.empty(self.y.numel() // 8, device=dev, dtype=torch.uint8)  # ReLU mask of the BN output, 1 bit / element
 
 
 class TrainEngine:
@@ -116,6 +117,8 @@ class TrainEngine:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_key = None
         self.use_cuda_graph = os.environ.get("HK_TRAIN_NO_GRAPH") is None   # eager launches for ncu launch lists
+        # ReLU masks of the backward pass as 1 bit / element written by the forward apply pass (HK_BN_BITS=0: re-read the bf16 outputs)
+        self.use_relu_bits = os.environ.get("HK_BN_BITS", "1") != "0"
         self.launches = 0
 
     # ------------------------------------------------------------------ helpers
@@ -165,11 +168,14 @@ class TrainEngine:
         bn = c.bn
         ops.bn_train_stats(c.y, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.momentum, bn.eps, c.mean, c.invstd,
                            c.scale, c.shift, self.bn_ws)
-        ops.bn_apply(c.y, c.scale, c.shift, relu=relu, residual=residual, out=out)
+        ops.bn_apply(c.y, c.scale, c.shift, relu=relu, residual=residual, out=out, relu_bits=c.relu_bits if relu and self.use_relu_bits else None)
+        c.relu_out = out if relu else None
         return 4
 
-    def _bn_bwd(self, c: _ConvT, dout, mask, dy, dmasked=None) -> int:
+    def _bn_bwd(self, c: _ConvT, dout, relu: bool, dy, dmasked=None) -> int:
+        """relu: the BN output went through a ReLU; its mask is c.relu_bits (written by the forward apply pass)."""
         bn = c.bn
+        mask = None if not relu else (c.relu_bits if self.use_relu_bits else c.relu_out)
         ops.bn_train_bwd(dout, mask, c.y, c.mean, c.invstd, bn.weight.data, self._g(bn.weight), self._g(bn.bias), dy, self.bn_ws,
                          dmasked=dmasked)
         return 3
@@ -206,7 +212,8 @@ class TrainEngine:
         bn = st.bn
         ops.bn_train_stats(st.y, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.momentum, bn.eps, st.mean, st.invstd,
                            st.scale, st.shift, self.bn_ws)
-        ops.bn_apply(st.y, st.scale, st.shift, relu=True, out=self.a0)
+        ops.bn_apply(st.y, st.scale, st.shift, relu=True, out=self.a0, relu_bits=st.relu_bits if self.use_relu_bits else None)
+        st.relu_out = self.a0
         ops.maxpool3x3s2(self.a0, out=self.p0)
         n += 5
         x = self.p0
@@ -260,17 +267,17 @@ class TrainEngine:
             x_in = self.blocks[bi - 1][5] if bi > 0 else self.p0
             dy2 = self._buf("dy", c2.y.shape)
             dm = self._buf("dm", c2.y.shape)
-            n += self._bn_bwd(c2, d, out, dy2, dmasked=dm)            # d' = d*[out>0] also feeds the shortcut
+            n += self._bn_bwd(c2, d, True, dy2, dmasked=dm)            # d' = d*[out>0] also feeds the shortcut
             n += self._wgrad(c2, a1, dy2)
             da1 = self._buf("da1", a1.shape)
             n += self._dgrad(c2, dy2, da1)
             dy1 = self._buf("dy", c1.y.shape)
-            n += self._bn_bwd(c1, da1, a1, dy1)
+            n += self._bn_bwd(c1, da1, True, dy1)
             n += self._wgrad(c1, x_in, dy1)
             dx = self._buf(f"d{parity}", x_in.shape)
             if ds is not None:
                 dyd = self._buf("dyd", ds.y.shape)
-                n += self._bn_bwd(ds, dm, None, dyd)
+                n += self._bn_bwd(ds, dm, False, dyd)
                 n += self._wgrad(ds, x_in, dyd)
                 dxd = self._buf("dxd", x_in.shape)
                 n += self._dgrad(ds, dyd, dxd)
@@ -288,7 +295,7 @@ class TrainEngine:
         da0 = self._buf("da0", self.a0.shape)
         ops.maxpool3x3s2_bwd(d, self.a0, dx=da0, idx_ws=self.pool_idx)
         dy0 = self._buf("dy", st.y.shape)
-        n += 2 + self._bn_bwd(st, da0, self.a0, dy0)
+        n += 2 + self._bn_bwd(st, da0, True, dy0)
         ops.stem_wgrad(self.x, dy0, self._g(net.conv1.weight), ws=self.wgrad_ws)
         n += 2
         return n

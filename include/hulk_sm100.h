@@ -184,14 +184,17 @@ HK_API size_t hk_bn_workspace_bytes(int C);
 HK_API int hk_bn_train_stats(const void* y, long long P, int C, const float* gamma, const float* beta, float* running_mean,
                              float* running_var, float momentum, float eps, float* mean_out, float* invstd_out,
                              float* scale_out, float* shift_out, void* ws, size_t ws_bytes, void* stream);
-/* out = relu?(y*scale + shift [+ residual])  (BN apply + the in-place add and ReLU of BasicBlock.forward, src/resnet.py:64-67) */
+/* out = relu?(y*scale + shift [+ residual])  (BN apply + the in-place add and ReLU of BasicBlock.forward, src/resnet.py:64-67).
+ * relu_bits_or_null (P*C/8 bytes, only written when relu != 0): bit j of byte v = [out[8v+j] > 0], the ReLU mask for hk_bn_train_bwd
+ * at 1/16 of the bytes of `out`. */
 HK_API int hk_bn_apply_fwd(const void* y, const float* scale, const float* shift, const void* residual_or_null, int relu,
-                           void* out, long long P, int C, void* stream);
-/* Backward of ReLU (mask from the saved post-ReLU output; NULL = no ReLU) + train-mode BatchNorm:
+                           void* out, void* relu_bits_or_null, long long P, int C, void* stream);
+/* Backward of ReLU (mask: the saved post-ReLU output (mask_is_bits = 0) or the bit array written by hk_bn_apply_fwd (mask_is_bits = 1);
+ * NULL = no ReLU) + train-mode BatchNorm:
  *   d' = dout*[out>0]; dbeta = sum d'; dgamma = sum d'*xhat; dy = gamma*invstd*(d' - dbeta/P - xhat*dgamma/P)
  *   dmasked_or_null receives d' (the gradient of the shortcut branch).  accumulate != 0 adds to dgamma/dbeta.
  *   ws: hk_bn_workspace_bytes(C) + 3*C*4 bytes. */
-HK_API int hk_bn_train_bwd(const void* dout, const void* out_mask_or_null, const void* y, const float* mean, const float* invstd,
+HK_API int hk_bn_train_bwd(const void* dout, const void* out_mask_or_null, int mask_is_bits, const void* y, const float* mean, const float* invstd,
                            const float* gamma, long long P, int C, float* dgamma, float* dbeta, int accumulate, void* dy,
                            void* dmasked_or_null, void* ws, size_t ws_bytes, void* stream);
 

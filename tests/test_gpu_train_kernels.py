@@ -72,10 +72,18 @@ def test_bn_train_backward_matches_autograd(C_, with_relu):
     mean, invstd, scale, shift = (torch.empty(C_, device=DEV) for _ in range(4))
     ws = ops.bn_workspace(C_, DEV)
     ops.bn_train_stats(y, gamma, beta, None, None, 0.1, 1e-5, mean, invstd, scale, shift, ws)
-    out = ops.bn_apply(y, scale, shift, relu=with_relu, residual=res)
+    bits = torch.zeros(y.numel() // 8, device=DEV, dtype=torch.uint8)
+    out = ops.bn_apply(y, scale, shift, relu=with_relu, residual=res, relu_bits=bits)
     dgamma, dbeta = torch.empty(C_, device=DEV), torch.empty(C_, device=DEV)
     dy, dmasked = torch.empty_like(y), torch.empty_like(y)
     ops.bn_train_bwd(dout, out if with_relu else None, y, mean, invstd, gamma, dgamma, dbeta, dy, ws, dmasked=dmasked)
+    if with_relu:
+        # the 1-bit-per-element ReLU mask written by the forward apply pass == [out > 0], and the backward fed with it is bit-identical
+        expect = ((out.reshape(-1, 8) > 0).to(torch.int32) << torch.arange(8, device=DEV, dtype=torch.int32)).sum(1).to(torch.uint8)
+        assert torch.equal(bits, expect)
+        dg2, db2, dy2, dm2 = torch.empty_like(dgamma), torch.empty_like(dbeta), torch.empty_like(y), torch.empty_like(y)
+        ops.bn_train_bwd(dout, bits, y, mean, invstd, gamma, dg2, db2, dy2, ws, dmasked=dm2)
+        assert torch.equal(dy2, dy) and torch.equal(dm2, dmasked) and torch.equal(dg2, dgamma) and torch.equal(db2, dbeta)
     # autograd on the same operands; the ReLU mask is taken from OUR post-ReLU output (what the next layer saw)
     y32 = nchw(y.float()).requires_grad_(True)
     g32, b32 = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
