@@ -75,8 +75,10 @@ def load_peaks():
 
 
 def conv_flops_per_image(h, w, k):
-    from oracle.keypoints_oracle import conv_flops_per_image as f  # checker-side arithmetic only
-    return f(h, w, k)
+    """Algorithmic conv FLOPs per image from the product package's own module graph (no oracle on the product arm)."""
+    import hulk_keypoints_b200 as hk
+    from hulk_keypoints_b200.engine import conv_flops_per_image as f
+    return f(hk.KeypointsGauss(k, img_height=h, img_width=w), h, w)
 
 
 # --------------------------------------------------------------------------------------------- clocks
@@ -255,7 +257,7 @@ def per_launch_breakdown(engine, plan, decode=True):
             a.record(stream); fn(); b.record(stream); b.synchronize()
             t = a.elapsed_time(b)
             best = t if best is None else min(best, t)
-        rows.append({"name": name, "ms": best, "flops": flops, "algo": None})
+        rows.append({"name": name, "ms": best, "flops": flops, "algo": None, "bytes": 0.0})
 
     B = plan.B
     if engine._stem_w_tc is not None:
@@ -266,7 +268,9 @@ def per_launch_breakdown(engine, plan, decode=True):
               lambda: engine._conv(P["stem"], plan.x, plan.stem, relu=True, in_is_nchw=True))
     cur = 0
     x = plan.view(cur, plan.h4, plan.w4, 64)
+    rows[-1]["bytes"] = B * (3.0 * plan.H * plan.W * (1 if plan.input_is_u8 else 4) + plan.h2 * plan.w2 * 64 * 2)   # input read + bf16 output write
     timed("maxpool", 0.0, lambda: ops.maxpool3x3s2(plan.stem, out=x))
+    rows[-1]["bytes"] = B * 64.0 * 2 * (plan.h2 * plan.w2 + plan.h4 * plan.w4)
     h, w = plan.h4, plan.w4
     for i, blk in enumerate(net.blocks()):
         c1, c2 = P[f"b{i}.c1"], P[f"b{i}.c2"]
@@ -290,8 +294,10 @@ def per_launch_breakdown(engine, plan, decode=True):
     xf = x
     timed("head", 2.0 * B * h * w * engine.K * 512,
           lambda: ops.head(xf, engine._fc_w, engine._fc_b, plan.H, plan.W, heat=plan.heat, logits_ws=plan.logits))
+    rows[-1]["bytes"] = B * (512.0 * h * w * 2 + engine.K * plan.H * plan.W * 4.0)   # bf16 features read + fp32 heatmaps written
     if decode:
         timed("decode", 0.0, lambda: ops.argmax_decode(plan.heat, yx=plan.yx, maxval=plan.maxval, ws=plan.argmax_ws, want_max=True))
+        rows[-1]["bytes"] = B * engine.K * plan.H * plan.W * 4.0
     return rows
 
 
@@ -420,7 +426,7 @@ def run_ours(args, rank, world, local_rank):
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all launches of one step)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": ncu_conv_traffic_per_step(B, H, W, K_KEYPOINTS, args.precision),
-                "traffic_note": "DRAM bytes read+written by the 35 conv launches of one step (ncu, profiles/r01c_step_per_launch_dram.json); "
+                "traffic_note": "DRAM bytes read+written by the 35 conv launches of one step (ncu, profiles/r01d_step_per_launch_dram.json); "
                                 "algorithmic activation traffic of those launches: in+out+residual of every conv",
                 "peak_source": f"{peaks['source']} burst bf16 ({peak}); sustained {peaks['bf16_tflops_sustained']}",
                 "launches": len(tc), "ms_in_step": tc_ms, "share_of_step": tc_ms / sum(r["ms"] for r in rows)}
@@ -429,6 +435,10 @@ def run_ours(args, rank, world, local_rank):
         f, ms = sum(r["flops"] for r in ff), sum(r["ms"] for r in ff)
         roof = {"bound": "tensor", "kernel": "conv_ffma_kernel (fp32 correctness mode, CUDA cores)", "achieved": f / (ms * 1e-3) / 1e12,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": f / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "traffic": None}
+    # the HBM-bound kernels of the step against the measured copy bandwidth (informational; the headline roofline is the conv one)
+    hbm_rows = [{"kernel": r["name"], "bound": "hbm", "achieved": r["bytes"] / (r["ms"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                 "frac": r["bytes"] / (r["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": r["bytes"], "ms": r["ms"]}
+                for r in rows if r.get("bytes", 0) > 0]
     if args.breakdown and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.breakdown)), exist_ok=True)
         with open(args.breakdown, "w") as f:
@@ -457,6 +467,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": launches_per_step * args.steps * (3 if e2e_u8 else 2),  # timed regions: device-resident loop + e2e loop(s)
         "gpu_launches_per_step": launches_per_step,
         "roofline": roof,
+        "roofline_hbm_kernels": hbm_rows,
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world >= 1:
@@ -472,11 +483,11 @@ def run_ours(args, rank, world, local_rank):
 
 def ncu_conv_traffic_per_step(B, H, W, K, precision):
     """DRAM bytes (read + write) of the 35 tcgen05 conv launches of one step from the committed ncu capture
-    (profiles/r01c_step_per_launch_dram.json: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over bench.py's default
+    (profiles/r01d_step_per_launch_dram.json: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over bench.py's default
     workload).  None for any other workload."""
     if (B, H, W, K, precision) != (64, 480, 640, 4, "bf16"):
         return None
-    p = os.path.join(ROOT, "profiles", "r01c_step_per_launch_dram.json")
+    p = os.path.join(ROOT, "profiles", "r01d_step_per_launch_dram.json")
     if not os.path.exists(p):
         return None
     with open(p) as f:

@@ -25,6 +25,27 @@ from ._lib import HK_CONV_FFMA, HK_CONV_TCGEN05, require_device
 BN_EPS_DEFAULT = 1e-5
 
 
+def conv_flops_per_image(model, height: int, width: int) -> float:
+    """Algorithmic conv FLOPs of one image through `model` (2*M*N*K over the stem, the 16 BasicBlocks incl. their 1x1 downsamples, and
+    the K live rows of the scoring conv): 211.91 GFLOP at 480x640, K=4 -- the figure bench.py's roofline uses."""
+    net = model.resnet.resnet34_8s
+
+    def conv(c, h, w):
+        ho, wo = ops.conv_out_hw(h, w, c.kernel_size[0], c.stride[0], c.padding[0], c.dilation[0])
+        return 2.0 * ho * wo * c.out_channels * c.in_channels * c.kernel_size[0] * c.kernel_size[1], ho, wo
+
+    total, h, w = conv(net.conv1, height, width)
+    h, w = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+    for blk in net.blocks():
+        f1, ho, wo = conv(blk.conv1, h, w)
+        f2, _, _ = conv(blk.conv2, ho, wo)
+        total += f1 + f2
+        if blk.downsample is not None:
+            total += conv(blk.downsample[0], h, w)[0]
+        h, w = ho, wo
+    return total + 2.0 * h * w * int(model.num_keypoints) * net.fc.in_channels
+
+
 class _PackedConv:
     __slots__ = ("w", "scale", "bias", "stride", "pad", "dil", "algo")
 

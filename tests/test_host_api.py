@@ -195,3 +195,12 @@ def test_checkpoint_roundtrip_and_pretrained_import(tmp_path):
     bad.pop("bn1.weight")
     with pytest.raises(KeyError):
         checkpoint.load_pretrained_backbone(m2, bad)
+
+
+def test_conv_flops_per_image_matches_oracle_and_survey():
+    """The FLOP count bench.py's roofline uses (product package) == the oracle's network spec == SURVEY §8d's 211.91 GF."""
+    from hulk_keypoints_b200.engine import conv_flops_per_image
+    from oracle import keypoints_oracle as O
+    for (h, w, k) in ((480, 640, 4), (960, 1280, 16), (64, 96, 7)):
+        assert conv_flops_per_image(hk.KeypointsGauss(k, img_height=h, img_width=w), h, w) == O.conv_flops_per_image(h, w, k)
+    assert abs(conv_flops_per_image(hk.KeypointsGauss(4), 480, 640) / 1e9 - 211.91) < 0.01
