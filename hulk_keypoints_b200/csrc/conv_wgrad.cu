@@ -87,7 +87,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int total_units = a.ksplit * a.taps * a.m_tiles * a.n_tiles;
 
-  ptx::griddep_launch_dependents();  // launched with programmatic serialization: see launch_pdl (hk_common.cuh)
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_dy);
     ptx::prefetch_tensormap(&map_x);
@@ -114,7 +113,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp waits, one elected lane issues) =====================
-    ptx::griddep_wait();  // dY / X are complete and visible
     uint32_t stage = 0, phase = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       int ks, tap, m, n;
@@ -175,7 +173,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     // ===================== epilogue: TMEM -> fp32 partial tile in the workspace =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;  // accumulator row = output channel within the 128-row tile
-    ptx::griddep_wait();  // the previous kernel may still be reading the partial workspace
     uint32_t it = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -217,8 +214,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
 // measured 0.25-0.35 ms per step SLOWER (fewer loads in flight per SM) and dropped.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ksplit, int Cout, int taps,
                                                           int Cin, int accumulate) {
-  ptx::griddep_wait();
-  ptx::griddep_launch_dependents();
   const long long total = (long long)Cout * taps * Cin;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -272,7 +267,7 @@ static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const Wgr
   const int total = a.ksplit * a.taps * a.m_tiles * a.n_tiles;
   int grid = sm_count();
   if (grid > total) grid = total;
-  launch_pdl(conv_wgrad_kernel<BLOCK_N>, dim3(grid), dim3(WG_THREADS), (size_t)Cfg::SMEM_BYTES, s, mdy, mx, a);
+  conv_wgrad_kernel<BLOCK_N><<<grid, WG_THREADS, Cfg::SMEM_BYTES, s>>>(mdy, mx, a);
   return check_launch("conv_wgrad_kernel");
 }
 
@@ -341,7 +336,7 @@ int hk_conv_wgrad(const HkConvDesc* desc, const void* x, const void* dy, float* 
   const long long total = (long long)d.out_c * p.taps * d.in_c;
   int blocks = (int)ceil_div_ll(total, 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  launch_pdl(wgrad_reduce_kernel, dim3(blocks), dim3(256), (size_t)0, s, a.ws, dw_oihw, p.ksplit, d.out_c, p.taps, d.in_c, accumulate);
+  wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(a.ws, dw_oihw, p.ksplit, d.out_c, p.taps, d.in_c, accumulate);
   return check_launch("wgrad_reduce_kernel");
 }
 

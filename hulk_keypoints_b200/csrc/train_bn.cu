@@ -9,18 +9,8 @@
 // All four kernels are HBM-bound streaming passes (16-byte vectors of 8 bf16 channels); the reductions are two-level
 // (fixed grid of per-block fp32 partials, then a double-precision finalize) and therefore deterministic -- no atomics.
 #include "hk_common.cuh"
-#include "hk_ptx.cuh"
 
 namespace hk {
-
-// Every kernel of this file is launched with programmatic stream serialization (launch_pdl): its blocks may become resident while the
-// previous kernel drains, so the first statement waits for that kernel's results; the trigger right after lets the NEXT kernel do the
-// same.  (A train step is ~380 short launches: at per-GPU batch 4 the launch/drain gaps are a tenth of the step.)
-#define HK_PDL_PROLOGUE()        \
-  do {                           \
-    ptx::griddep_wait();         \
-    ptx::griddep_launch_dependents(); \
-  } while (0)
 
 constexpr int BN_THREADS = 256;
 constexpr int BN_MAX_BLOCKS = 592;  // 148 SMs x 4
@@ -63,7 +53,6 @@ __device__ __forceinline__ void block_reduce_2x8(const float (&a)[8], const floa
 // ---- forward statistics ----
 __global__ void __launch_bounds__(BN_THREADS) bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ y, long long P, int C,
                                                                      float* __restrict__ partial) {
-  HK_PDL_PROLOGUE();
   const int CG = C >> 3, cg = threadIdx.x % CG, ty = threadIdx.x / CG, rows = BN_THREADS / CG;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (long long r = (long long)blockIdx.x * rows + ty; r < P; r += (long long)gridDim.x * rows) {
@@ -114,7 +103,6 @@ __global__ void __launch_bounds__(BN_FIN_THREADS) bn_stats_finalize_kernel(const
                                          const float* __restrict__ beta, float* __restrict__ running_mean,
                                          float* __restrict__ running_var, float momentum, float eps, float* __restrict__ mean_out,
                                          float* __restrict__ invstd_out, float* __restrict__ scale_out, float* __restrict__ shift_out) {
-  HK_PDL_PROLOGUE();
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double s, q;
   bn_sum_partials(partial, nblocks, C, c, s, q);
@@ -142,7 +130,6 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_fwd_kernel(const __nv_bfl
                                                                  const __nv_bfloat16* __restrict__ residual, int relu,
                                                                  __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ relu_bits,
                                                                  long long nvec, int C) {
-  HK_PDL_PROLOGUE();
   // the grid stride (gridDim*256) is a multiple of C/8, so a thread keeps its 8 channels: coefficients live in registers
   const int cg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % (C >> 3));
   float sc[8], sh[8];
@@ -179,7 +166,6 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_partial_kernel(const __nv_b
                                                                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                                                                    const float* __restrict__ invstd, long long P, int C,
                                                                    float* __restrict__ partial) {
-  HK_PDL_PROLOGUE();
   const int CG = C >> 3, cg = threadIdx.x % CG, ty = threadIdx.x / CG, rows = BN_THREADS / CG;
   float mu[8], is[8];
 #pragma unroll
@@ -214,7 +200,6 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_partial_kernel(const __nv_b
 __global__ void __launch_bounds__(BN_FIN_THREADS) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, long long P, int C, const float* __restrict__ gamma,
                                        const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        int accumulate, float* __restrict__ coef) {
-  HK_PDL_PROLOGUE();
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double s1, s2;
   bn_sum_partials(partial, nblocks, C, c, s1, s2);
@@ -236,7 +221,6 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const __nv_bfl
                                                                  const float* __restrict__ invstd, const float* __restrict__ coef,
                                                                  __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dmasked,
                                                                  long long nvec, int C) {
-  HK_PDL_PROLOGUE();
   const int c0 = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % (C >> 3)) * 8;
   float k0[8], k1[8], k2[8];
 #pragma unroll
@@ -299,10 +283,10 @@ int hk_bn_train_stats(const void* y, long long P, int C, const float* gamma, con
   HK_REQUIRE(ws_bytes >= hk_bn_workspace_bytes(C), "hk_bn_train_stats: workspace too small");
   HK_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, "hk_bn_train_stats: y must be 16-byte aligned");
   const int blocks = bn_grid_rows(P, C);
-  launch_pdl(bn_stats_partial_kernel, dim3(blocks), dim3(BN_THREADS), (size_t)(0), as_stream(stream), static_cast<const __nv_bfloat16*>(y), P, C, static_cast<float*>(ws));
+  bn_stats_partial_kernel<<<blocks, BN_THREADS, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y), P, C, static_cast<float*>(ws));
   int rc = check_launch("bn_stats_partial_kernel");
   if (rc) return rc;
-  launch_pdl(bn_stats_finalize_kernel, dim3(ceil_div(C, 32)), dim3(BN_FIN_THREADS), (size_t)(0), as_stream(stream), static_cast<const float*>(ws), blocks, P, C, gamma, beta,
+  bn_stats_finalize_kernel<<<ceil_div(C, 32), BN_FIN_THREADS, 0, as_stream(stream)>>>(static_cast<const float*>(ws), blocks, P, C, gamma, beta,
                                                                            running_mean, running_var, momentum, eps, mean_out,
                                                                            invstd_out, scale_out, shift_out);
   return check_launch("bn_stats_finalize_kernel");
@@ -314,7 +298,7 @@ int hk_bn_apply_fwd(const void* y, const float* scale, const float* shift, const
   HK_REQUIRE(y && scale && shift && out, "hk_bn_apply_fwd: null pointer");
   HK_REQUIRE(P > 0 && C >= 8 && (C & 7) == 0, "hk_bn_apply_fwd: bad shape");
   const long long nvec = P * (C >> 3);
-  launch_pdl(bn_apply_fwd_kernel, dim3(bn_grid_elems(nvec)), dim3(BN_THREADS), (size_t)(0), as_stream(stream), 
+  bn_apply_fwd_kernel<<<bn_grid_elems(nvec), BN_THREADS, 0, as_stream(stream)>>>(
       static_cast<const __nv_bfloat16*>(y), scale, shift, static_cast<const __nv_bfloat16*>(residual_or_null), relu,
       static_cast<__nv_bfloat16*>(out), static_cast<uint8_t*>(relu_bits_or_null), nvec, C);
   return check_launch("bn_apply_fwd_kernel");
@@ -333,19 +317,19 @@ int hk_bn_train_bwd(const void* dout, const void* out_mask_or_null, int mask_is_
   const __nv_bfloat16* d = static_cast<const __nv_bfloat16*>(dout);
   const void* m = out_mask_or_null;
   const __nv_bfloat16* yy = static_cast<const __nv_bfloat16*>(y);
-  if (mask_is_bits) launch_pdl(bn_bwd_partial_kernel<true>, dim3(blocks), dim3(BN_THREADS), (size_t)(0), as_stream(stream), d, m, yy, mean, invstd, P, C, partial);
-  else launch_pdl(bn_bwd_partial_kernel<false>, dim3(blocks), dim3(BN_THREADS), (size_t)(0), as_stream(stream), d, m, yy, mean, invstd, P, C, partial);
+  if (mask_is_bits) bn_bwd_partial_kernel<true><<<blocks, BN_THREADS, 0, as_stream(stream)>>>(d, m, yy, mean, invstd, P, C, partial);
+  else bn_bwd_partial_kernel<false><<<blocks, BN_THREADS, 0, as_stream(stream)>>>(d, m, yy, mean, invstd, P, C, partial);
   int rc = check_launch("bn_bwd_partial_kernel");
   if (rc) return rc;
-  launch_pdl(bn_bwd_finalize_kernel, dim3(ceil_div(C, 32)), dim3(BN_FIN_THREADS), (size_t)(0), as_stream(stream), partial, blocks, P, C, gamma, invstd, dgamma, dbeta, accumulate, coef);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 32), BN_FIN_THREADS, 0, as_stream(stream)>>>(partial, blocks, P, C, gamma, invstd, dgamma, dbeta, accumulate, coef);
   rc = check_launch("bn_bwd_finalize_kernel");
   if (rc) return rc;
   const long long nvec = P * (C >> 3);
   if (mask_is_bits)
-    launch_pdl(bn_bwd_apply_kernel<true>, dim3(bn_grid_elems(nvec)), dim3(BN_THREADS), (size_t)(0), as_stream(stream), d, m, yy, mean, invstd, coef, static_cast<__nv_bfloat16*>(dy),
+    bn_bwd_apply_kernel<true><<<bn_grid_elems(nvec), BN_THREADS, 0, as_stream(stream)>>>(d, m, yy, mean, invstd, coef, static_cast<__nv_bfloat16*>(dy),
                                                                                        static_cast<__nv_bfloat16*>(dmasked_or_null), nvec, C);
   else
-    launch_pdl(bn_bwd_apply_kernel<false>, dim3(bn_grid_elems(nvec)), dim3(BN_THREADS), (size_t)(0), as_stream(stream), d, m, yy, mean, invstd, coef, static_cast<__nv_bfloat16*>(dy),
+    bn_bwd_apply_kernel<false><<<bn_grid_elems(nvec), BN_THREADS, 0, as_stream(stream)>>>(d, m, yy, mean, invstd, coef, static_cast<__nv_bfloat16*>(dy),
                                                                                         static_cast<__nv_bfloat16*>(dmasked_or_null), nvec, C);
   return check_launch("bn_bwd_apply_kernel");
 }
