@@ -119,6 +119,10 @@ class TrainEngine:
         self.use_cuda_graph = os.environ.get("HK_TRAIN_NO_GRAPH") is None   # eager launches for ncu launch lists
         # ReLU masks of the backward pass as 1 bit / element written by the forward apply pass (HK_BN_BITS=0: re-read the bf16 outputs)
         self.use_relu_bits = os.environ.get("HK_BN_BITS", "1") != "0"
+        # Weight gradients are leaves of the backward chain (bn_bwd -> dgrad -> bn_bwd ...): they run on a second stream inside the same
+        # graph, concurrently with the data-gradient chain (each conv then keeps its own dy buffer).  Measured on one box: per-GPU batch 4
+        # 5.74 -> 5.37 ms per step, batch 32 25.40 -> 24.53 ms.  HK_WGRAD_STREAM=0 keeps everything on one stream.
+        self.wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("HK_WGRAD_STREAM", "1") != "0" else None
         self.launches = 0
 
     # ------------------------------------------------------------------ helpers
@@ -180,8 +184,36 @@ class TrainEngine:
                          dmasked=dmasked)
         return 3
 
+    def _dy_buf(self, c: _ConvT, role: str = "dy") -> torch.Tensor:
+        """dL/d(raw conv output) of conv c: shared scratch per shape, or (wgrads on their own stream) one buffer per conv, because the
+        weight gradient may still be reading it while the data-gradient chain has moved on."""
+        if self.wgrad_stream is None:
+            return self._buf(role, c.y.shape)
+        if getattr(c, "dy", None) is None:
+            c.dy = torch.empty_like(c.y)
+        return c.dy
+
+    def _on_wgrad_stream(self, fn) -> None:
+        if self.wgrad_stream is None:
+            fn()
+            return
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())      # dy (just written on the main stream) is complete
+        self.wgrad_stream.wait_event(ready)
+        with torch.cuda.stream(self.wgrad_stream):
+            fn()
+        self._wgrad_pending = True
+
+    def _join_wgrad_stream(self) -> None:
+        if self.wgrad_stream is not None and getattr(self, "_wgrad_pending", False):
+            done = torch.cuda.Event()
+            done.record(self.wgrad_stream)
+            torch.cuda.current_stream().wait_event(done)
+            self._wgrad_pending = False
+
     def _wgrad(self, c: _ConvT, x, dy) -> int:
-        ops.conv_wgrad(x, dy, self._g(c.conv.weight), k=c.k, stride=c.stride, pad=c.pad, dil=c.dil, ws=self.wgrad_ws)
+        self._on_wgrad_stream(lambda: ops.conv_wgrad(x, dy, self._g(c.conv.weight), k=c.k, stride=c.stride, pad=c.pad, dil=c.dil,
+                                                     ws=self.wgrad_ws))
         return 2
 
     def _dgrad(self, c: _ConvT, dy, dx, residual=None) -> int:
@@ -265,18 +297,18 @@ class TrainEngine:
         for bi in range(hi - 1, lo - 1, -1):
             c1, c2, ds, a1, sc, out = self.blocks[bi]
             x_in = self.blocks[bi - 1][5] if bi > 0 else self.p0
-            dy2 = self._buf("dy", c2.y.shape)
+            dy2 = self._dy_buf(c2)
             dm = self._buf("dm", c2.y.shape)
             n += self._bn_bwd(c2, d, True, dy2, dmasked=dm)            # d' = d*[out>0] also feeds the shortcut
             n += self._wgrad(c2, a1, dy2)
             da1 = self._buf("da1", a1.shape)
             n += self._dgrad(c2, dy2, da1)
-            dy1 = self._buf("dy", c1.y.shape)
+            dy1 = self._dy_buf(c1)
             n += self._bn_bwd(c1, da1, True, dy1)
             n += self._wgrad(c1, x_in, dy1)
             dx = self._buf(f"d{parity}", x_in.shape)
             if ds is not None:
-                dyd = self._buf("dyd", ds.y.shape)
+                dyd = self._dy_buf(ds, "dyd")
                 n += self._bn_bwd(ds, dm, False, dyd)
                 n += self._wgrad(ds, x_in, dyd)
                 dxd = self._buf("dxd", x_in.shape)
@@ -291,12 +323,14 @@ class TrainEngine:
             dh = self._buf("dh", d.shape)
             dh.copy_(d)
             self._bwd_state = (dh, parity, lo)
+            self._join_wgrad_stream()
             return n + 1
         da0 = self._buf("da0", self.a0.shape)
         ops.maxpool3x3s2_bwd(d, self.a0, dx=da0, idx_ws=self.pool_idx)
-        dy0 = self._buf("dy", st.y.shape)
+        dy0 = self._dy_buf(st)
         n += 2 + self._bn_bwd(st, da0, True, dy0)
-        ops.stem_wgrad(self.x, dy0, self._g(net.conv1.weight), ws=self.wgrad_ws)
+        self._on_wgrad_stream(lambda: ops.stem_wgrad(self.x, dy0, self._g(net.conv1.weight), ws=self.wgrad_ws))
+        self._join_wgrad_stream()
         n += 2
         return n
 
