@@ -237,7 +237,8 @@ class TrainEngine:
         n = 0
         # weights of this step (parameters change every optimizer step)
         check(lib().hk_stem_pack_weights(ptr(net.conv1.weight.data), ptr(self.stem_w), stream_ptr()), "hk_stem_pack_weights")
-        n += 1 + self._pack_all()
+        self._on_wgrad_stream(self._pack_all)   # the block convs' weights are repacked while the stem, its BN and the maxpool run
+        n += 2
         # ---------------- forward (train mode) ----------------
         st = self.stem
         ops.stem_conv(self.x, self.stem_w, st.one_out, st.zero_out, relu=False, out=st.y)
@@ -247,6 +248,7 @@ class TrainEngine:
         ops.bn_apply(st.y, st.scale, st.shift, relu=True, out=self.a0, relu_bits=st.relu_bits if self.use_relu_bits else None)
         st.relu_out = self.a0
         ops.maxpool3x3s2(self.a0, out=self.p0)
+        self._join_wgrad_stream()               # packed weights ready
         n += 5
         x = self.p0
         for (c1, c2, ds, a1, sc, out) in self.blocks:
