@@ -123,6 +123,10 @@ class TrainEngine:
         # graph, concurrently with the data-gradient chain (each conv then keeps its own dy buffer).  Measured on one box: per-GPU batch 4
         # 5.74 -> 5.37 ms per step, batch 32 25.40 -> 24.53 ms.  HK_WGRAD_STREAM=0 keeps everything on one stream.
         self.wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("HK_WGRAD_STREAM", "1") != "0" else None
+        # The 1x1 downsample branch of the three stride/channel-changing blocks (conv + BN forward; BN backward + dgrad) is independent
+        # of the block's main branch until the residual add: it runs on a third stream with its own BN workspace (HK_AUX_STREAM=0: off).
+        self.aux_stream = torch.cuda.Stream(device=dev) if os.environ.get("HK_AUX_STREAM", "1") != "0" else None
+        self.bn_ws_aux = ops.bn_workspace(512, dev) if self.aux_stream is not None else None
         self.launches = 0
 
     # ------------------------------------------------------------------ helpers
@@ -166,22 +170,37 @@ class TrainEngine:
             n += 1
         return n
 
-    def _conv_bn(self, c: _ConvT, x, out, relu: bool, residual=None) -> int:
+    def _conv_bn(self, c: _ConvT, x, out, relu: bool, residual=None, ws=None) -> int:
         """raw conv -> batch statistics (+ running stats) -> fused normalise (+ shortcut) (+ ReLU)."""
         ops.conv_bn_act(x, c.w_fwd, c.one_out, c.zero_out, stride=c.stride, pad=c.pad, dil=c.dil, relu=False, out=c.y)
         bn = c.bn
         ops.bn_train_stats(c.y, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.momentum, bn.eps, c.mean, c.invstd,
-                           c.scale, c.shift, self.bn_ws)
+                           c.scale, c.shift, self.bn_ws if ws is None else ws)
         ops.bn_apply(c.y, c.scale, c.shift, relu=relu, residual=residual, out=out, relu_bits=c.relu_bits if relu and self.use_relu_bits else None)
         c.relu_out = out if relu else None
         return 4
 
-    def _bn_bwd(self, c: _ConvT, dout, relu: bool, dy, dmasked=None) -> int:
+    def _fork_aux(self):
+        """aux stream waits for everything enqueued on the current stream so far; returns the stream (None: stay on the current one)."""
+        if self.aux_stream is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.aux_stream.wait_event(ev)
+        return self.aux_stream
+
+    def _join_aux(self) -> None:
+        if self.aux_stream is not None:
+            ev = torch.cuda.Event()
+            ev.record(self.aux_stream)
+            torch.cuda.current_stream().wait_event(ev)
+
+    def _bn_bwd(self, c: _ConvT, dout, relu: bool, dy, dmasked=None, ws=None) -> int:
         """relu: the BN output went through a ReLU; its mask is c.relu_bits (written by the forward apply pass)."""
         bn = c.bn
         mask = None if not relu else (c.relu_bits if self.use_relu_bits else c.relu_out)
-        ops.bn_train_bwd(dout, mask, c.y, c.mean, c.invstd, bn.weight.data, self._g(bn.weight), self._g(bn.bias), dy, self.bn_ws,
-                         dmasked=dmasked)
+        ops.bn_train_bwd(dout, mask, c.y, c.mean, c.invstd, bn.weight.data, self._g(bn.weight), self._g(bn.bias), dy,
+                         self.bn_ws if ws is None else ws, dmasked=dmasked)
         return 3
 
     def _dy_buf(self, c: _ConvT, role: str = "dy") -> torch.Tensor:
@@ -216,11 +235,11 @@ class TrainEngine:
                                                      ws=self.wgrad_ws))
         return 2
 
-    def _dgrad(self, c: _ConvT, dy, dx, residual=None) -> int:
+    def _dgrad(self, c: _ConvT, dy, dx, residual=None, scratch: str = "up") -> int:
         """dx = conv_transpose(dy, W) (+ residual) through the forward kernel on the flipped weights."""
         n = 1
         if c.stride == 2:
-            up = self._buf("up", (self.B, c.H, c.W, c.cout))
+            up = self._buf(scratch, (self.B, c.H, c.W, c.cout))
             ops.zero_insert2x(dy, out=up)
             dy, n = up, 2
         ops.conv_bn_act(dy, c.w_dgrad, c.one_in, c.zero_in, stride=1, pad=c.dil * (c.k - 1) - c.pad, dil=c.dil, relu=False,
@@ -252,11 +271,19 @@ class TrainEngine:
         n += 5
         x = self.p0
         for (c1, c2, ds, a1, sc, out) in self.blocks:
-            n += self._conv_bn(c1, x, a1, relu=True)
             if ds is not None:
-                n += self._conv_bn(ds, x, sc, relu=False)
+                aux = self._fork_aux()
+                if aux is not None:
+                    with torch.cuda.stream(aux):
+                        n += self._conv_bn(ds, x, sc, relu=False, ws=self.bn_ws_aux)
+                    n += self._conv_bn(c1, x, a1, relu=True)
+                    self._join_aux()
+                else:
+                    n += self._conv_bn(c1, x, a1, relu=True)
+                    n += self._conv_bn(ds, x, sc, relu=False)
                 shortcut = sc
             else:
+                n += self._conv_bn(c1, x, a1, relu=True)
                 shortcut = x
             n += self._conv_bn(c2, a1, out, relu=True, residual=shortcut)
             x = out
@@ -302,6 +329,15 @@ class TrainEngine:
             dy2 = self._dy_buf(c2)
             dm = self._buf("dm", c2.y.shape)
             n += self._bn_bwd(c2, d, True, dy2, dmasked=dm)            # d' = d*[out>0] also feeds the shortcut
+            dxd = None
+            if ds is not None:                                          # shortcut branch: needs only d'; joins at the residual add
+                dyd = self._dy_buf(ds, "dyd")
+                dxd = self._buf("dxd", x_in.shape)
+                aux = self._fork_aux()
+                with torch.cuda.stream(aux if aux is not None else torch.cuda.current_stream()):
+                    n += self._bn_bwd(ds, dm, False, dyd, ws=self.bn_ws_aux)
+                    n += self._wgrad(ds, x_in, dyd)
+                    n += self._dgrad(ds, dyd, dxd, scratch="up_aux")
             n += self._wgrad(c2, a1, dy2)
             da1 = self._buf("da1", a1.shape)
             n += self._dgrad(c2, dy2, da1)
@@ -310,11 +346,7 @@ class TrainEngine:
             n += self._wgrad(c1, x_in, dy1)
             dx = self._buf(f"d{parity}", x_in.shape)
             if ds is not None:
-                dyd = self._dy_buf(ds, "dyd")
-                n += self._bn_bwd(ds, dm, False, dyd)
-                n += self._wgrad(ds, x_in, dyd)
-                dxd = self._buf("dxd", x_in.shape)
-                n += self._dgrad(ds, dyd, dxd)
+                self._join_aux()
                 n += self._dgrad(c1, dy1, dx, residual=dxd)
             else:
                 n += self._dgrad(c1, dy1, dx, residual=dm)
