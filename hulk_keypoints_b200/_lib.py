@@ -12,7 +12,8 @@ import threading
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libhulk_sm100.so")
+# HK_LIB_PATH: another build of the same library (A/B runs of kernel changes on one GPU box)
+LIB_PATH = os.environ.get("HK_LIB_PATH") or os.path.join(_PKG_DIR, "libhulk_sm100.so")
 
 # enums of include/hulk_sm100.h
 HK_F32, HK_BF16, HK_F64 = 0, 1, 2

@@ -32,7 +32,8 @@ namespace hk {
 constexpr int T2_BOX_H = 4, T2_BOX_W = 16;
 constexpr int T2_BOX_BYTES = 64 * 128;   // 8 KB: 64 pixels x 64 ch bf16
 constexpr int T2_A_BYTES = 2 * T2_BOX_BYTES;  // 128 rows per CTA
-constexpr int T2_THREADS = 256;
+constexpr int T2_THREADS = 384;      // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare; warps 4-11: epilogue
+constexpr int T2_EPI_THREADS = 256;
 
 struct ConvTc2Args {
   const float* scale;
@@ -114,7 +115,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
-      ptx::mbar_init(&tmem_empty_bar[i], 256);
+      ptx::mbar_init(&tmem_empty_bar[i], 2 * T2_EPI_THREADS);  // both CTAs' epilogue threads
     }
     for (int i = 0; i < 3; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_mbar_init();
@@ -199,8 +200,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       if (it >= 2) { const uint32_t j = it - 2; ptx::mbar_wait(&tmem_empty_bar[j & 1], (j >> 1) & 1, 35); }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (both CTAs, own 128 TMEM lanes; 128 threads, named barrier 1) =====================
-    const int q = warp & 3;
+    // ===================== epilogue (both CTAs, own 128 TMEM lanes; 8 warps = 256 threads, named barrier 1) =====================
+    // warp % 4 = TMEM lane quarter (32 rows), (warp - 4) / 4 = which 32 of a chunk's 64 columns: with 4 warps the drain of a 256-column
+    // tile took ~6k clocks, which capped the output-heavy 1x1 downsample convs (K = 64..256) at ~3 TB/s of stores
+    const int q = warp & 3, half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const bool elected = (warp == 4 && lane == 0);
     const int sw = row & 7;
@@ -249,11 +252,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           ptx::bulk_wait_group_read1();
           if (has_res && chunk + 1 < CHUNKS) issue_residual(chunk + 1, chunk_ctr + 1);  // one chunk ahead
         }
-        ptx::named_bar_sync(1, 128);  // staging[bsel] is free for everybody (elected passed its wait_group)
+        ptx::named_bar_sync(1, T2_EPI_THREADS);  // staging[bsel] is free for everybody (elected passed its wait_group)
         if (elected && chunk == 0) T2_STAMP(2, it, 2);
-        uint32_t r0[32], r1[32];
-        ptx::tmem_ld_32x32(taddr + chunk * 64, r0);
-        ptx::tmem_ld_32x32(taddr + chunk * 64 + 32, r1);
+        uint32_t r0[32];
+        ptx::tmem_ld_32x32(taddr + chunk * 64 + half * 32, r0);
         ptx::tmem_ld_wait();
         if (elected && chunk == 0) T2_STAMP(2, it, 3);
         if (chunk == CHUNKS - 1) {  // accumulator fully drained: release it to the MMA warp
@@ -263,7 +265,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (has_res) ptx::mbar_wait(&res_bar[bsel], (chunk_ctr / 3) & 1, 37);
         if (elected && chunk == 0) T2_STAMP(2, it, 4);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int gg = 0; gg < 4; ++gg) {
+          const int g = half * 4 + gg;     // 16-byte slot of the 128-byte row
           const int c = chunk * 64 + g * 8;
           const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c));
           const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
@@ -273,7 +276,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
           float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(g < 4 ? r0[g * 8 + j] : r1[(g - 4) * 8 + j]), sc[j], bi[j]);
+          for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r0[gg * 8 + j]), sc[j], bi[j]);
           uint4* slot = reinterpret_cast<uint4*>(my_row + (((g ^ sw) & 7) << 4));  // 128-byte swizzle, as TMA expects
           if (has_res) {
             const uint4 rr = *slot;
@@ -291,7 +294,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
         ptx::fence_proxy_async_smem();
         if (elected && chunk == 0) T2_STAMP(2, it, 5);
-        ptx::named_bar_sync(1, 128);
+        ptx::named_bar_sync(1, T2_EPI_THREADS);
         if (elected && chunk == 0) T2_STAMP(2, it, 6);
         if (elected && chunk == CHUNKS - 1) T2_STAMP(2, it, 7);
         if (elected) {

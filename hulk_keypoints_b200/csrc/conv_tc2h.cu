@@ -23,7 +23,8 @@ namespace hk {
 
 constexpr int TH_TILE_H = 8, TH_TILE_W = 16;
 constexpr int TH_ROW_BYTES = TH_TILE_W * 128;  // one patch row: 16 px x 64 ch bf16
-constexpr int TH_THREADS = 256;
+constexpr int TH_THREADS = 384;   // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare; warps 4-11: epilogue
+constexpr int TH_EPI_THREADS = 256;
 constexpr int TH_STAGING_BYTES = 3 * 128 * 128;
 constexpr int TH_MAX_A = 4, TH_MAX_B = 8;
 
@@ -97,7 +98,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
-      ptx::mbar_init(&tmem_empty_bar[i], 256);
+      ptx::mbar_init(&tmem_empty_bar[i], 2 * TH_EPI_THREADS);  // both CTAs' epilogue threads
     }
     for (int i = 0; i < 3; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_mbar_init();
@@ -183,8 +184,9 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       if (it >= 2) { const uint32_t j = it - 2; ptx::mbar_wait(&tmem_empty_bar[j & 1], (j >> 1) & 1, 57); }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (both CTAs, own 128 TMEM lanes; 128 threads, named barrier 1) =====================
-    const int q = warp & 3;
+    // ===================== epilogue (both CTAs, own 128 TMEM lanes; 8 warps = 256 threads, named barrier 1) =====================
+    // warp % 4 = TMEM lane quarter (32 rows), (warp - 4) / 4 = which 32 of a chunk's 64 columns (as in conv_tc2_kernel)
+    const int q = warp & 3, half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const bool elected = (warp == 4 && lane == 0);
     const int sw = row & 7;
@@ -220,10 +222,9 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           ptx::bulk_wait_group_read1();
           if (has_res && chunk + 1 < CHUNKS) issue_residual(chunk + 1, chunk_ctr + 1);
         }
-        ptx::named_bar_sync(1, 128);
-        uint32_t r0[32], r1[32];
-        ptx::tmem_ld_32x32(taddr + chunk * 64, r0);
-        ptx::tmem_ld_32x32(taddr + chunk * 64 + 32, r1);
+        ptx::named_bar_sync(1, TH_EPI_THREADS);
+        uint32_t r0[32];
+        ptx::tmem_ld_32x32(taddr + chunk * 64 + half * 32, r0);
         ptx::tmem_ld_wait();
         if (chunk == CHUNKS - 1) {
           ptx::tc_fence_before();
@@ -231,7 +232,8 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         if (has_res) ptx::mbar_wait(&res_bar[bsel], (chunk_ctr / 3) & 1, 59);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int gg = 0; gg < 4; ++gg) {
+          const int g = half * 4 + gg;  // 16-byte slot of the 128-byte row
           const int c = chunk * 64 + g * 8;
           const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c));
           const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
@@ -241,7 +243,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
           float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(g < 4 ? r0[g * 8 + j] : r1[(g - 4) * 8 + j]), sc[j], bi[j]);
+          for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r0[gg * 8 + j]), sc[j], bi[j]);
           uint4* slot = reinterpret_cast<uint4*>(my_row + (((g ^ sw) & 7) << 4));
           if (has_res) {
             const uint4 rr = *slot;
@@ -258,7 +260,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           *slot = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
         ptx::fence_proxy_async_smem();
-        ptx::named_bar_sync(1, 128);
+        ptx::named_bar_sync(1, TH_EPI_THREADS);
         if (elected) {
           ptx::tma_store_4d(&map_y, staging + bsel * 16384, n0 + chunk * 64, x0, y0, b);  // clipped outside the image / batch
           ptx::bulk_commit_group();
