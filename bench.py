@@ -16,6 +16,8 @@ argmax decode for `--batch` (64) images of 480x640 (BASELINE.json configs[1]).  
   roofline   the dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOPs of its launches in one step /
              their CUDA-event time, against MEASURED_PEAKS.json's dense bf16 peak.
   cpu_baseline / --impl reference: the oracle port (torch CPU restatement of the reference) on the host cores.
+  roofline_hbm_kernels / train_step: informational extras -- the memory-bound kernels against the measured copy bandwidth, and
+             (N=1, default workload) ms per training step at per-GPU batch 4 / 32 (BASELINE configs[3]; bench_train.py is the full tool).
 """
 from __future__ import annotations
 
@@ -57,6 +59,8 @@ def parse_args():
     ap.add_argument("--keypoints", type=int, default=4, help="K (config.py: 4; BASELINE config 5 also quotes 16 and 32)")
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true",
+                    help="skip the secondary measurement (BASELINE configs[3]: one training step per iteration, per-GPU batch 4 and 32, N=1 only)")
     ap.add_argument("--breakdown", default="", help="write the per-launch timing table to this JSON file")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay (profiling)")
     ap.add_argument("--profile-mode", action="store_true",
@@ -478,7 +482,44 @@ def run_ours(args, rank, world, local_rank):
         v, cores = n / secs, ref.cores
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{n} images {H}x{W}, B=1 per call, oracle port in the reference's as-written op order (torch CPU), {secs:.1f} s"}
+    if not args.no_train_step and world == 1 and args.precision == "bf16" and (B, H, W, K_KEYPOINTS) == (64, 480, 640, 4):
+        line["train_step"] = measure_train_step(dev, H, W)
     print(json.dumps(line), flush=True)
+
+
+def measure_train_step(dev, H, W):
+    """Secondary metric (BASELINE.json configs[3]; bench_train.py is the full tool): ms per training step -- Gaussian targets from labels +
+    train-mode forward + BCE + backward + fused Adam on libhulk_sm100 kernels, one CUDA graph -- at per-GPU batch 4 (config.py) and 32.
+    Never fails the headline line: errors are reported as text."""
+    out = {"config": "BASELINE configs[3], 1 GPU, 480x640, K=4, Adam lr 1e-4 wd 1e-4, synthetic images and labels", "unit": "ms/step"}
+    try:
+        import hulk_keypoints_b200 as hk
+        from hulk_keypoints_b200 import train_ops
+        from hulk_keypoints_b200.optim import FusedAdam
+        for bsz in (4, 32):
+            torch.manual_seed(0)
+            model = hk.KeypointsGauss(4, img_height=H, img_width=W).to(dev).train()
+            opt = FusedAdam(model.parameters(), lr=1e-4, weight_decay=1e-4)
+            g = torch.Generator().manual_seed(2000)
+            img = torch.rand(bsz, 3, H, W, generator=g).to(dev)
+            uv = torch.stack([torch.randint(0, W, (bsz, 4), generator=g), torch.randint(0, H, (bsz, 4), generator=g)], -1).float().to(dev)
+            for _ in range(3):
+                train_ops.train_step(model, opt, img, uv, sigma=8.0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps = 20
+            e0.record()
+            for _ in range(steps):
+                loss = train_ops.train_step(model, opt, img, uv, sigma=8.0)
+            e1.record(); e1.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[f"batch{bsz}"] = {"ms_per_step": ms, "images_per_sec": bsz / (ms * 1e-3), "loss": float(loss.item()),
+                                  "gpu_launches_per_step": model.train_engine(bsz, H, W).launches + 1}
+            del model, opt
+            torch.cuda.empty_cache()
+    except Exception as exc:  # noqa: BLE001 -- reported, never raised: this block is informational
+        out["error"] = f"{type(exc).__name__}: {exc}"
+    return out
 
 
 def ncu_conv_traffic_per_step(B, H, W, K, precision):
