@@ -177,13 +177,12 @@ __device__ __forceinline__ void stem_build_im2col(const __nv_bfloat16* patch, ui
   }
 }
 // k in [224,256) = chunks 4..7 of K block 3 never receive data: zero them once (they meet zero weights, but must be finite)
-__device__ __forceinline__ void stem_zero_k_padding(uint8_t* sA, __nv_bfloat16* patch, int tid) {
+// (the patch buffer needs no initialisation: all 21 x 38 pixels are rewritten for every tile, zeros outside the image)
+__device__ __forceinline__ void stem_zero_k_padding(uint8_t* sA, int tid) {
   for (int i = tid; i < 128 * 4; i += ST_THREADS) {
     const int row = i >> 2, chunk = 4 + (i & 3);
     *reinterpret_cast<uint4*>(sA + 3 * 16384 + sw128_off(row, chunk)) = make_uint4(0, 0, 0, 0);
   }
-  // the patch is fully rewritten for every tile (all 21 x 38 pixels, zeros outside the image)
-  (void)patch;
 }
 
 template <bool U8>
@@ -217,7 +216,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     ptx::tmem_relinquish();
   }
   if (tid >= 64 && tid < 64 + ST_COUT) { s_scale[tid - 64] = a.scale[tid - 64]; s_bias[tid - 64] = a.bias[tid - 64]; }
-  stem_zero_k_padding(sA, patch, tid);
+  stem_zero_k_padding(sA, tid);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -400,7 +399,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const StemWgrad
     ptx::tmem_alloc(tmem_ptr_smem, SWG_TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  stem_zero_k_padding(sA, patch, tid);
+  stem_zero_k_padding(sA, tid);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
