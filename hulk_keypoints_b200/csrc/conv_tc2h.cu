@@ -10,8 +10,11 @@
 //   * weights stream through their own ring, one (tap, channel block) tile per stage, half of the BLOCK_N rows per CTA as before.
 // Two rings (A: haloed boxes, B: weight tiles), each with full (leader's smem, 2 arrivals + both CTAs' TMA bytes) / empty (both
 // CTAs, multicast commit) barriers; accumulate order is (s, channel block, r).  Epilogue as in conv_tc2 with one 8x16 box per chunk.
-// Cost: a feature map whose height is not a multiple of 8 wastes the bottom rows of its last patch row (60 rows -> 64: 6.7 %); the
-// dispatcher routes here the shapes that gain nevertheless (conv_tc2h_applicable).
+// A feature map whose height is 1..4 rows past a multiple of 8 (60 = 7 x 8 + 4) would waste half of its last 8-row patch row (6.7 % of
+// the MMAs at 60 rows): those bottom rows are covered by 4x32 STRIP patches instead -- same 128 accumulator rows, box (64 ch, 32 px,
+// 4 + 2*dil rows), vertical taps r*dil*4096 bytes apart.  Full patches are enumerated first, strips after them, and the boundary is
+// padded to an even index, because both CTAs of a pair must work on the same patch shape (the tap offset is part of the ONE A
+// descriptor of the cta_group::2 MMA).  HK_CONV_STRIPS=0 keeps 8x16 patches everywhere.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -33,9 +36,10 @@ struct ConvTc2hArgs {
   const float* bias;
   const __nv_bfloat16* residual;
   int B, Ho, Wo, Cout, Cin, pad, dil, relu;
-  int tiles_x, tiles_per_img, num_patches;
+  int tiles_x, tiles_per_img, num_patches;   // 8x16 patches: per row, per image, in total (index range [0, num_patches))
+  int strip_first, num_strips, strips_per_img, strip_y0;  // 4x32 strips: index range [strip_first, strip_first + num_strips)
   int num_m_tiles, num_n_tiles, cblocks;  // m tile = 2 patches (one per CTA)
-  int a_slot_bytes, a_slots, b_slots;
+  int a_slot_bytes, a_bytes_full, a_bytes_strip, a_slots, b_slots;
 };
 
 __device__ __forceinline__ void th_decode_patch(const ConvTc2hArgs& a, int patch, int& b, int& y0, int& x0) {
@@ -45,6 +49,11 @@ __device__ __forceinline__ void th_decode_patch(const ConvTc2hArgs& a, int patch
     const int ty = r / a.tiles_x;
     y0 = ty * TH_TILE_H;
     x0 = (r - ty * a.tiles_x) * TH_TILE_W;
+  } else if (patch >= a.strip_first && patch < a.strip_first + a.num_strips) {
+    const int q = patch - a.strip_first;
+    b = q / a.strips_per_img;
+    y0 = a.strip_y0;
+    x0 = (q - b * a.strips_per_img) * (2 * TH_TILE_W);
   } else {
     b = a.B;  // out of range in the batch dimension: TMA zero fill, stores clipped
     y0 = 0;
@@ -55,7 +64,9 @@ __device__ __forceinline__ void th_decode_patch(const ConvTc2hArgs& a, int patch
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TH_THREADS, 1)
 conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res, const ConvTc2hArgs a) {
+                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res,
+                 const __grid_constant__ CUtensorMap map_xs, const __grid_constant__ CUtensorMap map_ys,
+                 const __grid_constant__ CUtensorMap map_ress, const ConvTc2hArgs a) {
   constexpr int HALF_N = BLOCK_N / 2;
   constexpr int B_BYTES = HALF_N * 128;
   extern __shared__ uint8_t smem_raw[];
@@ -86,6 +97,11 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     ptx::prefetch_tensormap(&map_w);
     ptx::prefetch_tensormap(&map_y);
     if (a.residual) ptx::prefetch_tensormap(&map_res);
+    if (a.num_strips > 0) {
+      ptx::prefetch_tensormap(&map_xs);
+      ptx::prefetch_tensormap(&map_ys);
+      if (a.residual) ptx::prefetch_tensormap(&map_ress);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < TH_MAX_A; ++i) {
@@ -120,13 +136,16 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const int m_tile = tile / a.num_n_tiles, n_tile = tile - m_tile * a.num_n_tiles;
       int b, y0, x0;
       th_decode_patch(a, 2 * m_tile + (int)rank, b, y0, x0);
+      const bool strip = 2 * m_tile >= a.strip_first;   // the same for both CTAs of the pair
+      const CUtensorMap* mxp = strip ? &map_xs : &map_x;
+      const uint32_t a_tx = 2u * (uint32_t)(strip ? a.a_bytes_strip : a.a_bytes_full);
       const int n_row0 = n_tile * BLOCK_N + (int)rank * HALF_N;
       for (int s = 0; s < 3; ++s) {
         for (int cb = 0; cb < a.cblocks; ++cb) {
           ptx::mbar_wait(&a_empty[as], aph ^ 1, 51);
           if (ptx::elect_one_sync()) {
-            ptx::tma2_load_4d(sA + as * a.a_slot_bytes, &map_x, &a_full[as], cb * 64, x0 + (s - 1) * a.dil, y0 - a.dil, b);
-            if (leader) ptx::mbar_arrive_expect_tx(&a_full[as], 2 * a.a_slot_bytes);
+            ptx::tma2_load_4d(sA + as * a.a_slot_bytes, mxp, &a_full[as], cb * 64, x0 + (s - 1) * a.dil, y0 - a.dil, b);
+            if (leader) ptx::mbar_arrive_expect_tx(&a_full[as], a_tx);
             else ptx::mbar_arrive_remote(&a_full[as], 0);
           }
           __syncwarp();
@@ -149,9 +168,10 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       // ===================== MMA issuer (leader CTA only; whole warp waits, one elected lane issues) =====================
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(256, BLOCK_N);
       uint32_t as = 0, aph = 0, bs = 0, bph = 0, it = 0;
-      const uint32_t tap_bytes = (uint32_t)a.dil * TH_ROW_BYTES;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        const bool strip = 2 * (tile / a.num_n_tiles) >= a.strip_first;
+        const uint32_t tap_bytes = (uint32_t)a.dil * (strip ? 2 * TH_ROW_BYTES : TH_ROW_BYTES);  // one image row of the staged box
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 53);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -199,13 +219,16 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const int m_tile = tile / a.num_n_tiles, n_tile = tile - m_tile * a.num_n_tiles;
       int b, y0, x0;
       th_decode_patch(a, 2 * m_tile + (int)rank, b, y0, x0);
+      const bool strip = 2 * m_tile >= a.strip_first;
+      const CUtensorMap* myp = strip ? &map_ys : &map_y;
+      const CUtensorMap* mrp = strip ? &map_ress : &map_res;
       const int n0 = n_tile * BLOCK_N;
       const float* scale = a.scale + n0;
       const float* bias = a.bias + n0;
       auto issue_residual = [&](int chunk, uint32_t ctr) {
         const uint32_t bsel = ctr % 3;
         ptx::mbar_arrive_expect_tx(&res_bar[bsel], 16384);
-        ptx::tma_load_4d(staging + bsel * 16384, &map_res, &res_bar[bsel], n0 + chunk * 64, x0, y0, b);
+        ptx::tma_load_4d(staging + bsel * 16384, mrp, &res_bar[bsel], n0 + chunk * 64, x0, y0, b);
       };
       if (elected) {
         ptx::bulk_wait_group_read1();
@@ -262,7 +285,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         ptx::fence_proxy_async_smem();
         ptx::named_bar_sync(1, TH_EPI_THREADS);
         if (elected) {
-          ptx::tma_store_4d(&map_y, staging + bsel * 16384, n0 + chunk * 64, x0, y0, b);  // clipped outside the image / batch
+          ptx::tma_store_4d(myp, staging + bsel * 16384, n0 + chunk * 64, x0, y0, b);  // clipped outside the image / batch
           ptx::bulk_commit_group();
         }
       }
@@ -297,8 +320,8 @@ bool conv_tc2h_applicable(const HkConvDesc& d) {
 }
 
 template <int BLOCK_N>
-static int launch_tc2h(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& mres, ConvTc2hArgs& a,
-                       cudaStream_t s) {
+static int launch_tc2h(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& mres,
+                       const CUtensorMap& mxs, const CUtensorMap& mys, const CUtensorMap& mress, ConvTc2hArgs& a, cudaStream_t s) {
   constexpr int B_BYTES = (BLOCK_N / 2) * 128;
   const int budget = 227 * 1024 - 1024 - TH_STAGING_BYTES - 512;
   int na = 3, nb = (budget - na * a.a_slot_bytes) / B_BYTES;
@@ -321,7 +344,8 @@ static int launch_tc2h(const CUtensorMap& mx, const CUtensorMap& mw, const CUten
   const int total = a.num_m_tiles * a.num_n_tiles;
   int clusters = sm_count() / 2;
   if (clusters > total) clusters = total;
-  cudaError_t le = launch_pdl(conv_tc2h_kernel<BLOCK_N>, dim3(2 * clusters), dim3(TH_THREADS), (size_t)smem, s, mx, mw, my, mres, a);
+  cudaError_t le = launch_pdl(conv_tc2h_kernel<BLOCK_N>, dim3(2 * clusters), dim3(TH_THREADS), (size_t)smem, s, mx, mw, my, mres, mxs, mys,
+                              mress, a);
   if (le != cudaSuccess) return fail(HK_ERR_CUDA, "conv_tc2h_kernel: %s", cudaGetErrorString(le));
   return check_launch("conv_tc2h_kernel");
 }
@@ -330,10 +354,22 @@ int conv_tc2h_launch(const HkConvDesc& d, const void* x, const void* w, const fl
                      void* y, cudaStream_t s) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return fail(HK_ERR_CUDA, "conv(tcgen05,halo): cuTensorMapEncodeTiled entry point not available");
-  const long long patches_all = (long long)ceil_div(d.out_w, TH_TILE_W) * ceil_div(d.out_h, TH_TILE_H) * d.batch;
+  // patch geometry: 8x16 patches over the rows that fill whole patch rows, 4x32 strips over a remainder of 1..4 rows (see the header)
+  const char* strips_env = getenv("HK_CONV_STRIPS");
+  const int rem_rows = d.out_h % TH_TILE_H;
+  // (dilation 4 strip boxes are 48 KB: three of them plus the weight ring do not fit next to the staging buffers)
+  const bool use_strips = !(strips_env && strips_env[0] == '0') && rem_rows >= 1 && rem_rows <= 4 && d.out_h > TH_TILE_H && d.dil <= 2;
+  const int tiles_x = ceil_div(d.out_w, TH_TILE_W);
+  const int tiles_y = use_strips ? d.out_h / TH_TILE_H : ceil_div(d.out_h, TH_TILE_H);
+  const int strips_per_img = use_strips ? ceil_div(d.out_w, 2 * TH_TILE_W) : 0;
+  const long long full_all = (long long)tiles_x * tiles_y * d.batch;
+  const long long strip_first_ll = (full_all + 1) / 2 * 2;
+  const long long strips_all = (long long)strips_per_img * d.batch;
+  const long long patches_all = use_strips ? strip_first_ll + strips_all : full_all;
   const int block_n = pick_block_n_pair(d.out_c, (patches_all + 1) / 2);
   const int ktot = 9 * d.in_c;
   const int box_rows = TH_TILE_H + 2 * d.dil;
+  const int strip_box_rows = TH_TILE_H / 2 + 2 * d.dil;
   CUtensorMap mx, mw, my, mres;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)d.in_c, (cuuint64_t)d.in_w, (cuuint64_t)d.in_h, (cuuint64_t)d.batch};
@@ -371,20 +407,51 @@ int conv_tc2h_launch(const HkConvDesc& d, const void* x, const void* w, const fl
       if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,halo): cuTensorMapEncodeTiled(residual) failed: %d", (int)r);
     }
   }
+  CUtensorMap mxs = mx, mys = my, mress = mres;   // 4x32 strip flavours of the activation / output / residual maps
+  if (use_strips) {
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    {
+      const cuuint64_t dims[4] = {(cuuint64_t)d.in_c, (cuuint64_t)d.in_w, (cuuint64_t)d.in_h, (cuuint64_t)d.batch};
+      const cuuint64_t strides[3] = {(cuuint64_t)d.in_c * 2, (cuuint64_t)d.in_w * d.in_c * 2, (cuuint64_t)d.in_h * d.in_w * d.in_c * 2};
+      const cuuint32_t box[4] = {64, (cuuint32_t)(2 * TH_TILE_W), (cuuint32_t)strip_box_rows, 1};
+      CUresult r = encode(&mxs, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,halo): cuTensorMapEncodeTiled(strip activations) failed: %d", (int)r);
+    }
+    const cuuint64_t dims[4] = {(cuuint64_t)d.out_c, (cuuint64_t)d.out_w, (cuuint64_t)d.out_h, (cuuint64_t)d.batch};
+    const cuuint64_t strides[3] = {(cuuint64_t)d.out_c * 2, (cuuint64_t)d.out_w * d.out_c * 2, (cuuint64_t)d.out_h * d.out_w * d.out_c * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)(2 * TH_TILE_W), (cuuint32_t)(TH_TILE_H / 2), 1};
+    CUresult r = encode(&mys, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,halo): cuTensorMapEncodeTiled(strip output) failed: %d", (int)r);
+    mress = mys;
+    if (residual) {
+      r = encode(&mress, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(residual), dims, strides, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,halo): cuTensorMapEncodeTiled(strip residual) failed: %d", (int)r);
+    }
+  }
   ConvTc2hArgs a;
   a.scale = scale; a.bias = bias;
   a.residual = static_cast<const __nv_bfloat16*>(residual);
   a.B = d.batch; a.Ho = d.out_h; a.Wo = d.out_w; a.Cout = d.out_c; a.Cin = d.in_c; a.pad = d.pad; a.dil = d.dil; a.relu = d.relu;
-  a.tiles_x = ceil_div(d.out_w, TH_TILE_W);
-  a.tiles_per_img = a.tiles_x * ceil_div(d.out_h, TH_TILE_H);
-  const long long patches = (long long)a.tiles_per_img * d.batch;
-  HK_REQUIRE(patches < 0x3fffffffLL, "conv(tcgen05,halo): too many tiles");
-  a.num_patches = (int)patches;
-  a.num_m_tiles = (a.num_patches + 1) / 2;
+  a.tiles_x = tiles_x;
+  a.tiles_per_img = tiles_x * tiles_y;
+  HK_REQUIRE(patches_all < 0x3fffffffLL, "conv(tcgen05,halo): too many tiles");
+  a.num_patches = (int)full_all;
+  a.strip_first = use_strips ? (int)strip_first_ll : 0x7fffffff;   // no strips: no pair ever reaches the strip range
+  a.num_strips = (int)strips_all;
+  a.strips_per_img = strips_per_img > 0 ? strips_per_img : 1;
+  a.strip_y0 = tiles_y * TH_TILE_H;
+  a.num_m_tiles = (int)((patches_all + 1) / 2);
   a.num_n_tiles = d.out_c / block_n;
   a.cblocks = d.in_c / 64;
-  a.a_slot_bytes = box_rows * TH_ROW_BYTES;
-  return block_n == 256 ? launch_tc2h<256>(mx, mw, my, mres, a, s) : launch_tc2h<128>(mx, mw, my, mres, a, s);
+  a.a_bytes_full = box_rows * TH_ROW_BYTES;
+  a.a_bytes_strip = strip_box_rows * 2 * TH_ROW_BYTES;
+  a.a_slot_bytes = use_strips && a.a_bytes_strip > a.a_bytes_full ? a.a_bytes_strip : a.a_bytes_full;
+  return block_n == 256 ? launch_tc2h<256>(mx, mw, my, mres, mxs, mys, mress, a, s) : launch_tc2h<128>(mx, mw, my, mres, mxs, mys, mress, a, s);
 }
 
 }  // namespace hk

@@ -378,6 +378,38 @@ HALO_CASES = [
 ]
 
 
+STRIP_CASES = [
+    # heights 1..4 rows past a multiple of 8: the bottom rows are covered by 4x32 strip patches (conv_tc2h.cu)
+    (2, 60, 80, 128, 128, 3, 1, 1, True, True),     # layer2 shape: 7 patch rows + a strip row, 80 = 2.5 strips wide
+    (1, 60, 80, 256, 256, 3, 1, 2, True, True),     # layer3 shape, dilation 2 (32 KB strip boxes)
+    (3, 12, 37, 128, 128, 3, 1, 1, True, False),    # odd number of 8x16 patches -> padded boundary; ragged strips
+    (2, 9, 70, 128, 256, 3, 1, 2, False, True),     # one remainder row only: strips clipped to a single row
+    (5, 20, 48, 128, 128, 3, 1, 1, False, True),    # strips with odd count per batch
+]
+
+
+@pytest.mark.parametrize("case", STRIP_CASES)
+def test_conv_tcgen05_strip_patches(case):
+    """Strip patches against the oracle, and bit-identical to the all-8x16 schedule (same accumulation order per output element)."""
+    import os
+    os.environ["HK_CONV_HALO"] = "1"
+    try:
+        test_conv_tcgen05_vs_oracle(case)
+        B, H, W, cin, cout, k, stride, dil, residual, relu = case
+        x, w, s, b, res, pad = _conv_case(*case, seed=21)
+        xd = x.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous().to(dev())
+        rd = None if res is None else res.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous().to(dev())
+        wp, _, _ = ops.pack_conv_weights(w.to(dev()), None, 1e-5, torch.bfloat16)
+        run = lambda: ops.conv_bn_act(xd, wp, s.to(dev()), b.to(dev()), stride=stride, pad=pad, dil=dil, relu=relu, residual=rd)
+        y_strips = run()
+        os.environ["HK_CONV_STRIPS"] = "0"
+        y_plain = run()
+        assert torch.equal(y_strips, y_plain)
+    finally:
+        os.environ.pop("HK_CONV_HALO", None)
+        os.environ.pop("HK_CONV_STRIPS", None)
+
+
 @pytest.mark.parametrize("case", HALO_CASES)
 def test_conv_tcgen05_haloed_operand_kernel(case):
     """conv_tc2h (one haloed activation box per horizontal tap) against the oracle, forced on for every eligible shape."""
