@@ -430,7 +430,7 @@ def run_ours(args, rank, world, local_rank):
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all launches of one step)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": ncu_conv_traffic_per_step(B, H, W, K_KEYPOINTS, args.precision),
-                "traffic_note": "DRAM bytes read+written by the 35 conv launches of one step (ncu, profiles/r01e_step_per_launch_dram.json); "
+                "traffic_note": "DRAM bytes read+written by the 35 conv launches of one step (ncu, profiles/r01f_step_per_launch_dram.json); "
                                 "algorithmic activation traffic of those launches: in+out+residual of every conv",
                 "peak_source": f"{peaks['source']} burst bf16 ({peak}); sustained {peaks['bf16_tflops_sustained']}",
                 "launches": len(tc), "ms_in_step": tc_ms, "share_of_step": tc_ms / sum(r["ms"] for r in rows)}
@@ -524,11 +524,11 @@ def measure_train_step(dev, H, W):
 
 def ncu_conv_traffic_per_step(B, H, W, K, precision):
     """DRAM bytes (read + write) of the 35 tcgen05 conv launches of one step from the committed ncu capture
-    (profiles/r01e_step_per_launch_dram.json: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over bench.py's default
+    (profiles/r01f_step_per_launch_dram.json: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over bench.py's default
     workload).  None for any other workload."""
     if (B, H, W, K, precision) != (64, 480, 640, 4, "bf16"):
         return None
-    p = os.path.join(ROOT, "profiles", "r01e_step_per_launch_dram.json")
+    p = os.path.join(ROOT, "profiles", "r01f_step_per_launch_dram.json")
     if not os.path.exists(p):
         return None
     with open(p) as f:
