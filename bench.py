@@ -474,7 +474,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline_hbm_kernels": hbm_rows,
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline and world >= 1:
+    if not args.no_cpu_baseline and world == 1:   # rank 0 at N=1 only (the reference arm covers N>1)
         ref = CpuReference(H, W)
         ref.run(2)
         n = args.cpu_images or 120
