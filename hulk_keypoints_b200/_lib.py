@@ -30,6 +30,8 @@ EXPORTS = (
     "hk_pack_conv_weights_dgrad", "hk_zero_insert2x", "hk_conv_wgrad_workspace_bytes", "hk_conv_wgrad",
     "hk_stem_wgrad_workspace_bytes", "hk_stem_wgrad", "hk_maxpool3x3s2_bwd", "hk_head_logits_fwd",
     "hk_head_bwd_workspace_bytes", "hk_head_bwd", "hk_sigmoid_fwd", "hk_sigmoid_bwd", "hk_pack_conv_weights_many",
+    # round 2
+    "hk_soft_argmax_workspace_bytes", "hk_soft_argmax", "hk_l1_normalize_dim1",
 )
 
 
@@ -112,6 +114,12 @@ def _declare(lib):
     lib.hk_sigmoid_fwd.argtypes = [vp, vp, ll, vp]
     lib.hk_sigmoid_bwd.restype = i
     lib.hk_sigmoid_bwd.argtypes = [vp, vp, vp, ll, vp]
+    lib.hk_soft_argmax_workspace_bytes.restype = sz
+    lib.hk_soft_argmax_workspace_bytes.argtypes = [i, i, i]
+    lib.hk_soft_argmax.restype = i
+    lib.hk_soft_argmax.argtypes = [vp, i, i, i, vp, vp, vp, sz, vp]
+    lib.hk_l1_normalize_dim1.restype = i
+    lib.hk_l1_normalize_dim1.argtypes = [vp, i, i, i, vp, vp]
     lib.hk_bce_workspace_bytes.restype = sz
     lib.hk_bce_workspace_bytes.argtypes = [C.c_longlong]
     lib.hk_bce_fwd_bwd.restype = i
@@ -148,6 +156,21 @@ def require_device() -> None:
     if not torch.cuda.is_available():
         raise RuntimeError("hulk_keypoints_b200 needs a CUDA device (B200, sm_100a); no CPU path exists")
     check(lib().hk_check_device(), "hk_check_device")
+
+
+# Kernels that write parameters / BatchNorm buffers through raw pointers (hk_adam_step, hk_bn_train_stats, graph replays) do not bump
+# torch's tensor `_version`; writers that do not know which model owns the memory (FusedAdam gets bare parameters, like
+# torch.optim.Adam in train.py:79) bump this process-wide counter instead and InferenceEngine._weights_key includes it.
+_raw_write_generation = 0
+
+
+def note_raw_parameter_write() -> None:
+    global _raw_write_generation
+    _raw_write_generation += 1
+
+
+def raw_write_generation() -> int:
+    return _raw_write_generation
 
 
 def ptr(t):

@@ -44,11 +44,19 @@ struct ConvTc2Args {
   int Cin, kh, kw, stride, pad, dil, relu;
   int tiles_x, tiles_per_img, num_boxes;
   int num_m_tiles, num_n_tiles, cblocks;  // m tiles of 256 pixels (4 boxes)
-  int dbg_mode;    // diagnostics only (HK_TC2_DEBUG): bit flags 1 = skip the MMAs, 2 = skip the TMA operand loads, 4 = skip the epilogue body (results are garbage)
-  long long* dbg;  // optional timeline of cluster 0's leader CTA (tools/diag_tc2_timeline.py); null in production
+#ifdef HK_DIAG  // diagnostics build only (python -m hulk_keypoints_b200.build --diag -> libhulk_sm100_diag.so); never in the shipped library
+  int dbg_mode;    // HK_TC2_DEBUG bit flags: 1 = skip the MMAs, 2 = skip the TMA operand loads, 4 = skip the epilogue body (results are garbage)
+  long long* dbg;  // optional timeline of cluster 0's leader CTA (tools/diag_tc2_timeline.py)
+#endif
 };
+#ifdef HK_DIAG
+#define T2_DBG_MODE(a) ((a).dbg_mode)
 #define T2_STAMP(role, t, slot) \
   do { if (a.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (t) < 16) a.dbg[((role) * 16 + (t)) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define T2_DBG_MODE(a) 0
+#define T2_STAMP(role, t, slot) do { } while (0)
+#endif
 
 template <int BLOCK_N>
 struct Tc2Cfg {
@@ -146,7 +154,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const int dy = r * a.dil - a.pad, dx = s * a.dil - a.pad;
             const int kbase = (r * a.kw + s) * a.Cin;
             for (int cb = 0; cb < a.cblocks; ++cb) {
-              if (a.dbg_mode & 2) continue;
+              if (T2_DBG_MODE(a) & 2) continue;
               ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 31);
               if (ptx::elect_one_sync()) {
                 uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -177,7 +185,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         T2_STAMP(1, it, 1);
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
-          if (!(a.dbg_mode & 2)) ptx::mbar_wait(&full_bar[stage], phase, 33);
+          if (!(T2_DBG_MODE(a) & 2)) ptx::mbar_wait(&full_bar[stage], phase, 33);
           if (kb == 0) T2_STAMP(1, it, 2);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -186,7 +194,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (ptx::elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (!(a.dbg_mode & 1)) ptx::umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (!(T2_DBG_MODE(a) & 1)) ptx::umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             ptx::umma2_commit_mc(&empty_bar[stage]);
             if (kb == num_kb - 1) ptx::umma2_commit_mc(&tmem_full_bar[acc]);
           }
@@ -238,7 +246,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 36);
       ptx::tc_fence_after();
       if (elected) T2_STAMP(2, it, 1);
-      if (a.dbg_mode & 4) {
+      if (T2_DBG_MODE(a) & 4) {
         ptx::tc_fence_before();
         ptx::mbar_arrive_remote(&tmem_empty_bar[acc], 0);
         continue;
@@ -321,8 +329,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_fn();
 
+#ifdef HK_DIAG
 static long long* g_tc2_dbg = nullptr;
 extern "C" __attribute__((visibility("default"))) void hk_debug_set_tc2_timeline(long long* dev_buf) { g_tc2_dbg = dev_buf; }
+#endif
 
 bool conv_tc2_applicable(const HkConvDesc& d) {
   static const bool disabled = getenv("HK_DISABLE_2CTA") != nullptr;
@@ -408,8 +418,10 @@ int conv_tc2_launch(const HkConvDesc& d, const void* x, const void* w, const flo
   a.num_m_tiles = (a.num_boxes + 3) / 4;
   a.num_n_tiles = d.out_c / block_n;
   a.cblocks = d.in_c / 64;
+#ifdef HK_DIAG
   a.dbg = g_tc2_dbg;
   { const char* m = getenv("HK_TC2_DEBUG"); a.dbg_mode = m ? atoi(m) : 0; }
+#endif
   return block_n == 256 ? launch_tc2<256>(mx, mw, my, mres, a, s) : launch_tc2<128>(mx, mw, my, mres, a, s);
 }
 

@@ -40,10 +40,16 @@ struct ConvC64Args {
   int box_rows, patch_bytes;  // 8 + 2*dil rows; box_rows * 2048
   int has_residual;
   int slots;  // number of patch slots in the ring
-  long long* dbg;  // optional timeline of CTA 0 (tools/diag_c64_timeline.py); null in production
+#ifdef HK_DIAG
+  long long* dbg;  // optional timeline of CTA 0 (tools/diag_c64_timeline.py); diagnostics build only
+#endif
 };
+#ifdef HK_DIAG
 #define C64_STAMP(role, t, slot) \
   do { if (a.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (t) < 16) a.dbg[((role) * 16 + (t)) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define C64_STAMP(role, t, slot) do { } while (0)
+#endif
 constexpr int C64_STAGING_BYTES = 128 * 128;  // one output tile: 128 pixels x 64 ch bf16 (two of them: tiles alternate)
 
 __global__ void __launch_bounds__(C64_THREADS, 1)
@@ -275,8 +281,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_fn();
 
+#ifdef HK_DIAG
 static long long* g_c64_dbg = nullptr;
 extern "C" __attribute__((visibility("default"))) void hk_debug_set_c64_timeline(long long* dev_buf) { g_c64_dbg = dev_buf; }
+#endif
 
 bool conv_tc_c64_applicable(const HkConvDesc& d) {
   static const bool disabled = getenv("HK_DISABLE_C64") != nullptr;
@@ -332,7 +340,9 @@ int conv_tc_c64_launch(const HkConvDesc& d, const void* x, const void* w, const 
   }
   ConvC64Args a;
   a.has_residual = residual ? 1 : 0;
+#ifdef HK_DIAG
   a.dbg = g_c64_dbg;
+#endif
   a.scale = scale; a.bias = bias;
   a.residual = static_cast<const __nv_bfloat16*>(residual);
   a.y = static_cast<__nv_bfloat16*>(y);

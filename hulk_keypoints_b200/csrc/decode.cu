@@ -133,9 +133,149 @@ static void argmax_plan(int hw, int* chunk_len, int* chunks) {
   *chunks = ceil_div(hw, len);
 }
 
+
+// ------------------------------------------------------------------------------------------------ soft-argmax
+// `Prediction.expectation` (reference src/prediction.py:31-38, called at :45): softmax over one (H, W) map, then the expected
+// (x, y) index -- with the reference's flattening quirk kept: the map is flattened as `d.T.ravel()` (column-major: flat index
+// i = c*H + r for element d[r, c]) while the index arrays assume row-major order (x' = i % W, y' = i // W).  One pass over the
+// heatmap (HBM-bound: 4*H*W bytes per map): each thread keeps an online-softmax state (running max m, and S = sum e,
+// Sx = sum e*x', Sy = sum e*y' relative to m, e = expf(v - m) in fp32 like numpy's float32 exp, sums in fp64 like the
+// reference's float64 dot); fixed-order warp / CTA / chunk reductions (deterministic, no atomics).
+struct SoftPartial {
+  float m;
+  float pad;
+  double s, sx, sy;
+};
+
+__device__ __forceinline__ void soft_merge(float& m, double& s, double& sx, double& sy, float om, double os, double osx, double osy) {
+  // combine two online-softmax states; an empty state has m = -inf and zero sums
+  const float nm = fmaxf(m, om);
+  const double fa = (m == nm) ? 1.0 : (double)expf(m - nm);   // m = -inf -> 0
+  const double fb = (om == nm) ? 1.0 : (double)expf(om - nm);
+  s = s * fa + os * fb;
+  sx = sx * fa + osx * fb;
+  sy = sy * fa + osy * fb;
+  m = nm;
+}
+
+constexpr int kSoftThreads = 256;
+
+__global__ void __launch_bounds__(kSoftThreads)
+soft_argmax_partial_kernel(const float* __restrict__ heat, int H, int W, int rows_per_chunk, int chunks, SoftPartial* __restrict__ partial) {
+  const int map = blockIdx.y, chunk = blockIdx.x;
+  const float* src = heat + (size_t)map * H * W;
+  const int r0 = chunk * rows_per_chunk, r1 = min(H, r0 + rows_per_chunk);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -INFINITY;
+  double s = 0.0, sx = 0.0, sy = 0.0;
+  const int hx = H % W, hy = H / W;   // flat index step between neighbouring columns of one row: i += H
+  const bool vec_ok = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  for (int r = r0 + warp; r < r1; r += kSoftThreads / 32) {
+    const float* row = src + (size_t)r * W;
+    for (int c = lane * 4; c < W; c += 128) {
+      float v[4];
+      int n = 4;
+      if (vec_ok) {
+        const float4 q = __ldcs(reinterpret_cast<const float4*>(row + c));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+        n = min(4, W - c);
+        for (int j = 0; j < 4; ++j) v[j] = j < n ? row[c + j] : -INFINITY;
+      }
+      float vm = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+      if (vm > m) {   // rescale the running sums once per 4 elements at most
+        const double f = (double)expf(m - vm);   // m = -inf -> 0
+        s *= f; sx *= f; sy *= f;
+        m = vm;
+      }
+      const unsigned i0 = (unsigned)c * (unsigned)H + (unsigned)r;   // flat index of d.T.ravel() (< 2^31, checked on the host)
+      int yq = (int)(i0 / (unsigned)W), xq = (int)(i0 - (unsigned)yq * (unsigned)W);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < n) {
+          const double e = (double)expf(v[j] - m);
+          s += e;
+          sx += e * (double)xq;
+          sy += e * (double)yq;
+        }
+        xq += hx; yq += hy;
+        if (xq >= W) { xq -= W; ++yq; }
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, off);
+    const double os = __shfl_xor_sync(0xffffffffu, s, off), osx = __shfl_xor_sync(0xffffffffu, sx, off),
+                 osy = __shfl_xor_sync(0xffffffffu, sy, off);
+    soft_merge(m, s, sx, sy, om, os, osx, osy);
+  }
+  __shared__ SoftPartial sp[kSoftThreads / 32];
+  if (lane == 0) { sp[warp].m = m; sp[warp].s = s; sp[warp].sx = sx; sp[warp].sy = sy; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kSoftThreads / 32; ++w) soft_merge(m, s, sx, sy, sp[w].m, sp[w].s, sp[w].sx, sp[w].sy);
+    SoftPartial out;
+    out.m = m; out.pad = 0.f; out.s = s; out.sx = sx; out.sy = sy;
+    partial[(size_t)map * chunks + chunk] = out;
+  }
+}
+
+__global__ void soft_argmax_final_kernel(const SoftPartial* __restrict__ partial, int maps, int chunks, double* __restrict__ exp_xy,
+                                         int32_t* __restrict__ exp_int) {
+  const int map = blockIdx.x * blockDim.x + threadIdx.x;
+  if (map >= maps) return;
+  float m = -INFINITY;
+  double s = 0.0, sx = 0.0, sy = 0.0;
+  for (int c = 0; c < chunks; ++c) {
+    const SoftPartial p = partial[(size_t)map * chunks + c];
+    soft_merge(m, s, sx, sy, p.m, p.s, p.sx, p.sy);
+  }
+  const double ex = sx / s, ey = sy / s;
+  exp_xy[2 * map + 0] = ex;
+  exp_xy[2 * map + 1] = ey;
+  if (exp_int) {   // int(np.dot(...)) of the reference: truncation toward zero (values are >= 0)
+    exp_int[2 * map + 0] = (int32_t)ex;
+    exp_int[2 * map + 1] = (int32_t)ey;
+  }
+}
+
+static void soft_plan(int H, int* rows_per_chunk, int* chunks) {
+  int c = ceil_div(H, 16);   // >= 16 rows per CTA (two per warp); at most 64 chunks per map
+  if (c > 64) c = 64;
+  if (c < 1) c = 1;
+  *rows_per_chunk = ceil_div(H, c);
+  *chunks = ceil_div(H, *rows_per_chunk);
+}
+
 }  // namespace hk
 
 extern "C" {
+
+size_t hk_soft_argmax_workspace_bytes(int maps, int H, int W) {
+  if (maps <= 0 || H <= 0 || W <= 0) return 0;
+  int rows, chunks;
+  hk::soft_plan(H, &rows, &chunks);
+  return (size_t)maps * chunks * sizeof(hk::SoftPartial);
+}
+
+int hk_soft_argmax(const float* heat, int maps, int H, int W, double* exp_xy, int32_t* exp_int_or_null, void* ws, size_t ws_bytes,
+                   void* stream) {
+  using namespace hk;
+  HK_REQUIRE(heat && exp_xy && ws, "hk_soft_argmax: null pointer");
+  HK_REQUIRE(maps > 0 && H > 0 && W > 0 && maps <= 65535, "hk_soft_argmax: bad shape maps=%d H=%d W=%d", maps, H, W);
+  HK_REQUIRE((long long)H * W < 0x7fffffffLL, "hk_soft_argmax: map too large");
+  HK_REQUIRE(ws_bytes >= hk_soft_argmax_workspace_bytes(maps, H, W), "hk_soft_argmax: workspace too small");
+  HK_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "hk_soft_argmax: workspace must be 8-byte aligned");
+  int rows, chunks;
+  soft_plan(H, &rows, &chunks);
+  cudaStream_t s = as_stream(stream);
+  soft_argmax_partial_kernel<<<dim3(chunks, maps), kSoftThreads, 0, s>>>(heat, H, W, rows, chunks, static_cast<SoftPartial*>(ws));
+  int rc = check_launch("soft_argmax_partial_kernel");
+  if (rc) return rc;
+  soft_argmax_final_kernel<<<ceil_div(maps, 64), 64, 0, s>>>(static_cast<const SoftPartial*>(ws), maps, chunks, exp_xy, exp_int_or_null);
+  return check_launch("soft_argmax_final_kernel");
+}
 
 size_t hk_argmax_workspace_bytes(int B, int K, int H, int W) {
   if (B <= 0 || K <= 0 || H <= 0 || W <= 0) return 0;

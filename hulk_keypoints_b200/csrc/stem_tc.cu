@@ -49,12 +49,19 @@ struct StemTcArgs {
   int B, H, W, Ho, Wo;
   int tiles_x, tiles_per_img, num_tiles;
   int relu;         // 1: ReLU in the epilogue (inference / folded BN); 0: raw affine output (train-mode BN follows)
-  long long* dbg;  // optional phase timeline of CTA 0 (tools/diag_stem_timeline.py); null in production
+#ifdef HK_DIAG
+  long long* dbg;  // optional phase timeline of CTA 0 (tools/diag_stem_timeline.py); diagnostics build only
+#endif
 };
+#ifdef HK_DIAG
+#define ST_DBG(a) ((a).dbg)
+#else
+#define ST_DBG(a) (static_cast<long long*>(nullptr))
+#endif
 constexpr int ST_DBG_FIRST = 36;  // first tile (of CTA 0) recorded in the diagnostic timeline: steady state, L2 full of dirty lines
 #define ST_STAMP(slot)                                                                            \
   do {                                                                                            \
-    if (a.dbg && blockIdx.x == 0 && tid == 0 && dbg_tile >= ST_DBG_FIRST && dbg_tile < ST_DBG_FIRST + 24) a.dbg[(dbg_tile - ST_DBG_FIRST) * 8 + (slot)] = clock64(); \
+    if (ST_DBG(a) && blockIdx.x == 0 && tid == 0 && dbg_tile >= ST_DBG_FIRST && dbg_tile < ST_DBG_FIRST + 24) ST_DBG(a)[(dbg_tile - ST_DBG_FIRST) * 8 + (slot)] = clock64(); \
   } while (0)
 
 // byte offset of (row, 16-byte chunk) inside one 128-row x 128-byte K block, SWIZZLE_128B
@@ -240,7 +247,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   }
 
   int dbg_tile = 0;
-  if (a.dbg && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) a.dbg[192 + (blockIdx.x ? 4 : 0)] = clock64();
+  if (ST_DBG(a) && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) ST_DBG(a)[192 + (blockIdx.x ? 4 : 0)] = clock64();
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++dbg_tile) {
     ST_STAMP(0);
     const int oy0 = ty * ST_TILE_H, ox0 = tx * ST_TILE_W, ob = b;
@@ -326,11 +333,11 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     ST_STAMP(7);
   }
 
-  if (a.dbg && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) a.dbg[193 + (blockIdx.x ? 4 : 0)] = clock64();
+  if (ST_DBG(a) && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) ST_DBG(a)[193 + (blockIdx.x ? 4 : 0)] = clock64();
   if (tid == 0) ptx::bulk_wait_group0();
-  if (a.dbg && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
-    a.dbg[194 + (blockIdx.x ? 4 : 0)] = clock64();
-    a.dbg[195 + (blockIdx.x ? 4 : 0)] = dbg_tile;
+  if (ST_DBG(a) && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+    ST_DBG(a)[194 + (blockIdx.x ? 4 : 0)] = clock64();
+    ST_DBG(a)[195 + (blockIdx.x ? 4 : 0)] = dbg_tile;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -536,9 +543,11 @@ int hk_stem_pack_weights(const float* w_oihw, void* w_out, void* stream) {
   return check_launch("stem_pack_kernel");
 }
 
+#ifdef HK_DIAG
 static long long* g_stem_dbg = nullptr;
-// Undocumented diagnostic hook (not in the public header): device buffer of 24*8 int64 receiving CTA 0's phase clocks.
+// Diagnostic hook of the --diag build (not in the public header): device buffer of 24*8 int64 receiving CTA 0's phase clocks.
 __attribute__((visibility("default"))) void hk_debug_set_stem_timeline(long long* dev_buf) { g_stem_dbg = dev_buf; }
+#endif
 
 static int stem_launch(const void* x, bool u8, const void* w_packed, const float* scale, const float* bias, void* y_nhwc, int B,
                        int H, int W, void* stream, int relu = 1) {
@@ -574,7 +583,9 @@ static int stem_launch(const void* x, bool u8, const void* w_packed, const float
   StemTcArgs a;
   a.x = x; a.scale = scale; a.bias = bias; a.y = static_cast<__nv_bfloat16*>(y_nhwc);
   a.B = B; a.H = H; a.W = W;
+#ifdef HK_DIAG
   a.dbg = g_stem_dbg;
+#endif
   a.relu = relu;
   a.Ho = (H + 6 - 7) / 2 + 1;
   a.Wo = (W + 6 - 7) / 2 + 1;

@@ -52,6 +52,20 @@ gauss_targets_kernel(const float* __restrict__ uv, int H, int W, float denom, Ou
   }
 }
 
+// `normalize` of reference src/dataset.py:33-34 (F.normalize(x, p=1): L1 over dim 1 = the H axis of a (K,H,W) tensor, eps 1e-12),
+// applied by gauss_2d_batch(normalize_dist=True) (dataset.py:42-43; unused by the reference's own calls).  One thread per (k, w)
+// column: coalesced across the warp, sequential fp32 sum over h, then the divide; fp32 in, fp64 out (the `.double()` of :44).
+__global__ void l1_normalize_dim1_kernel(const float* __restrict__ x, int H, int W, double* __restrict__ out) {
+  const int k = blockIdx.y, w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  const float* src = x + (size_t)k * H * W + w;
+  float acc = 0.f;
+  for (int h = 0; h < H; ++h) acc = __fadd_rn(acc, fabsf(__ldg(src + (size_t)h * W)));
+  const float denom = fmaxf(acc, 1e-12f);
+  double* dst = out + (size_t)k * H * W + w;
+  for (int h = 0; h < H; ++h) dst[(size_t)h * W] = (double)__fdiv_rn(__ldg(src + (size_t)h * W), denom);
+}
+
 constexpr int kBceThreads = 256;
 constexpr int kBceMaxBlocks = 148 * 8;
 
@@ -192,6 +206,14 @@ int hk_gauss_targets(const float* uv, int B, int K, int H, int W, float sigma, v
   else
     gauss_targets_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(uv, H, W, denom, static_cast<float*>(out));
   return check_launch("gauss_targets_kernel");
+}
+
+int hk_l1_normalize_dim1(const float* x, int K, int H, int W, double* out, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(x && out, "hk_l1_normalize_dim1: null pointer");
+  HK_REQUIRE(K > 0 && H > 0 && W > 0 && K <= 65535, "hk_l1_normalize_dim1: bad shape");
+  l1_normalize_dim1_kernel<<<dim3(ceil_div(W, 128), K), 128, 0, as_stream(stream)>>>(x, H, W, out);
+  return check_launch("l1_normalize_dim1_kernel");
 }
 
 size_t hk_bce_workspace_bytes(long long n) {

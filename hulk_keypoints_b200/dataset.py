@@ -12,7 +12,6 @@ import os
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 from torch.utils.data import Dataset
 
 from . import ops
@@ -43,7 +42,7 @@ def gauss_2d_batch(width, height, sigma, U, V, normalize_dist=False):
     uv = torch.stack([U.float(), V.float()], dim=-1).unsqueeze(0).cuda()
     G32 = ops.gauss_targets(uv, int(height), int(width), float(sigma), torch.float32)[0]
     if normalize_dist:
-        return F.normalize(G32, p=1).double()  # reference dataset.py:33-34,42-43 (L1 over dim 1)
+        return ops.l1_normalize_dim1(G32)  # reference dataset.py:33-34,42-43: F.normalize(p=1) = L1 over dim 1 (H), then .double()
     return G32.double()
 
 

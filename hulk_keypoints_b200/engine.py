@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import ops
-from ._lib import HK_CONV_FFMA, HK_CONV_TCGEN05, require_device
+from ._lib import HK_CONV_FFMA, HK_CONV_TCGEN05, raw_write_generation, require_device
 
 BN_EPS_DEFAULT = 1e-5
 
@@ -103,8 +103,12 @@ class InferenceEngine:
 
     # ---- weights ----
     def _weights_key(self):
+        """(data_ptr, _version) of every parameter and buffer, plus the model's `_weights_generation`: kernels that write through raw
+        pointers (hk_adam_step, the TrainEngine's BatchNorm running-stat updates, CUDA-graph replays) never bump `_version`, so
+        FusedAdam.step and every TrainEngine forward bump the generation counter instead (KeypointsGauss.mark_weights_changed)."""
         net = self.model.resnet.resnet34_8s
-        return tuple((t.data_ptr(), t._version) for t in list(net.parameters()) + list(net.buffers()))
+        gen = (getattr(self.model, "_weights_generation", 0), raw_write_generation())
+        return gen + tuple((t.data_ptr(), t._version) for t in list(net.parameters()) + list(net.buffers()))
 
     def _pack_one(self, conv, bn, algo) -> _PackedConv:
         wdt = torch.bfloat16 if algo == HK_CONV_TCGEN05 else torch.float32

@@ -6,9 +6,10 @@ can import it unchanged.  Underneath:
 
   * eval() mode  -> the B200 engine (`engine.InferenceEngine`): hand-written sm_100a kernels through
                     the C ABI; BatchNorm folded; only the K live fc rows are computed.  CUDA only.
-  * train() mode -> a torch-autograd graph over the same parameters (batch-stat BatchNorm, K-row
-                    head).  The backbone backward is SURVEY.md §8(f1) "next"; the loss side
-                    (Gaussian targets, BCE forward/backward) already runs on our kernels (train_ops.py).
+  * train() mode -> the B200 training engine (`train_engine.TrainEngine`: bf16 tcgen05 forward, dgrad, wgrad,
+                    batch-stat BatchNorm, K-row head).  `train_backend = "autograd"` selects, explicitly, the
+                    torch-autograd graph over the same parameters (the fp32 checker of the parity tests);
+                    nothing falls back to it silently.
 
 The network definition restates reference src/resnet.py:117-196 + src/resnet_dilated.py:10-22
 (ResNet-34, output stride 8: layer3 dilation 2, layer4 dilation 4 on EVERY block incl. block 0).
@@ -138,12 +139,14 @@ def _reference_seeded_init(net: _DilatedResNet34) -> None:
 class KeypointsGauss(nn.Module):
     """Drop-in for reference `src/model.py:KeypointsGauss`.
 
-    Extra keyword (additive): `precision` = "bf16" (default; tcgen05 path, heatmaps within 2e-2 of
-    the fp32 reference) or "fp32" (CUDA-core correctness mode, within 1e-4 relative).  The env var
-    HULK_PRECISION overrides the default.
+    Extra keywords (additive): `precision` = "bf16" (default; tcgen05 path, heatmaps within 2e-2 of
+    the fp32 reference) or "fp32" (CUDA-core correctness mode, within 1e-4 relative); the env var
+    HULK_PRECISION overrides the default.  `pretrained` = path of a torchvision ResNet-34 checkpoint
+    (or "auto" / env HULK_PRETRAINED): the reference's real initialisation, which needs a download there.
     """
 
-    def __init__(self, num_keypoints, img_height=480, img_width=640, precision: Optional[str] = None):
+    def __init__(self, num_keypoints, img_height=480, img_width=640, precision: Optional[str] = None,
+                 pretrained: Optional[str] = None):
         super().__init__()
         self.num_keypoints = num_keypoints
         self.num_outputs = self.num_keypoints
@@ -159,6 +162,18 @@ class KeypointsGauss(nn.Module):
         _reference_seeded_init(self.resnet.resnet34_8s)
         self.sigmoid = nn.Sigmoid()
         self._engine = None
+        self._weights_generation = 0
+        # The reference ALWAYS starts from the ImageNet ResNet-34 (resnet_dilated.py:10-13, pretrained=True -> model_zoo download,
+        # resnet.py:237-238).  There is no network here, so that initialisation is opt-in: `pretrained=<path>` / HULK_PRETRAINED=<path>
+        # names a torchvision-format `resnet34-333f7ec4.pth`; "auto" looks in the torch hub cache.  Without it the backbone keeps the
+        # seeded random init (what the reference produces when its download is stubbed out) -- INTEGRATION.md §1.
+        src = pretrained if pretrained is not None else os.environ.get("HULK_PRETRAINED")
+        if src:
+            from .checkpoint import find_pretrained_resnet34, load_pretrained_backbone
+            path = find_pretrained_resnet34() if src == "auto" else src
+            if path is None:
+                raise FileNotFoundError("pretrained='auto': resnet34-333f7ec4.pth is not in the torch hub cache")
+            load_pretrained_backbone(self, path)
 
     # ---- engine plumbing ----
     def engine(self):
@@ -178,6 +193,11 @@ class KeypointsGauss(nn.Module):
             engines[key] = TrainEngine(self, batch, height, width)
         return engines[key]
 
+    def mark_weights_changed(self) -> None:
+        """Tell the inference engine that parameters or BatchNorm buffers were written behind torch's back (raw-pointer kernels:
+        FusedAdam.step, TrainEngine forwards, graph replays): the folded bf16 weights are rebuilt on the next eval-mode forward."""
+        self._weights_generation = getattr(self, "_weights_generation", 0) + 1
+
     def set_precision(self, precision: str) -> "KeypointsGauss":
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
@@ -187,17 +207,38 @@ class KeypointsGauss(nn.Module):
     def forward(self, x):
         if self.training:
             # B200 path: bf16 tensor-core forward now, tcgen05 dgrad/wgrad when autograd calls back (train_ops._EngineForward).
-            # The torch-autograd graph remains for CPU tensors (CPU tests of the host logic), the fp32 mode, odd shapes, and
-            # train_backend="autograd" (the parity checker).
-            if (x.is_cuda and self.precision == "bf16" and getattr(self, "train_backend", "hk") == "hk" and x.dim() == 4
-                    and x.shape[2] % 8 == 0 and x.shape[3] % 8 == 0 and min(x.shape[2:]) >= 32 and torch.is_grad_enabled()):
-                from .train_ops import engine_forward
-                return engine_forward(self, x)
-            return self._forward_autograd(x)
+            # There is NO silent fallback: the torch-autograd graph over the same parameters runs only when asked for with
+            # `model.train_backend = "autograd"` (the fp32 checker of the parity tests, and CPU tests of the host logic).
+            backend = getattr(self, "train_backend", "hk")
+            if backend == "autograd":
+                return self._forward_autograd(x)
+            if backend != "hk":
+                raise ValueError("train_backend must be 'hk' or 'autograd'")
+            why = self._train_engine_unsupported(x)
+            if why is not None:
+                raise RuntimeError(f"KeypointsGauss train-mode forward cannot run on the B200 training engine: {why}.  There is no "
+                                   "silent fallback; set model.train_backend = 'autograd' to use the torch autograd graph explicitly, "
+                                   "or call model.eval() for inference")
+            from .train_ops import engine_forward
+            return engine_forward(self, x)
         if not x.is_cuda:
             raise RuntimeError("KeypointsGauss inference runs on CUDA (B200) only: there is no CPU fallback; "
                                "move the model and the input with .cuda()")
         return self.engine().forward(x)
+
+    def _train_engine_unsupported(self, x):
+        """None when the training engine (bf16 tcgen05 forward/backward) takes this input, else the reason as text."""
+        if not x.is_cuda:
+            return "the input is a CPU tensor (the engine is CUDA-only)"
+        if self.precision != "bf16":
+            return "precision='fp32' has no training engine (fp32 training is not implemented on these kernels; see DESIGN.md §7)"
+        if x.dim() != 4 or x.shape[1] != 3:
+            return f"expected a (B,3,H,W) batch, got {tuple(x.shape)}"
+        if x.shape[2] % 8 or x.shape[3] % 8 or min(x.shape[2:]) < 32:
+            return f"H and W must be multiples of 8 and >= 32, got {tuple(x.shape[2:])}"
+        if not torch.is_grad_enabled():
+            return "autograd is disabled (train-mode forward under no_grad; use model.eval() for inference)"
+        return None
 
     def forward_logits(self, x):
         """Train-mode graph up to the upsampled logits of the K live channels (additive API; the fused

@@ -159,6 +159,33 @@ def argmax_decode(heat: torch.Tensor, yx: Optional[torch.Tensor] = None, maxval:
     return (yx, maxval) if want_max else yx
 
 
+def soft_argmax(heat: torch.Tensor, want_int: bool = True):
+    """Soft-argmax of every (H, W) map of a (..., H, W) fp32 CUDA tensor: Prediction.expectation (reference prediction.py:31-38,
+    transposed-ravel quirk included).  Returns (exp_xy fp64 (..., 2) = (E[x'], E[y']), exp_int int32 (..., 2) or None)."""
+    _need_cuda(heat)
+    if heat.dtype != torch.float32 or not heat.is_contiguous() or heat.dim() < 2:
+        raise ValueError("soft_argmax needs a contiguous fp32 tensor of (..., H, W) maps")
+    H, W = heat.shape[-2:]
+    maps = heat.numel() // (H * W)
+    lead = tuple(heat.shape[:-2])
+    exp_xy = torch.empty(lead + (2,), device=heat.device, dtype=torch.float64)
+    exp_int = torch.empty(lead + (2,), device=heat.device, dtype=torch.int32) if want_int else None
+    ws = torch.empty(max(8, int(lib().hk_soft_argmax_workspace_bytes(maps, H, W))), device=heat.device, dtype=torch.uint8)
+    check(lib().hk_soft_argmax(ptr(heat), maps, H, W, ptr(exp_xy), ptr(exp_int), ptr(ws), ws.numel(), stream_ptr()), "hk_soft_argmax")
+    return exp_xy, exp_int
+
+
+def l1_normalize_dim1(x: torch.Tensor) -> torch.Tensor:
+    """(K,H,W) fp32 -> fp64, L1-normalised over dim 1 (reference dataset.py:33-34, F.normalize(x, p=1))."""
+    _need_cuda(x)
+    if x.dtype != torch.float32 or x.dim() != 3 or not x.is_contiguous():
+        raise ValueError("l1_normalize_dim1 needs a contiguous (K,H,W) fp32 tensor")
+    K, H, W = x.shape
+    out = torch.empty((K, H, W), device=x.device, dtype=torch.float64)
+    check(lib().hk_l1_normalize_dim1(ptr(x), K, H, W, ptr(out), stream_ptr()), "hk_l1_normalize_dim1")
+    return out
+
+
 def gauss_targets(uv: torch.Tensor, H: int, W: int, sigma: float, out_dtype: torch.dtype = torch.float64,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """uv (B,K,2) = (x, y) -> (B,K,H,W) Gaussian targets (fp32 math, stored as out_dtype)."""

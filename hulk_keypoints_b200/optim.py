@@ -12,7 +12,7 @@ from typing import Iterable
 
 import torch
 
-from ._lib import check, lib, ptr, stream_ptr
+from ._lib import check, lib, note_raw_parameter_write, ptr, stream_ptr
 
 
 class FusedAdam:
@@ -88,3 +88,4 @@ class FusedAdam:
         check(lib().hk_adam_step(ptr(self.flat_param), ptr(self.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
                                  C.c_longlong(self.numel), C.c_float(self.lr), C.c_float(self.betas[0]), C.c_float(self.betas[1]),
                                  C.c_float(self.eps), C.c_float(self.weight_decay), self.step_count, stream_ptr()), "hk_adam_step")
+        note_raw_parameter_write()   # raw-pointer write: tensor versions do not move, eval engines must refold their weights

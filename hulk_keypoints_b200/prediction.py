@@ -52,12 +52,26 @@ class Prediction:
     def expectation(self, d):
         """Soft-argmax of one (H, W) map, as written in reference prediction.py:31-38: the map is flattened in the order of
         `d.T.ravel()` while the index arrays assume row-major order (x = i % W, y = i // W), so for H != W rows and columns mix;
-        kept as is for result parity (the reference computes it in `plot` and discards it).  Truncated to int."""
+        kept as is for result parity (the reference computes it in `plot` and discards it).  Truncated to int.
+        A CUDA tensor goes through the hk_soft_argmax reduction kernel (one pass over the map); a numpy array takes the
+        reference's own host formula (this method is a host-side helper there)."""
+        if isinstance(d, torch.Tensor) and d.is_cuda:
+            if d.dim() != 2:
+                raise ValueError("expectation takes one (H, W) map; use expectation_batch for (B,K,H,W)")
+            exp_xy, exp_int = ops.soft_argmax(d.detach().float().contiguous())
+            if bool(torch.isnan(exp_xy).any()):
+                raise ValueError("cannot convert float NaN to integer")   # what int(np.dot(...)) raises in the reference
+            return [int(v) for v in exp_int.tolist()]
         d = np.asarray(d)
         width, height = d.T.shape
         p = self.softmax(d.T.ravel())
         flat = np.arange(width * height)
         return [int(np.dot(p, flat % width)), int(np.dot(p, flat // width))]
+
+    def expectation_batch(self, heatmap):
+        """Additive API: soft-argmax of every map of a (B,K,H,W) CUDA heatmap in one launch pair -> (exp_xy fp64 (B,K,2) = (E[x'], E[y'])
+        with the reference's index convention, exp_int int32 (B,K,2) = its int() truncation), both on the GPU."""
+        return ops.soft_argmax(heatmap.detach().float().contiguous())
 
     def plot(self, img, heatmap, image_id=0, cls=None, classes=None):
         """Overlay visualisation (reference prediction.py:40-66): host-side cv2 drawing, out of the hot

@@ -127,6 +127,13 @@ class TrainEngine:
         # of the block's main branch until the residual add: it runs on a third stream with its own BN workspace (HK_AUX_STREAM=0: off).
         self.aux_stream = torch.cuda.Stream(device=dev) if os.environ.get("HK_AUX_STREAM", "1") != "0" else None
         self.bn_ws_aux = ops.bn_workspace(512, dev) if self.aux_stream is not None else None
+        # HK_WGRAD_STREAM=0 with the aux stream on: the downsample conv's weight gradient then runs on the aux stream concurrently with
+        # conv2's on the main stream, so it needs its own split-K partials buffer
+        self.wgrad_ws_aux = None
+        if self.aux_stream is not None and self.wgrad_stream is None:
+            wga = max(ops.conv_wgrad_workspace_bytes(B, c.H, c.W, c.cin, c.cout, c.k, c.stride, c.pad, c.dil)
+                      for b in self.blocks for c in (b[2],) if c is not None)
+            self.wgrad_ws_aux = torch.empty(wga, device=dev, dtype=torch.uint8)
         self.launches = 0
 
     # ------------------------------------------------------------------ helpers
@@ -230,9 +237,9 @@ class TrainEngine:
             torch.cuda.current_stream().wait_event(done)
             self._wgrad_pending = False
 
-    def _wgrad(self, c: _ConvT, x, dy) -> int:
-        self._on_wgrad_stream(lambda: ops.conv_wgrad(x, dy, self._g(c.conv.weight), k=c.k, stride=c.stride, pad=c.pad, dil=c.dil,
-                                                     ws=self.wgrad_ws))
+    def _wgrad(self, c: _ConvT, x, dy, ws=None) -> int:
+        ws = self.wgrad_ws if ws is None else ws
+        self._on_wgrad_stream(lambda: ops.conv_wgrad(x, dy, self._g(c.conv.weight), k=c.k, stride=c.stride, pad=c.pad, dil=c.dil, ws=ws))
         return 2
 
     def _dgrad(self, c: _ConvT, dy, dx, residual=None, scratch: str = "up") -> int:
@@ -336,7 +343,7 @@ class TrainEngine:
                 aux = self._fork_aux()
                 with torch.cuda.stream(aux if aux is not None else torch.cuda.current_stream()):
                     n += self._bn_bwd(ds, dm, False, dyd, ws=self.bn_ws_aux)
-                    n += self._wgrad(ds, x_in, dyd)
+                    n += self._wgrad(ds, x_in, dyd, ws=self.wgrad_ws_aux)
                     n += self._dgrad(ds, dyd, dxd, scratch="up_aux")
             n += self._wgrad(c2, a1, dy2)
             da1 = self._buf("da1", a1.shape)
@@ -369,7 +376,9 @@ class TrainEngine:
         return n
 
     def _key(self):
-        return (tuple(p.data_ptr() for p in self.params), None if self.target is None else (self.target.data_ptr(), self.target.dtype))
+        # sigma is passed by value to hk_bce_fwd_bwd, i.e. baked into a captured graph: a new sigma needs a new capture
+        return (tuple(p.data_ptr() for p in self.params), None if self.target is None else (self.target.data_ptr(), self.target.dtype),
+                self.sigma)
 
     def forward_backward(self, img: torch.Tensor, uv: Optional[torch.Tensor] = None, target: Optional[torch.Tensor] = None) -> torch.Tensor:
         """img (B,3,H,W) fp32 CUDA; labels uv (B,K,2) = (x,y) [Gaussian targets generated on the fly, dataset.py:36-44] or a
@@ -379,6 +388,7 @@ class TrainEngine:
             raise ValueError("pass exactly one of uv / target")
         if not img.is_cuda or tuple(img.shape) != (self.B, 3, self.H, self.W):
             raise ValueError(f"expected a CUDA image batch of shape {(self.B, 3, self.H, self.W)}, got {tuple(img.shape)} on {img.device}")
+        self.model.mark_weights_changed()   # BatchNorm running stats are advanced through raw pointers (tensor versions do not move)
         with torch.no_grad():
             self.x.copy_(img)
             if uv is not None:
@@ -411,6 +421,8 @@ class TrainEngine:
     # ------------------------------------------------------------------ split step: the caller owns the loss (unmodified train.py)
     def _run(self, name: str, fn, name_key: Optional[str] = None) -> None:
         """Eager, or capture-once / replay of one of the split graphs.  `name` "fwd" marks graphs that advance the BN buffers."""
+        if name == "fwd":
+            self.model.mark_weights_changed()   # BatchNorm running stats move (raw-pointer writes)
         if not self.use_cuda_graph:
             fn()
             return

@@ -139,12 +139,25 @@ HK_API size_t hk_argmax_workspace_bytes(int B, int K, int H, int W);
 HK_API int hk_argmax_decode(const float* heat, int B, int K, int H, int W, int32_t* yx, float* maxval_or_null,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* Soft-argmax of every (H, W) map: Prediction.expectation, src/prediction.py:31-38 (called at :45), softmax (:26-29) included.
+ * The reference's flattening quirk is kept: the map is flattened column-major (`d.T.ravel()`, flat index i = c*H + r) while the
+ * index arrays assume row-major order (x' = i % W, y' = i // W).  One pass over the heatmaps (online softmax; fp32 exp, fp64 sums).
+ *   heat (maps, H, W) fp32 contiguous (maps = B*K) ; exp_xy (maps, 2) fp64 = (E[x'], E[y']) ;
+ *   exp_int_or_null (maps, 2) int32 = the reference's `int(...)` truncation ; ws : hk_soft_argmax_workspace_bytes bytes. */
+HK_API size_t hk_soft_argmax_workspace_bytes(int maps, int H, int W);
+HK_API int hk_soft_argmax(const float* heat, int maps, int H, int W, double* exp_xy, int32_t* exp_int_or_null, void* ws,
+                          size_t ws_bytes, void* stream);
+
 /* ---- training-side elementwise / reduction kernels ----
  * Gaussian heatmap targets.  Replaces gauss_2d_batch, src/dataset.py:36-44 (fp32 math, widened to f64).
  *   uv (B,K,2) fp32 = (x, y) ; out (B,K,H,W) in out_dtype (HK_F64 drop-in, HK_F32 compact)
  */
 HK_API int hk_gauss_targets(const float* uv, int B, int K, int H, int W, float sigma, void* out, int out_dtype,
                      void* stream);
+
+/* `normalize` of src/dataset.py:33-34 as applied by gauss_2d_batch(normalize_dist=True) (dataset.py:42-44): L1-normalise a (K,H,W)
+ * fp32 tensor over dim 1 (F.normalize(x, p=1), eps 1e-12) and widen to fp64. */
+HK_API int hk_l1_normalize_dim1(const float* x, int K, int H, int W, double* out, void* stream);
 
 /* BCE(mean) forward + backward through the sigmoid.  Replaces train.py:21,25 (pred.double(), nn.BCELoss)
  * and the autograd of train.py:35 down to the logits (model.py:21).

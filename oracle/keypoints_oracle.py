@@ -272,6 +272,34 @@ def soft_expectation(d: np.ndarray) -> List[int]:
     return [int(np.dot(p, idx % width)), int(np.dot(p, idx // width))]
 
 
+def soft_expectation_raw(d: np.ndarray) -> np.ndarray:
+    """`soft_expectation` before the int() truncation: float64 (E[x'], E[y']) with the reference's arithmetic (prediction.py:26-38:
+    softmax in the map's dtype, dot with int64 index arrays in float64)."""
+    d = np.asarray(d)
+    width, height = d.T.shape
+    flat = d.T.ravel()
+    e = np.exp(flat - np.max(flat))
+    p = e / e.sum()
+    idx = np.arange(width * height)
+    return np.array([np.dot(p, idx % width), np.dot(p, idx // width)], dtype=np.float64)
+
+
+def clip_labels(label_xy: np.ndarray, height: int, width: int) -> np.ndarray:
+    """Label handling of reference src/dataset.py:63-66: (K,2) = (x, y); x clipped to [0, W-1], y to [0, H-1]."""
+    lab = np.array(label_xy, dtype=np.float64).reshape(-1, 2)
+    lab[:, 0] = np.clip(lab[:, 0], 0, width - 1)
+    lab[:, 1] = np.clip(lab[:, 1], 0, height - 1)
+    return lab
+
+
+def l1_normalize_dim1(g: np.ndarray) -> np.ndarray:
+    """`normalize` of reference src/dataset.py:33-34 (F.normalize(x, p=1): L1 over dim 1, eps 1e-12) on a (K,H,W) float32 array,
+    widened to float64 like dataset.py:44."""
+    g = np.asarray(g, dtype=np.float32)
+    denom = np.maximum(np.abs(g).sum(axis=1, keepdims=True, dtype=np.float32), np.float32(1e-12))
+    return (g / denom).astype(np.float64)
+
+
 def gauss_targets(uv: np.ndarray, height: int, width: int, sigma: float) -> np.ndarray:
     """`gauss_2d_batch` (dataset.py:36-44) for a batch: uv (B,K,2)=(x,y) -> (B,K,H,W) float64.
 

@@ -37,6 +37,13 @@ def golden():
     return arrays, meta
 
 
+@pytest.fixture(scope="session")
+def golden2():
+    """Round-2 goldens from the unmodified reference (oracle/make_golden_v2.py): KeypointsDataset round trip, normalize_dist,
+    Prediction.expectation before truncation."""
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_v2.npz")))
+
+
 def sd_digest(sd) -> str:
     import hashlib
 

@@ -94,6 +94,84 @@ def test_dropin_gauss_2d_batch(golden):
     assert _ulp_close(g.cpu().numpy(), arrays["gauss_small"])
 
 
+def test_gauss_normalize_dist_vs_reference_golden(golden2):
+    """gauss_2d_batch(normalize_dist=True) (dataset.py:33-34,42-44) on the hk_l1_normalize_dim1 kernel vs the reference's output."""
+    import hulk_keypoints_b200 as hk
+    uv = golden2["gauss_norm_uv"]
+    g = hk.gauss_2d_batch(64, 48, 3, torch.from_numpy(uv[:, 0].copy()), torch.from_numpy(uv[:, 1].copy()), normalize_dist=True)
+    assert g.is_cuda and g.dtype == torch.float64 and g.shape == (4, 48, 64)
+    assert np.allclose(g.cpu().numpy(), golden2["gauss_norm"], rtol=4e-6, atol=1e-12)
+
+
+# ------------------------------------------------------------------ soft-argmax (Prediction.expectation)
+def test_soft_argmax_vs_reference_golden_and_oracle(golden2):
+    """hk_soft_argmax vs the reference's Prediction.expectation (golden, before and after its int()) and the oracle; the
+    transposed-ravel quirk (prediction.py:32: d.T.ravel() against row-major index arrays) is part of the expected result."""
+    import hulk_keypoints_b200 as hk
+    pred = hk.Prediction(hk.KeypointsGauss(4), 4, 48, 64, use_cuda=True)
+    for i in range(6):
+        d = golden2[f"exp_map_{i}"]
+        t = torch.from_numpy(d).to(dev())
+        raw, ints = ops.soft_argmax(t)
+        assert raw.shape == (2,) and raw.dtype == torch.float64 and ints.dtype == torch.int32
+        ref = golden2[f"exp_raw_{i}"]
+        assert np.allclose(raw.cpu().numpy(), ref, rtol=1e-6, atol=1e-6), (i, raw.cpu().numpy(), ref)
+        if np.all(np.abs(ref - np.round(ref)) > 1e-4):            # away from an integer boundary the truncation agrees too
+            assert ints.cpu().tolist() == list(golden2[f"exp_int_{i}"])
+            assert pred.expectation(t) == list(golden2[f"exp_int_{i}"])          # CUDA tensor -> kernel
+        assert pred.expectation(d) == list(golden2[f"exp_int_{i}"])              # numpy -> the reference's host formula
+
+
+def test_soft_argmax_batched_full_resolution():
+    """(B,K,480,640) in one launch pair vs the oracle map by map; saturated / constant maps; ragged width (scalar path)."""
+    g = torch.Generator().manual_seed(5)
+    heat = torch.rand(2, 4, 480, 640, generator=g) * 0.2
+    heat[0, 0, 100, 200] = 0.95
+    heat[0, 1] = 1.0                       # constant map: uniform softmax
+    heat[1, 2, 479, 639] = 1.0
+    heat[1, 3] *= 50.0                     # wide dynamic range: exp underflows away from the maximum
+    import hulk_keypoints_b200 as hk
+    pred = hk.Prediction(hk.KeypointsGauss(4), 4, 480, 640, use_cuda=True)
+    raw, ints = pred.expectation_batch(heat.to(dev()))
+    assert raw.shape == (2, 4, 2)
+    for b in range(2):
+        for k in range(4):
+            ref = O.soft_expectation_raw(heat[b, k].numpy())
+            assert np.allclose(raw[b, k].cpu().numpy(), ref, rtol=2e-6, atol=1e-4), (b, k, raw[b, k].tolist(), ref)
+    assert torch.equal(ints.cpu(), raw.cpu().to(torch.int32))
+    odd = torch.rand(3, 37, 53, generator=g)
+    raw_odd, _ = ops.soft_argmax(odd.to(dev()))
+    for j in range(3):
+        assert np.allclose(raw_odd[j].cpu().numpy(), O.soft_expectation_raw(odd[j].numpy()), rtol=2e-6, atol=1e-5)
+
+
+# ------------------------------------------------------------------ KeypointsDataset (reference src/dataset.py:52-79)
+def test_keypoints_dataset_roundtrip_vs_reference_golden(golden2, tmp_path):
+    """A temporary folder of `%05d.jpg` + `%05d.npy` files through hk.KeypointsDataset against what the unmodified reference class
+    returned for the same files (oracle/make_golden_v2.py): label clipping, (x, y) order, labels on the GPU, the fp32 host image
+    tensor (3,H,W) = ToTensor(cv2.imread), the fp64 CUDA Gaussians (K,H,W)."""
+    import hulk_keypoints_b200 as hk
+    img_dir, lab_dir = tmp_path / "images", tmp_path / "keypoints"
+    img_dir.mkdir(); lab_dir.mkdir()
+    for i in range(2):
+        np.save(str(lab_dir / ("%05d.npy" % i)), golden2[f"ds_raw_label_{i}"])
+        (img_dir / ("%05d.jpg" % i)).write_bytes(golden2[f"ds_jpeg_{i}"].tobytes())
+    ds = hk.KeypointsDataset(str(img_dir), str(lab_dir), 4, 48, 64, hk.transform, gauss_sigma=3)
+    assert len(ds) == 2
+    for i in range(2):
+        assert ds.labels[i].is_cuda and ds.labels[i].dtype == torch.float64
+        assert np.array_equal(ds.labels[i].cpu().numpy(), golden2[f"ds_clipped_label_{i}"])
+        img, gauss = ds[i]
+        assert not img.is_cuda and img.dtype == torch.float32 and tuple(img.shape) == (3, 48, 64)
+        assert np.array_equal(img.numpy(), golden2[f"ds_img_{i}"])               # same cv2 build decodes the same JPEG bytes
+        assert gauss.is_cuda and gauss.dtype == torch.float64 and tuple(gauss.shape) == (4, 48, 64)
+        assert _ulp_close(gauss.cpu().numpy(), golden2[f"ds_gauss_{i}"])
+    # the DataLoader of train.py:63 (shuffle, num_workers=0) collates (img CPU fp32, gauss CUDA fp64) batches
+    loader = torch.utils.data.DataLoader(ds, batch_size=2, shuffle=False, num_workers=0)
+    imgs, gausses = next(iter(loader))
+    assert tuple(imgs.shape) == (2, 3, 48, 64) and tuple(gausses.shape) == (2, 4, 48, 64) and gausses.is_cuda
+
+
 # ------------------------------------------------------------------ BCE
 def test_bce_vs_golden_bit_exact_grad(golden):
     arrays, _ = golden

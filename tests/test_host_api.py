@@ -52,6 +52,7 @@ def test_train_mode_forward_matches_oracle_on_cpu():
     torch.manual_seed(0)
     m = hk.KeypointsGauss(4)
     m.train()
+    m.train_backend = "autograd"   # the explicit torch-autograd checker graph (the engine is CUDA-only; nothing falls back silently)
     x = rand_img(6, 2, 64, 96)
     sd = O.init_state_dict(0)
     with torch.no_grad():
@@ -69,6 +70,7 @@ def test_train_mode_forward_matches_oracle_on_cpu():
 def test_dead_fc_rows_get_zero_grad():
     m = hk.KeypointsGauss(4)
     m.train()
+    m.train_backend = "autograd"
     m(rand_img(1, 1, 32, 32)).sum().backward()
     g = m.resnet.resnet34_8s.fc.weight.grad
     assert g[:4].abs().sum() > 0 and g[4:].abs().sum() == 0
@@ -77,6 +79,17 @@ def test_dead_fc_rows_get_zero_grad():
 def test_eval_forward_refuses_cpu():
     m = hk.KeypointsGauss(4).eval()
     with pytest.raises(RuntimeError, match="CUDA"):
+        m(rand_img(1, 1, 32, 32))
+
+
+def test_train_forward_never_falls_back_silently():
+    """train() mode is engine-backed; a CPU tensor, the fp32 mode or an odd shape raise instead of quietly running torch/cuDNN."""
+    m = hk.KeypointsGauss(4).train()
+    with pytest.raises(RuntimeError, match="silent"):
+        m(rand_img(1, 1, 32, 32))
+    assert "CPU tensor" in m._train_engine_unsupported(torch.zeros(1, 3, 32, 32))
+    m.train_backend = "cudnn"
+    with pytest.raises(ValueError):
         m(rand_img(1, 1, 32, 32))
 
 
@@ -195,6 +208,24 @@ def test_checkpoint_roundtrip_and_pretrained_import(tmp_path):
     bad.pop("bn1.weight")
     with pytest.raises(KeyError):
         checkpoint.load_pretrained_backbone(m2, bad)
+    # the file the reference downloads (resnet34-333f7ec4.pth) predates `num_batches_tracked`: an old-format dict loads, and a bad
+    # dict leaves the model untouched (validation happens before the first copy)
+    old_fmt = {k: v for k, v in tv.state_dict().items() if not k.endswith("num_batches_tracked")}
+    m3 = hk.KeypointsGauss(4)
+    assert checkpoint.load_pretrained_backbone(m3, old_fmt) == len(old_fmt) - 2
+    assert torch.equal(m3.state_dict()[checkpoint.PREFIX + "conv1.weight"], tv.state_dict()["conv1.weight"])
+    m4 = hk.KeypointsGauss(4)
+    before = sd_digest(m4.state_dict())
+    wrong_shape = dict(old_fmt)
+    wrong_shape["layer4.2.conv2.weight"] = torch.zeros(512, 512, 1, 1)
+    with pytest.raises(ValueError):
+        checkpoint.load_pretrained_backbone(m4, wrong_shape)
+    assert sd_digest(m4.state_dict()) == before
+    # the drop-in constructor reproduces the reference's real initialisation when given the file
+    ppath = str(tmp_path / "resnet34-333f7ec4.pth")
+    torch.save(old_fmt, ppath)
+    m5 = hk.KeypointsGauss(4, pretrained=ppath)
+    assert torch.equal(m5.state_dict()[checkpoint.PREFIX + "layer1.0.conv1.weight"], tv.state_dict()["layer1.0.conv1.weight"])
 
 
 def test_conv_flops_per_image_matches_oracle_and_survey():

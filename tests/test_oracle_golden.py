@@ -178,3 +178,24 @@ def test_soft_expectation_matches_reference_golden():
         assert pred.expectation(d) == c["expectation"]
         sm = pred.softmax(d.ravel().astype(np.float64))
         assert abs(sm.max() - c["softmax_max"]) < 1e-15 and abs(sm.sum() - c["softmax_sum"]) < 1e-15
+
+
+def test_round2_goldens_dataset_normalize_expectation(golden2):
+    """Oracle restatements against outputs of the unmodified reference (tests/golden/golden_v2.npz, oracle/make_golden_v2.py):
+    KeypointsDataset's label clipping and Gaussians (dataset.py:63-66,72-76), normalize_dist (dataset.py:33-34,42-44) and
+    Prediction.expectation before its int() (prediction.py:26-38)."""
+    g = golden2
+    for i in range(2):
+        clipped = O.clip_labels(g[f"ds_raw_label_{i}"], 48, 64)
+        assert np.array_equal(clipped, g[f"ds_clipped_label_{i}"])
+        assert np.array_equal(O.gauss_targets(clipped[None].astype(np.float32), 48, 64, 3.0)[0], g[f"ds_gauss_{i}"])
+        img = g[f"ds_img_{i}"]
+        assert img.dtype == np.float32 and img.shape == (3, 48, 64) and 0.0 <= img.min() and img.max() <= 1.0
+    gn = O.l1_normalize_dim1(O.gauss_targets(g["gauss_norm_uv"][None].astype(np.float32), 48, 64, 3.0)[0].astype(np.float32))
+    assert np.allclose(gn, g["gauss_norm"], rtol=2e-6, atol=1e-12)
+    colsum = g["gauss_norm"].sum(axis=1)
+    assert np.allclose(colsum[:, 5:16][0], 1.0, atol=1e-5)                   # (k, :, w) columns near a keypoint sum to one
+    for i in range(6):
+        raw = O.soft_expectation_raw(g[f"exp_map_{i}"])
+        assert np.array_equal(raw, g[f"exp_raw_{i}"])
+        assert O.soft_expectation(g[f"exp_map_{i}"]) == list(g[f"exp_int_{i}"])

@@ -4,6 +4,9 @@ MMAs run on stale shared memory -- no L2->SM operand traffic), 4 (no epilogue bo
 so (t0 - t2) / t0 bounds what removing ALL operand traffic could give; a 4-CTA multicast cluster removes a quarter of it."""
 import os, subprocess, sys, threading, time
 import torch
+# needs the diagnostics build of the library (timeline stamps / HK_TC2_DEBUG switches are compiled out of the shipped .so):
+#   python -m hulk_keypoints_b200.build --diag   ->  hulk_keypoints_b200/libhulk_sm100_diag.so
+os.environ.setdefault("HK_LIB_PATH", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hulk_keypoints_b200", "libhulk_sm100_diag.so"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hulk_keypoints_b200 import ops
 dev = torch.device("cuda:0")

@@ -1,6 +1,9 @@
 """Phase timeline of the stem kernel's CTA 0 (GPU box).  Prints per-tile cycle deltas between phase stamps."""
 import ctypes as C, os, sys
 import torch
+# needs the diagnostics build of the library (timeline stamps / HK_TC2_DEBUG switches are compiled out of the shipped .so):
+#   python -m hulk_keypoints_b200.build --diag   ->  hulk_keypoints_b200/libhulk_sm100_diag.so
+os.environ.setdefault("HK_LIB_PATH", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hulk_keypoints_b200", "libhulk_sm100_diag.so"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hulk_keypoints_b200 import _lib, ops
 lib = _lib.lib()

@@ -1,6 +1,9 @@
 """Which side bounds the 2-CTA conv mainloop?  Times each layer shape with HK_TC2_DEBUG = 0 (normal), 1 (no MMA), 2 (no TMA)."""
 import os, sys
 import torch
+# needs the diagnostics build of the library (timeline stamps / HK_TC2_DEBUG switches are compiled out of the shipped .so):
+#   python -m hulk_keypoints_b200.build --diag   ->  hulk_keypoints_b200/libhulk_sm100_diag.so
+os.environ.setdefault("HK_LIB_PATH", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hulk_keypoints_b200", "libhulk_sm100_diag.so"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hulk_keypoints_b200 import ops
 dev = torch.device("cuda:0")
