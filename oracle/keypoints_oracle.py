@@ -218,6 +218,32 @@ def forward(sd, x: torch.Tensor, num_keypoints: int = 4, train: bool = False,
         return heatmaps_from_logits(logits_lowres(sd, feat, num_keypoints), x.shape[2:])
 
 
+def train_step_loss_and_grads(sd, x: torch.Tensor, uv: np.ndarray, num_keypoints: int = 4, sigma: float = 8.0):
+    """One training step's loss and parameter gradients as reference train.py:18-26,35 computes them: train-mode forward
+    (batch-statistic BatchNorm, running stats advanced), `pred.double()`, `nn.BCELoss()(pred, gt_gauss)` with the float64 Gaussian
+    targets of dataset.py:36-44, `loss.backward()` -- torch CPU autograd over the functional restatement above.
+
+    Returns (loss float, grads {state_dict key: tensor} for every parameter, new_stats {running_mean/var key: tensor}).  The head is
+    evaluated on the K live fc rows only (per-channel ops: identical values); the 996 dead rows receive exactly zero gradient, as in
+    the reference where the `[:, :K]` slice (model.py:21) cuts them off."""
+    work = OrderedDict()
+    params = {}
+    for k, v in sd.items():
+        if v.dtype.is_floating_point and "running_" not in k:
+            params[k] = v.detach().clone().requires_grad_(True)
+            work[k] = params[k]
+        else:
+            work[k] = v.detach().clone()
+    stats: dict = {}
+    feat = backbone_features(work, x, True, stats)
+    heat = heatmaps_from_logits(logits_lowres(work, feat, num_keypoints), x.shape[2:])
+    gt = torch.from_numpy(gauss_targets(np.asarray(uv), x.shape[2], x.shape[3], sigma))
+    loss = F.binary_cross_entropy(heat.double(), gt)          # == nn.BCELoss()(pred.double(), gt)
+    loss.backward()
+    grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()}
+    return float(loss.item()), grads, stats
+
+
 def forward_as_written(sd, x: torch.Tensor, num_keypoints: int = 4) -> torch.Tensor:
     return forward(sd, x, num_keypoints, as_written=True)
 

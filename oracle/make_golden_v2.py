@@ -7,6 +7,8 @@ TEST INFRASTRUCTURE ONLY.  Contents:
     outside the image: the JPEG bytes, the raw labels, the clipped labels the reference stores (x clipped to [0, W-1], y to [0, H-1],
     (x, y) order), the image tensor `transform(cv2.imread(path))` and the float64 Gaussians `__getitem__` returns (sigma = 3).
   * `gauss_2d_batch(..., normalize_dist=True)` (src/dataset.py:33-34,42-44).
+  * one training step as written (train.py:18-26,35) on seed-0 weights, a (2,3,64,96) batch: float64 loss and a sample of the
+    parameter gradients (autograd through the unmodified reference modules).
   * `Prediction.expectation` BEFORE the int() truncation on the maps of make_golden_prediction.maps() plus a 48x64 peaked map, so the
     hk_soft_argmax kernel can be compared in floating point.
 """
@@ -90,6 +92,25 @@ def main():
         out[f"exp_map_{i}"] = d
         out[f"exp_raw_{i}"] = raw
         out[f"exp_int_{i}"] = np.array(p.expectation(d), dtype=np.int64)
+    # one training step of the reference as written (train.py:18-26,35): model.forward(img).double() -> nn.BCELoss -> backward
+    model = reference_loader.build_reference_model(0, K, 64, 96)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 3, 64, 96, generator=g)
+    uv = np.array([[[10, 20], [30, 40], [50, 10], [90, 60]], [[5, 5], [60, 30], [20, 50], [80, 8]]], dtype=np.float64)
+    gt = torch.stack([ds.gauss_2d_batch(96, 64, 8, torch.tensor(uv[b, :, 0]), torch.tensor(uv[b, :, 1])) for b in range(2)])
+    model.train()
+    loss = torch.nn.BCELoss()(model.forward(x).double(), gt)
+    loss.backward()
+    out["step_uv"] = uv
+    out["step_loss"] = np.array(loss.item())
+    named = dict(model.named_parameters())
+    pre = "resnet.resnet34_8s."
+    for short in ("conv1.weight", "bn1.weight", "layer1.0.conv1.weight", "layer2.0.downsample.0.weight", "layer3.0.bn1.bias",
+                  "layer4.2.bn2.weight", "fc.bias"):
+        out["step_grad_" + short] = named[pre + short].grad.numpy().copy()
+    out["step_grad_fc.weight_live"] = named[pre + "fc.weight"].grad[:K].numpy().copy()
+    out["step_grad_fc.weight_dead_abs_sum"] = np.array(named[pre + "fc.weight"].grad[K:].abs().sum().item())
+    out["step_grad_l4_conv2_sub"] = named[pre + "layer4.2.conv2.weight"].grad[::16, ::16].numpy().copy()
     path = os.path.join(ROOT, "tests", "golden", "golden_v2.npz")
     np.savez_compressed(path, **out)
     print(path, {k: v.shape for k, v in out.items()})

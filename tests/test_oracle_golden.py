@@ -199,3 +199,24 @@ def test_round2_goldens_dataset_normalize_expectation(golden2):
         raw = O.soft_expectation_raw(g[f"exp_map_{i}"])
         assert np.array_equal(raw, g[f"exp_raw_{i}"])
         assert O.soft_expectation(g[f"exp_map_{i}"]) == list(g[f"exp_int_{i}"])
+
+
+def test_train_step_loss_and_grads_match_reference_golden(golden2, sd0):
+    """oracle.train_step_loss_and_grads (the checker of the GPU TrainEngine tests) against autograd through the UNMODIFIED reference
+    modules (train.py:18-26,35; golden_v2.npz): loss bit-equal, gradients to 1e-5 of each tensor's scale, dead fc rows exactly 0."""
+    g = golden2
+    x = torch.rand(2, 3, 64, 96, generator=torch.Generator().manual_seed(3))
+    loss, grads, stats = O.train_step_loss_and_grads(sd0, x, g["step_uv"], 4, 8.0)
+    assert abs(loss - float(g["step_loss"])) <= 1e-12 * abs(loss)
+    for key in g:
+        if not key.startswith("step_grad_") or key.endswith("_sum") or key.endswith("_live") or key.endswith("_sub"):
+            continue
+        ref = g[key]
+        got = grads[O.PREFIX + key[len("step_grad_"):]].numpy()
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max() + 1e-12, key
+    fcw = grads[O.PREFIX + "fc.weight"].numpy()
+    assert np.abs(fcw[:4] - g["step_grad_fc.weight_live"]).max() <= 1e-5 * np.abs(g["step_grad_fc.weight_live"]).max()
+    assert np.abs(fcw[4:]).sum() == 0.0 == float(g["step_grad_fc.weight_dead_abs_sum"])
+    l4 = grads[O.PREFIX + "layer4.2.conv2.weight"].numpy()[::16, ::16]
+    assert np.abs(l4 - g["step_grad_l4_conv2_sub"]).max() <= 1e-5 * np.abs(g["step_grad_l4_conv2_sub"]).max()
+    assert len(stats) == 72      # running_mean + running_var of the 36 BatchNorms
