@@ -51,7 +51,7 @@ def synth_batch(gen, B, H, W, K=4):
 
 @pytest.fixture(scope="module")
 def sd_trained():
-    """F-trn, small: 200 deterministic steps of the product's own B200 train step (TrainEngine + FusedAdam) on synthetic discs
+    """F-trn, small: 300 deterministic steps of the product's own B200 train step (TrainEngine + FusedAdam) on synthetic discs
     (hulk_keypoints_b200/synth.py), so heatmaps are peaked and 'keypoints within 1 px' means something.  Its SHA-256 is pinned in
     tests/test_gpu_parity.py; the config-sized fixtures live there too."""
     from hulk_keypoints_b200 import synth
