@@ -15,7 +15,8 @@ argmax decode for `--batch` (64) images of 480x640 (BASELINE.json configs[1]).  
              host -- every step, inside the timed region (copies double-buffered against compute).
   roofline   the dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOPs of its launches in one step /
              their CUDA-event time, against MEASURED_PEAKS.json's dense bf16 peak.
-  cpu_baseline / --impl reference: the oracle port (torch CPU restatement of the reference) on the host cores.
+  cpu_baseline / --impl reference: the reference's own CPU path on the host cores -- the unmodified reference classes staged in
+             oracle/_ref/ by build() (kind "reference"), else the oracle port (kind "port").
   roofline_hbm_kernels / train_step: informational extras -- the memory-bound kernels against the measured copy bandwidth, and
              (N=1, default workload) ms per training step at per-GPU batch 4 / 32 (BASELINE configs[3]; bench_train.py is the full tool).
 """
@@ -61,6 +62,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true",
                     help="skip the secondary measurement (BASELINE configs[3]: one training step per iteration, per-GPU batch 4 and 32, N=1 only)")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 3 s sustained loop")
+    ap.add_argument("--no-config3", action="store_true", help="skip the BASELINE configs[2] extra (4096 images split across the ranks)")
     ap.add_argument("--breakdown", default="", help="write the per-launch timing table to this JSON file")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay (profiling)")
     ap.add_argument("--profile-mode", action="store_true",
@@ -140,25 +143,47 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------------- CPU arm
 class CpuReference:
-    """Oracle port (torch CPU restatement of the reference's eval forward + numpy argmax decode), B=1 per call as
-    analysis.py does, all host threads.  Weights and inputs are prepared once, outside any timed region."""
+    """The reference's CPU path, B=1 per call as analysis.py does, all host threads.  Weights and inputs are prepared once, outside
+    any timed region.  kind "reference": the UNMODIFIED reference classes (src/model.py KeypointsGauss + src/prediction.py
+    Prediction.predict + the numpy argmax of prediction.py:46) from oracle/_ref/, staged there by __graft_entry__.build() in the
+    build container (git-ignored; it travels to the GPU box with the snapshot), eval() + no_grad (BASELINE configs[0]).
+    kind "port": oracle/keypoints_oracle.py in the reference's as-written op order, when oracle/_ref/ is absent."""
 
     def __init__(self, height: int, width: int):
-        from oracle import keypoints_oracle as O
-
-        self.O = O
         self.cores = os.cpu_count() or 1
         torch.set_num_threads(self.cores)
-        self.sd = O.init_state_dict(0)
         g = torch.Generator().manual_seed(1000)
         self.imgs = [torch.rand(1, 3, height, width, generator=g) for _ in range(2)]
+        ref_root = os.path.join(ROOT, "oracle", "_ref")
+        self.kind = "port"
+        if os.path.isfile(os.path.join(ref_root, "src", "model.py")):
+            try:
+                os.environ["HULK_REFERENCE_ROOT"] = ref_root
+                from oracle import reference_loader as RL
+                model = RL.build_reference_model(0, K_KEYPOINTS, height, width).eval()
+                _, pr = RL.reference_modules()
+                self.pred = pr.Prediction(model, K_KEYPOINTS, height, width, False)
+                self.kind = "reference"
+            except Exception as exc:  # noqa: BLE001 -- fall back to the port, say why
+                print(f"[bench] oracle/_ref present but not importable ({type(exc).__name__}: {exc}); timing the oracle port", file=sys.stderr)
+        if self.kind == "port":
+            from oracle import keypoints_oracle as O
+            self.O = O
+            self.sd = O.init_state_dict(0)
 
     def run(self, n_images: int) -> float:
         """Process n_images; returns elapsed seconds."""
+        import numpy as np
         t0 = time.perf_counter()
         for i in range(n_images):
-            # as_written=True: the reference's literal op order (1000-channel fc and upsample, then slice, model.py:21)
-            self.O.argmax_decode(self.O.forward(self.sd, self.imgs[i % 2], K_KEYPOINTS, as_written=True).numpy())
+            if self.kind == "reference":
+                with torch.no_grad():
+                    heat = self.pred.predict(self.imgs[i % 2][0]).detach().cpu().numpy()       # analysis.py:40-41
+                for k in range(K_KEYPOINTS):
+                    np.unravel_index(heat[0][k].argmax(), heat[0][k].shape)                    # prediction.py:46
+            else:
+                # as_written=True: the reference's literal op order (1000-channel fc and upsample, then slice, model.py:21)
+                self.O.argmax_decode(self.O.forward(self.sd, self.imgs[i % 2], K_KEYPOINTS, as_written=True).numpy())
         return time.perf_counter() - t0
 
 
@@ -182,8 +207,9 @@ def run_reference_arm(args, rank):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"KeypointsGauss eval forward + argmax decode, {args.height}x{args.width}, K={K_KEYPOINTS}, "
-                               f"oracle port of the reference (as-written op order: 1000-channel head) on host CPU (bounded sample)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                               + ("the unmodified reference classes (oracle/_ref)" if ref.kind == "reference" else
+                                  "oracle port of the reference (as-written op order: 1000-channel head)") + " on host CPU (bounded sample)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": ref.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -253,15 +279,15 @@ def per_launch_breakdown(engine, plan, decode=True):
     rows = []
     stream = torch.cuda.current_stream()
 
-    def timed(name, flops, fn, reps=3):
+    def timed(name, flops, fn, reps=5):
         fn()
-        best = None
+        ts = []
         for _ in range(reps):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream); fn(); b.record(stream); b.synchronize()
-            t = a.elapsed_time(b)
-            best = t if best is None else min(best, t)
-        rows.append({"name": name, "ms": best, "flops": flops, "algo": None, "bytes": 0.0})
+            ts.append(a.elapsed_time(b))
+        # the MEAN over the repetitions is what the roofline uses (the minimum is kept for reference only)
+        rows.append({"name": name, "ms": sum(ts) / len(ts), "ms_min": min(ts), "flops": flops, "algo": None, "bytes": 0.0})
 
     B = plan.B
     if engine._stem_w_tc is not None:
@@ -363,6 +389,25 @@ def run_ours(args, rank, world, local_rank):
                               "gpu_launches_per_step": launches_per_step}), flush=True)
         return
 
+    # ---------------- sustained: the same loop for >= 3 s (thermal / power steady state) ----------------
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(args.steps, int(3.2e3 / max(dev_ms / args.steps, 1e-3)) + 1)
+        sampler2 = ClockSampler(local_rank)
+        barrier()
+        if rank == 0:
+            sampler2.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n_sus):
+            engine.run_plan(plan, decode=True)
+        s1.record()
+        s1.synchronize()
+        barrier()
+        sus_ms = max_over_ranks(s0.elapsed_time(s1))
+        sustained = {"value": world * B * n_sus / (sus_ms * 1e-3), "unit": UNIT, "steps": n_sus, "seconds": sus_ms * 1e-3,
+                     "ms_per_step": sus_ms / n_sus, "clocks": sampler2.stop() if rank == 0 else None}
+
     # ---------------- end to end through the public API, host buffers ----------------
     copy_stream = torch.cuda.Stream(device=dev)
     compute = torch.cuda.current_stream()
@@ -423,17 +468,19 @@ def run_ours(args, rank, world, local_rank):
     rows = per_launch_breakdown(engine, plan)
     tc = [r for r in rows if r["algo"] == HK_CONV_TCGEN05]
     peaks = load_peaks()
+    traffic, traffic_note = ncu_conv_traffic_per_step(B, H, W, K_KEYPOINTS, args.precision, launches_per_step, len(tc))
     if tc:
         tc_flops, tc_ms = sum(r["flops"] for r in tc), sum(r["ms"] for r in tc)
         achieved = tc_flops / (tc_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops"]
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all launches of one step)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": ncu_conv_traffic_per_step(B, H, W, K_KEYPOINTS, args.precision),
-                "traffic_note": "DRAM bytes read+written by the 35 conv launches of one step (ncu, profiles/r01f_step_per_launch_dram.json); "
-                                "algorithmic activation traffic of those launches: in+out+residual of every conv",
+                "traffic": traffic,
+                "traffic_note": traffic_note,
                 "peak_source": f"{peaks['source']} burst bf16 ({peak}); sustained {peaks['bf16_tflops_sustained']}",
-                "launches": len(tc), "ms_in_step": tc_ms, "share_of_step": tc_ms / sum(r["ms"] for r in rows)}
+                "launches": len(tc), "ms_in_step": tc_ms, "ms_in_step_min_of_reps": sum(r["ms_min"] for r in tc),
+                "timing": "mean of 5 CUDA-event-timed repetitions per launch (eager, isolated launches)",
+                "share_of_step": tc_ms / sum(r["ms"] for r in rows)}
     else:
         ff = [r for r in rows if r["flops"] > 0]
         f, ms = sum(r["flops"] for r in ff), sum(r["ms"] for r in ff)
@@ -448,6 +495,14 @@ def run_ours(args, rank, world, local_rank):
         with open(args.breakdown, "w") as f:
             json.dump({"batch": B, "rows": rows}, f, indent=1)
 
+    default_workload = args.precision == "bf16" and (B, H, W, K_KEYPOINTS) == (64, 480, 640, 4)
+    config3 = measure_config3(model, dev, rank, world, barrier, max_over_ranks) if (default_workload and not args.no_config3) else None
+    train = None
+    if default_workload and not args.no_train_step:
+        del engine, plan
+        model._engine = None
+        torch.cuda.empty_cache()
+        train = measure_train_step(dev, H, W, rank, world, barrier, max_over_ranks)
     if rank != 0:
         return
     gf_img = conv_flops_per_image(H, W, K_KEYPOINTS) / 1e9
@@ -468,6 +523,8 @@ def run_ours(args, rank, world, local_rank):
                 "note": "pinned-host fp32 images -> device (model.staging_input), model.keypoints: forward + decode, keypoints + peak "
                         "values -> host; H2D double-buffered over two serving slots on a copy stream"},
         "e2e_uint8_input": e2e_u8,
+        "sustained": sustained,
+        "config3_4096_images": config3,
         "gpu_launches": launches_per_step * args.steps * (3 if e2e_u8 else 2),  # timed regions: device-resident loop + e2e loop(s)
         "gpu_launches_per_step": launches_per_step,
         "roofline": roof,
@@ -480,41 +537,94 @@ def run_ours(args, rank, world, local_rank):
         n = args.cpu_images or 120
         secs = ref.run(n)
         v, cores = n / secs, ref.cores
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{n} images {H}x{W}, B=1 per call, oracle port in the reference's as-written op order (torch CPU), {secs:.1f} s"}
-    if not args.no_train_step and world == 1 and args.precision == "bf16" and (B, H, W, K_KEYPOINTS) == (64, 480, 640, 4):
-        line["train_step"] = measure_train_step(dev, H, W)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": ref.kind,
+                                "sample": f"{n} images {H}x{W}, B=1 per call, " + ("unmodified reference classes from oracle/_ref" if ref.kind == "reference"
+                                          else "oracle port in the reference's as-written op order") + f" (torch CPU), {secs:.1f} s"}
+    if train is not None:
+        line["train_step"] = train
     print(json.dumps(line), flush=True)
 
 
-def measure_train_step(dev, H, W):
+def measure_config3(model, dev, rank, world, barrier, max_over_ranks):
+    """BASELINE.json configs[2] as SURVEY.md §8d specifies it: 4096 synthetic 480x640 images in 64-image batches, split contiguously
+    across the ranks (strong scaling), each replica loops over its shard through the public serving call (model.keypoints), no
+    collective on the data path; wall time = max over ranks.  Images are generated on the device (a 4096-image fp32 set is 15 GB:
+    resident in HBM, H2D excluded as in configs[1])."""
+    from hulk_keypoints_b200.parallel import shard_range
+    total, bs = 4096, 64
+    b0, b1 = shard_range(total // bs, world, rank)          # contiguous range of 64-image batches owned by this rank
+    n_local = b1 - b0
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    shard = torch.rand((max(n_local, 1) * bs, 3, 480, 640), device=dev, generator=gen)
+    out = torch.empty((max(n_local, 1) * bs, K_KEYPOINTS, 2), device=dev, dtype=torch.int32)
+    model.keypoints(shard[:bs])                               # plan + graph for this shape
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n_local):
+        yx, _ = model.keypoints(shard[i * bs:(i + 1) * bs])
+        out[i * bs:(i + 1) * bs].copy_(yx)
+    e1.record()
+    e1.synchronize()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    checksum = int(out[: n_local * bs].to(torch.int64).sum().item())
+    del shard
+    torch.cuda.empty_cache()
+    return {"images": total, "batch": bs, "batches_on_rank0": n_local, "seconds": ms * 1e-3, "value": total / (ms * 1e-3), "unit": UNIT,
+            "scaling": "strong", "keypoint_checksum_rank0": checksum,
+            "note": "4096 images split contiguously over the ranks, device-resident, model.keypoints per 64-image batch, max over ranks"}
+
+
+def measure_train_step(dev, H, W, rank=0, world=1, barrier=None, max_over_ranks=None):
     """Secondary metric (BASELINE.json configs[3]; bench_train.py is the full tool): ms per training step -- Gaussian targets from labels +
-    train-mode forward + BCE + backward + fused Adam on libhulk_sm100 kernels, one CUDA graph -- at per-GPU batch 4 (config.py) and 32.
+    train-mode forward + BCE + backward + gradient exchange (NCCL, world > 1) + fused Adam on libhulk_sm100 kernels -- at per-GPU batch
+    4 (config.py) and 32, every rank, max over ranks.  For world > 1 also: the same step with the exchange switched off (compute only),
+    and the all-reduce of the flat gradient buffer timed alone, so the share of the step inside NCCL and the exposed part are measured.
     Never fails the headline line: errors are reported as text."""
-    out = {"config": "BASELINE configs[3], 1 GPU, 480x640, K=4, Adam lr 1e-4 wd 1e-4, synthetic images and labels", "unit": "ms/step"}
+    out = {"config": f"BASELINE configs[3], {world} GPU(s), per-GPU batch 4 and 32, 480x640, K=4, Adam lr 1e-4 wd 1e-4, synthetic images and labels",
+           "unit": "ms/step", "n_gpus": world}
+    barrier = barrier or (lambda: torch.cuda.synchronize())
+    max_over_ranks = max_over_ranks or (lambda ms: ms)
     try:
+        import torch.distributed as dist
+
         import hulk_keypoints_b200 as hk
-        from hulk_keypoints_b200 import train_ops
+        from hulk_keypoints_b200 import parallel, train_ops
         from hulk_keypoints_b200.optim import FusedAdam
+
+        def timed(fn, steps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                r = fn()
+            e1.record(); e1.synchronize()
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1)) / steps, r
+
         for bsz in (4, 32):
             torch.manual_seed(0)
             model = hk.KeypointsGauss(4, img_height=H, img_width=W).to(dev).train()
+            parallel.broadcast_model(model)
             opt = FusedAdam(model.parameters(), lr=1e-4, weight_decay=1e-4)
-            g = torch.Generator().manual_seed(2000)
+            g = torch.Generator().manual_seed(2000 + rank)
             img = torch.rand(bsz, 3, H, W, generator=g).to(dev)
             uv = torch.stack([torch.randint(0, W, (bsz, 4), generator=g), torch.randint(0, H, (bsz, 4), generator=g)], -1).float().to(dev)
             for _ in range(3):
                 train_ops.train_step(model, opt, img, uv, sigma=8.0)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             steps = 20
-            e0.record()
-            for _ in range(steps):
-                loss = train_ops.train_step(model, opt, img, uv, sigma=8.0)
-            e1.record(); e1.synchronize()
-            ms = e0.elapsed_time(e1) / steps
-            out[f"batch{bsz}"] = {"ms_per_step": ms, "images_per_sec": bsz / (ms * 1e-3), "loss": float(loss.item()),
-                                  "gpu_launches_per_step": model.train_engine(bsz, H, W).launches + 1}
+            ms, loss = timed(lambda: train_ops.train_step(model, opt, img, uv, sigma=8.0), steps)
+            row = {"ms_per_step": ms, "images_per_sec": world * bsz / (ms * 1e-3), "loss": float(loss.item()),
+                   "gpu_launches_per_step": model.train_engine(bsz, H, W).launches + 1}
+            if world > 1:
+                for _ in range(2):
+                    train_ops.train_step(model, opt, img, uv, sigma=8.0, exchange=False)
+                ms_local, _ = timed(lambda: train_ops.train_step(model, opt, img, uv, sigma=8.0, exchange=False), steps)
+                ms_ar, _ = timed(lambda: dist.all_reduce(opt.flat_grad, op=dist.ReduceOp.SUM), steps)
+                row.update({"ms_per_step_no_exchange": ms_local, "allreduce_ms_alone": ms_ar, "allreduce_bytes": opt.flat_grad.numel() * 4,
+                            "pct_of_step_in_nccl": 100.0 * ms_ar / ms, "pct_of_step_exposed": 100.0 * max(ms - ms_local, 0.0) / ms})
+            out[f"batch{bsz}"] = row
             del model, opt
             torch.cuda.empty_cache()
     except Exception as exc:  # noqa: BLE001 -- reported, never raised: this block is informational
@@ -522,20 +632,28 @@ def measure_train_step(dev, H, W):
     return out
 
 
-def ncu_conv_traffic_per_step(B, H, W, K, precision):
-    """DRAM bytes (read + write) of the 35 tcgen05 conv launches of one step from the committed ncu capture
-    (profiles/r01f_step_per_launch_dram.json: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over bench.py's default
-    workload).  None for any other workload."""
+def ncu_conv_traffic_per_step(B, H, W, K, precision, launches_per_step, conv_launches):
+    """DRAM bytes (read + write) of the tcgen05 conv launches of ONE step from the newest committed per-launch ncu capture
+    (profiles/*_step_per_launch_dram.json: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over bench.py's default
+    workload, tools/gpu_profile_r2.sh).  The capture is matched to the running workload: its launch list must be a whole number of
+    steps of `launches_per_step` launches with `conv_launches` conv launches each.  Returns (bytes or None, note)."""
+    import glob
     if (B, H, W, K, precision) != (64, 480, 640, 4, "bf16"):
-        return None
-    p = os.path.join(ROOT, "profiles", "r01f_step_per_launch_dram.json")
-    if not os.path.exists(p):
-        return None
-    with open(p) as f:
-        rows = [r for r in json.load(f) if "conv_tc" in r["kernel"]]
-    if len(rows) < 35:
-        return None
-    return float(sum(r["dram__bytes_read.sum"] + r["dram__bytes_write.sum"] for r in rows[:35]))  # any 35 consecutive = one step
+        return None, "no ncu capture committed for this workload"
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_step_per_launch_dram.json")), reverse=True):
+        with open(p) as f:
+            data = json.load(f)
+        rows = data["rows"] if isinstance(data, dict) else data
+        conv = [r for r in rows if "conv_tc" in r["kernel"]]
+        if launches_per_step <= 0 or len(rows) % launches_per_step or not conv:
+            continue
+        n_steps = len(rows) // launches_per_step
+        if len(conv) != conv_launches * n_steps:
+            continue
+        total = float(sum(r["dram__bytes_read.sum"] + r["dram__bytes_write.sum"] for r in conv)) / n_steps
+        return total, (f"DRAM bytes read+written by the {conv_launches} conv launches of one step (ncu, profiles/{os.path.basename(p)}, "
+                       f"{n_steps} step(s) captured); algorithmic activation traffic of those launches: in+out+residual of every conv")
+    return None, "no committed per-launch ncu capture matches this build's launch sequence"
 
 
 def main():

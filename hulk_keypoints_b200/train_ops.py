@@ -97,12 +97,13 @@ def loss_from_batch(sample_batched, model, use_cuda: bool = True, backend: str =
 
 
 def train_step(model, optimizer, img: torch.Tensor, uv: torch.Tensor, sigma: float = 8.0, allreduce=None,
-               backend: str = "hk") -> torch.Tensor:
+               backend: str = "hk", exchange: bool = True) -> torch.Tensor:
     """One step of reference train.py:33-36 (zero_grad, forward, backward, step) with targets generated from
     labels on the fly.  `optimizer` is a `hulk_keypoints_b200.optim.FusedAdam` (flat buffers: one all-reduce, one
     update kernel) or any torch optimizer; `allreduce(params)` (data-parallel exchange) runs between backward and step
     for torch optimizers, FusedAdam reduces its flat gradient buffer itself.
 
+    `exchange=False` skips the data-parallel gradient exchange (a measurement switch: replicas then diverge).
     backend "hk" (default): the whole forward + loss + backward runs on libhulk_sm100 kernels (TrainEngine, one CUDA graph);
     with FusedAdam the engine writes the gradients straight into the optimiser's flat buffer.  backend "autograd": the
     backbone runs on torch autograd (fp32 cuDNN) -- the checker of the parity tests, not a product path."""
@@ -114,6 +115,12 @@ def train_step(model, optimizer, img: torch.Tensor, uv: torch.Tensor, sigma: flo
             if optimizer.flat_grad.data_ptr() != eng.flat_grad.data_ptr():
                 optimizer.adopt_grad_buffer(eng.flat_grad)
         import torch.distributed as dist
+        if not exchange:   # measurement only (bench.py: the step with its gradient exchange switched off = the compute-only time)
+            loss = eng.forward_backward(img, uv=uv)
+            if not fused:
+                eng.grads_into_params()
+            optimizer.step()
+            return loss.detach().clone()
         if fused and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             # data-parallel: the all-reduce of layer3/layer4/fc gradients (91 % of the bytes) overlaps the backward of layers 2..1 + stem
             loss = eng.forward_backward_late(img, uv)
