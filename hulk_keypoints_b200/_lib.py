@@ -31,7 +31,7 @@ EXPORTS = (
     "hk_stem_wgrad_workspace_bytes", "hk_stem_wgrad", "hk_maxpool3x3s2_bwd", "hk_head_logits_fwd",
     "hk_head_bwd_workspace_bytes", "hk_head_bwd", "hk_sigmoid_fwd", "hk_sigmoid_bwd", "hk_pack_conv_weights_many",
     # round 2
-    "hk_soft_argmax_workspace_bytes", "hk_soft_argmax", "hk_l1_normalize_dim1",
+    "hk_soft_argmax_workspace_bytes", "hk_soft_argmax", "hk_l1_normalize_dim1", "hk_stem_pool_fwd", "hk_stem_pool_fwd_u8",
 )
 
 
@@ -73,6 +73,10 @@ def _declare(lib):
     lib.hk_stem_pack_weights.argtypes = [vp, vp, vp]
     lib.hk_stem_fwd.restype = i
     lib.hk_stem_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
+    lib.hk_stem_pool_fwd.restype = i
+    lib.hk_stem_pool_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
+    lib.hk_stem_pool_fwd_u8.restype = i
+    lib.hk_stem_pool_fwd_u8.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
     lib.hk_adam_step.restype = i
     lib.hk_adam_step.argtypes = [vp, vp, vp, vp, C.c_longlong, f, f, f, f, f, i, vp]
     lib.hk_stem_fwd_u8.restype = i

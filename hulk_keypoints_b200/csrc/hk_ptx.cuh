@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace hk {
 namespace ptx {
@@ -39,6 +40,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // `hk_watchdog[0]` receives a code identifying the stuck wait before the trap.
 __device__ unsigned int hk_watchdog[4];
 
+#ifdef HK_DIAG
+// Diagnostics build: a stuck wait records its site ONCE (the first one is the root cause), raises an abort flag that lets every
+// other wait fall through, and the kernel runs to completion with garbage results; the host reads hk_watchdog afterwards
+// (hk_debug_read_watchdog_* in the kernel's translation unit).  The shipped build traps instead.
+__device__ unsigned int hk_watchdog_abort;
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t site) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*reinterpret_cast<volatile unsigned int*>(&hk_watchdog_abort)) return;
+    if (clock64() - t0 > 400000000LL) {
+      if (atomicCAS(&hk_watchdog[0], 0u, site) == 0u) {
+        hk_watchdog[1] = blockIdx.x;
+        hk_watchdog[2] = threadIdx.x;
+        hk_watchdog[3] = parity;
+      }
+      atomicExch(&hk_watchdog_abort, 1u);
+      __threadfence();
+      return;
+    }
+  }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t site) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
@@ -53,6 +77,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
     }
   }
 }
+#endif
 
 // one lane of the (converged) warp; the branch stays warp-uniform for the compiler, so descriptors/coordinates live in
 // uniform registers instead of being moved there one by one (R2UR) in front of every UTCHMMA / UTMALDG

@@ -15,6 +15,7 @@ and fp32 in precision="fp32" (all convs on the CUDA-core FFMA kernel).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -69,7 +70,8 @@ class _Plan:
         self.x = torch.empty((B, 3, H, W), device=dev, dtype=torch.float32)
         self.x_u8: Optional[torch.Tensor] = None  # (B,H,W,3) uint8 staging, allocated on first uint8 call
         self.input_is_u8 = False
-        self.stem = torch.empty((B, h2, w2, 64), device=dev, dtype=adt)
+        self._stem: Optional[torch.Tensor] = None   # (B,H/2,W/2,64): only the two-kernel stem path (fp32 mode, odd widths) needs it
+        self._stem_spec = ((B, h2, w2, 64), dev, adt)
         max_elems = max(B * h4 * w4 * 64, B * h8 * w8 * 512)
         self.pool = [torch.empty(max_elems, device=dev, dtype=adt) for _ in range(4)]
         self.logits = torch.empty((B, K, h8, w8), device=dev, dtype=torch.float32)
@@ -80,6 +82,13 @@ class _Plan:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_decode: Optional[bool] = None
         self.launches = 0
+
+    @property
+    def stem(self) -> torch.Tensor:
+        if self._stem is None:
+            shape, dev, adt = self._stem_spec
+            self._stem = torch.empty(shape, device=dev, dtype=adt)
+        return self._stem
 
     def view(self, i: int, h: int, w: int, c: int) -> torch.Tensor:
         return self.pool[i][: self.B * h * w * c].view(self.B, h, w, c)
@@ -96,6 +105,7 @@ class InferenceEngine:
         # stride-2 convs (layer2.0.conv1 and its 1x1 downsample) may be routed to the CUDA-core kernel
         self.stride2_algo = HK_CONV_TCGEN05
         self.stem_on_tensor_cores = True  # bf16 mode: tcgen05 stem; False keeps the fp32 CUDA-core stem
+        self.fuse_stem_pool = os.environ.get("HK_STEM_POOL", "1") != "0"   # A/B switch: 0 = stem_tc_kernel + maxpool3x3s2_kernel
         self._packed: Optional[Dict[str, _PackedConv]] = None
         self._packed_key = None
         self._plans: Dict[Tuple[int, int, int, int], _Plan] = {}
@@ -157,14 +167,18 @@ class InferenceEngine:
         net = self.model.resnet.resnet34_8s
         P = self._packed
         n = 0
-        if self._stem_w_tc is not None:
-            src = plan.x_u8 if plan.input_is_u8 else plan.x
-            ops.stem(src, self._stem_w_tc, P["stem"].scale, P["stem"].bias, out=plan.stem); n += 1
-        else:
-            self._conv(P["stem"], plan.x, plan.stem, relu=True, in_is_nchw=True); n += 1
         cur = 0
         x = plan.view(cur, plan.h4, plan.w4, 64)
-        ops.maxpool3x3s2(plan.stem, out=x); n += 1
+        src = plan.x_u8 if plan.input_is_u8 else plan.x
+        if self._stem_w_tc is not None and self.fuse_stem_pool and ops.stem_pool_supported(src):
+            # conv7x7 + BN + ReLU + maxpool in one row-streaming kernel: the (B,H/2,W/2,64) stem map never touches HBM
+            ops.stem_pool(src, self._stem_w_tc, P["stem"].scale, P["stem"].bias, out=x); n += 1
+        else:
+            if self._stem_w_tc is not None:
+                ops.stem(src, self._stem_w_tc, P["stem"].scale, P["stem"].bias, out=plan.stem); n += 1
+            else:
+                self._conv(P["stem"], plan.x, plan.stem, relu=True, in_is_nchw=True); n += 1
+            ops.maxpool3x3s2(plan.stem, out=x); n += 1
         h, w = plan.h4, plan.w4
         for i, blk in enumerate(net.blocks()):
             c1, c2 = P[f"b{i}.c1"], P[f"b{i}.c2"]

@@ -110,6 +110,36 @@ def stem(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, bias: tor
     return out
 
 
+def stem_pool_supported(x: torch.Tensor) -> bool:
+    """The fused stem + max-pool kernel feeds its input rows by TMA: the row pitch must be a multiple of 16 bytes."""
+    if x.dtype == torch.uint8:
+        return x.dim() == 4 and x.shape[3] == 3 and (3 * x.shape[2]) % 16 == 0
+    return x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3 and x.shape[3] % 4 == 0
+
+
+def stem_pool(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """conv7x7 s2 + affine + ReLU + MaxPool2d(3,2,1) in one tcgen05 kernel -> (B,Hp,Wp,64) bf16 NHWC (bit-identical to
+    maxpool3x3s2(stem(x))).  x: (B,3,H,W) fp32 NCHW or (B,H,W,3) uint8."""
+    _need_cuda(x, w_packed, scale, bias, out)
+    if not x.is_contiguous() or not stem_pool_supported(x):
+        raise ValueError("stem_pool needs a contiguous (B,3,H,W) fp32 input with W % 4 == 0 or (B,H,W,3) uint8 with W % 16 == 0")
+    if x.dtype == torch.uint8:
+        B, H, W, _ = x.shape
+        fn, name = lib().hk_stem_pool_fwd_u8, "hk_stem_pool_fwd_u8"
+    else:
+        B, _, H, W = x.shape
+        fn, name = lib().hk_stem_pool_fwd, "hk_stem_pool_fwd"
+    Ho, Wo = conv_out_hw(H, W, 7, 2, 3, 1)
+    Hp, Wp = (Ho + 2 - 3) // 2 + 1, (Wo + 2 - 3) // 2 + 1
+    if out is None:
+        out = torch.empty((B, Hp, Wp, 64), device=x.device, dtype=torch.bfloat16)
+    elif tuple(out.shape) != (B, Hp, Wp, 64) or out.dtype != torch.bfloat16 or not out.is_contiguous():
+        raise ValueError(f"stem_pool out must be a contiguous bf16 {(B, Hp, Wp, 64)} tensor")
+    check(fn(ptr(x), ptr(w_packed), ptr(scale), ptr(bias), ptr(out), B, H, W, stream_ptr()), name)
+    return out
+
+
 def maxpool3x3s2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(x, out)
     B, H, W, Cc = x.shape

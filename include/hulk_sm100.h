@@ -112,6 +112,15 @@ HK_API int hk_stem_fwd(const float* x_nchw, const void* w_packed, const float* s
 HK_API int hk_stem_fwd_u8(const uint8_t* x_nhwc_u8, const void* w_packed, const float* scale, const float* bias,
                           void* y_nhwc, int B, int H, int W, void* stream);
 
+/* Stem + max-pool in ONE kernel (inference): conv 7x7 s2 p3 + folded BN + ReLU + MaxPool2d(3,2,1).  Replaces src/resnet.py:137-141,
+ * 199-202 without writing the (B,H/2,W/2,64) stem map: row-streaming tcgen05 kernel, input rows by TMA, pooled bf16 NHWC out.
+ * y (B, Hp, Wp, 64) bf16 with Hp = (H/2 + 1)/2 rounded as MaxPool2d does.  Bit-identical to hk_stem_fwd + hk_maxpool3x3s2_fwd.
+ * Needs W % 4 == 0 (fp32) / W % 16 == 0 (uint8) for the TMA row pitch; otherwise HK_ERR_BAD_ARG (use the two-kernel path). */
+HK_API int hk_stem_pool_fwd(const float* x_nchw, const void* w_packed, const float* scale, const float* bias, void* y_pooled_nhwc,
+                            int B, int H, int W, void* stream);
+HK_API int hk_stem_pool_fwd_u8(const uint8_t* x_nhwc_u8, const void* w_packed, const float* scale, const float* bias,
+                               void* y_pooled_nhwc, int B, int H, int W, void* stream);
+
 /* MaxPool2d(kernel 3, stride 2, pad 1) on NHWC.  Replaces src/resnet.py:141,202. */
 HK_API int hk_maxpool3x3s2_fwd(const void* x, void* y, int dtype, int batch, int in_h, int in_w, int c,
                         int out_h, int out_w, void* stream);

@@ -412,6 +412,37 @@ def test_conv_tcgen05_c64_specialisation(case):
     test_conv_tcgen05_vs_oracle((B, H, W, 64, 64, 3, 1, dil, residual, relu))
 
 
+@pytest.mark.parametrize("shape", [(2, 480, 640), (1, 96, 128), (3, 64, 96), (1, 100, 132), (2, 72, 1040), (1, 330, 36)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_stem_pool_fused_bit_identical_to_two_kernels(shape):
+    """hk_stem_pool_fwd (row-streaming stem + max-pool, no-swizzle overlapping-core-matrix A operand straight from the input ring)
+    against hk_stem_fwd + hk_maxpool3x3s2_fwd: BIT-identical, incl. ragged strips (W/4 not a multiple of 63), odd stem heights,
+    widths over several strips, bands with carry rows."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(H * 7 + W)
+    x = torch.rand(B, 3, H, W, generator=g).to(dev())
+    w = (torch.randn(64, 3, 7, 7, generator=g) * 0.1).to(dev())
+    scale = (torch.rand(64, generator=g) + 0.5).to(dev())
+    bias = (torch.randn(64, generator=g) * 0.2).to(dev())
+    wp = ops.stem_pack_weights(w)
+    ref = ops.maxpool3x3s2(ops.stem(x, wp, scale, bias))
+    got = ops.stem_pool(x, wp, scale, bias)
+    assert got.shape == ref.shape and got.dtype == torch.bfloat16
+    assert torch.equal(got, ref), (got.float() - ref.float()).abs().max().item()
+    if W % 16 == 0:
+        u8 = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).to(dev())
+        ref8 = ops.maxpool3x3s2(ops.stem(u8, wp, scale, bias))
+        got8 = ops.stem_pool(u8, wp, scale, bias)
+        assert torch.equal(got8, ref8), (got8.float() - ref8.float()).abs().max().item()
+
+
+def test_stem_pool_rejects_unaligned_width():
+    x = torch.rand(1, 3, 64, 98).to(dev())
+    assert not ops.stem_pool_supported(x)
+    with pytest.raises(ValueError):
+        ops.stem_pool(x, torch.empty(64 * 256, device=dev(), dtype=torch.bfloat16), torch.ones(64, device=dev()), torch.zeros(64, device=dev()))
+
+
 def test_stem_uint8_input_matches_float_path():
     """(B,H,W,3) uint8 input with /255 fused into the load == the fp32 NCHW path fed ToTensor(img) (dataset.py:16)."""
     g = torch.Generator().manual_seed(33)
