@@ -322,13 +322,23 @@ def per_launch_breakdown(engine, plan, decode=True):
         free = [j for j in range(4) if j != cur]
         t = plan.view(free[0], ho, wo, planes)
         xin = x
-        timed(f"b{i}.c1", 2.0 * B * ho * wo * planes * cin * 9, lambda: engine._conv(c1, xin, t, relu=True))
-        rows[-1]["algo"] = c1.algo
-        if blk.downsample is not None:
+        ds = P.get(f"b{i}.ds")
+        if (ds is not None and engine.fuse_downsample and c1.algo == ds.algo == 0 and ds.stride == c1.stride
+                and ops.conv_ds_supported(xin, c1.w, ds.w, c1.stride, c1.pad, c1.dil)):
+            sc = plan.view(free[1], ho, wo, planes)      # block entry: conv1 + the 1x1 downsample conv in one launch (engine._enqueue)
+            timed(f"b{i}.c1+ds", 2.0 * B * ho * wo * planes * cin * 10,
+                  lambda: ops.conv_ds(xin, c1.w, c1.scale, c1.bias, ds.w, ds.scale, ds.bias, stride=c1.stride, pad=c1.pad, dil=c1.dil,
+                                      relu=True, out=t, out_ds=sc))
+            rows[-1]["algo"] = c1.algo
+        elif blk.downsample is not None:
+            timed(f"b{i}.c1", 2.0 * B * ho * wo * planes * cin * 9, lambda: engine._conv(c1, xin, t, relu=True))
+            rows[-1]["algo"] = c1.algo
             sc = plan.view(free[1], ho, wo, planes)
             timed(f"b{i}.ds", 2.0 * B * ho * wo * planes * cin, lambda: engine._conv(P[f"b{i}.ds"], xin, sc, relu=False))
             rows[-1]["algo"] = P[f"b{i}.ds"].algo
         else:
+            timed(f"b{i}.c1", 2.0 * B * ho * wo * planes * cin * 9, lambda: engine._conv(c1, xin, t, relu=True))
+            rows[-1]["algo"] = c1.algo
             sc = x
         y = plan.view(free[2], ho, wo, planes)
         timed(f"b{i}.c2", 2.0 * B * ho * wo * planes * planes * 9, lambda: engine._conv(c2, t, y, relu=True, residual=sc))

@@ -20,6 +20,14 @@
 // with the 128-byte swizzle) and one elected thread issues the TMA stores.  The direct version (16-byte accesses at a
 // >= 256-byte lane stride) cost 32 L1 wavefronts per warp instruction and made the 1x1 downsample convs and the
 // N=128 layer epilogue-bound.
+//
+// DS = true ("block entry", reference src/resnet.py:56-58 + :64-65,184-188): the 1x1 downsample conv of a stride/channel-changing
+// BasicBlock reads exactly the centre tap of conv1's activation operand (pad = dil*(k/2): tap offset 0, same stride), so both convs
+// run in ONE launch.  Every (m, n) work item is two accumulator uses: sub 0 = conv1 (kh*kw*cblocks K blocks, scale/bias/ReLU, y),
+// sub 1 = downsample (cblocks K blocks of the centre-tap boxes against the 1x1 weights, scale2/bias2, no ReLU, y2).  The barrier
+// protocol is unchanged (sub-tiles simply take consecutive accumulator turns); sub 1's epilogue hides under the next item's conv1
+// mainloop.  Sub 0's epilogue would otherwise hold its accumulator through the short sub-1 mainloop and stall the next conv1, so in
+// DS mode it drains all of its TMEM columns into packed bf16 registers first, releases the accumulator, and only then stages/stores.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -44,6 +52,9 @@ struct ConvTc2Args {
   int Cin, kh, kw, stride, pad, dil, relu;
   int tiles_x, tiles_per_img, num_boxes;
   int num_m_tiles, num_n_tiles, cblocks;  // m tiles of 256 pixels (4 boxes)
+  const float* scale2;   // DS kernels only: folded BN of the 1x1 downsample conv, ReLU flag of its epilogue (0 in the reference)
+  const float* bias2;
+  int relu2, early_release, s_major;
 #ifdef HK_DIAG  // diagnostics build only (python -m hulk_keypoints_b200.build --diag -> libhulk_sm100_diag.so); never in the shipped library
   int dbg_mode;    // HK_TC2_DEBUG bit flags: 1 = skip the MMAs, 2 = skip the TMA operand loads, 4 = skip the epilogue body (results are garbage)
   long long* dbg;  // optional timeline of cluster 0's leader CTA (tools/diag_tc2_timeline.py)
@@ -85,10 +96,12 @@ __device__ __forceinline__ void t2_decode_box(const ConvTc2Args& a, int box, int
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool DS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res, const ConvTc2Args a) {
+                const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res,
+                const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_y2, const ConvTc2Args a) {
+  constexpr int NSUB = DS ? 2 : 1;
   using Cfg = Tc2Cfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -115,6 +128,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     ptx::prefetch_tensormap(&map_w);
     ptx::prefetch_tensormap(&map_y);
     if (a.residual) ptx::prefetch_tensormap(&map_res);
+    if (DS) {
+      ptx::prefetch_tensormap(&map_w2);
+      ptx::prefetch_tensormap(&map_y2);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -149,6 +166,29 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         t2_decode_box(a, 4 * m_tile + 2 * (int)rank, b0, y0, x0);
         t2_decode_box(a, 4 * m_tile + 2 * (int)rank + 1, b1, y1, x1);
         const int n_row0 = n_tile * BLOCK_N + (int)rank * Cfg::HALF_N;
+        if (DS && a.s_major) {
+          // K blocks in the haloed kernel's order (s, channel block, r): the fp32 accumulation sequence -- and therefore every output
+          // bit -- matches conv_tc2h_kernel, which is where this conv runs when it is launched on its own
+          for (int s = 0; s < a.kw; ++s) {
+            for (int cb = 0; cb < a.cblocks; ++cb) {
+              for (int r = 0; r < a.kh; ++r) {
+                const int dy = r * a.dil - a.pad, dx = s * a.dil - a.pad;
+                const int kbase = (r * a.kw + s) * a.Cin;
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 31);
+                if (ptx::elect_one_sync()) {
+                  uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                  ptx::tma2_load_4d(sa, &map_x, &full_bar[stage], cb * 64, x0 * a.stride + dx, y0 * a.stride + dy, b0);
+                  ptx::tma2_load_4d(sa + T2_BOX_BYTES, &map_x, &full_bar[stage], cb * 64, x1 * a.stride + dx, y1 * a.stride + dy, b1);
+                  ptx::tma2_load_2d(sa + T2_A_BYTES, &map_w, &full_bar[stage], kbase + cb * 64, n_row0);
+                  if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                  else ptx::mbar_arrive_remote(&full_bar[stage], 0);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              }
+            }
+          }
+        } else
         for (int r = 0; r < a.kh; ++r) {
           for (int s = 0; s < a.kw; ++s) {
             const int dy = r * a.dil - a.pad, dx = s * a.dil - a.pad;
@@ -169,6 +209,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             }
           }
         }
+        if (DS) {  // sub 1: the 1x1 downsample conv = centre tap (offset 0) of the same boxes against its own weights
+          const int cdy = (a.kh >> 1) * a.dil - a.pad, cdx = (a.kw >> 1) * a.dil - a.pad;
+          for (int cb = 0; cb < a.cblocks; ++cb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 31);
+            if (ptx::elect_one_sync()) {
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              ptx::tma2_load_4d(sa, &map_x, &full_bar[stage], cb * 64, x0 * a.stride + cdx, y0 * a.stride + cdy, b0);
+              ptx::tma2_load_4d(sa + T2_BOX_BYTES, &map_x, &full_bar[stage], cb * 64, x1 * a.stride + cdx, y1 * a.stride + cdy, b1);
+              ptx::tma2_load_2d(sa + T2_A_BYTES, &map_w2, &full_bar[stage], cb * 64, n_row0);
+              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              else ptx::mbar_arrive_remote(&full_bar[stage], 0);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
         T2_STAMP(0, pit, 1);
       }
     }
@@ -177,31 +233,35 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       // ===================== MMA issuer (leader CTA only; whole warp waits, one elected lane issues) =====================
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(256, BLOCK_N);
       uint32_t stage = 0, phase = 0, it = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
-        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-        T2_STAMP(1, it, 0);
-        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 32);
-        ptx::tc_fence_after();
-        T2_STAMP(1, it, 1);
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          if (!(T2_DBG_MODE(a) & 2)) ptx::mbar_wait(&full_bar[stage], phase, 33);
-          if (kb == 0) T2_STAMP(1, it, 2);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
-          const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + T2_A_BYTES);
-          if (ptx::elect_one_sync()) {
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (!(T2_DBG_MODE(a) & 1)) ptx::umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            ptx::umma2_commit_mc(&empty_bar[stage]);
-            if (kb == num_kb - 1) ptx::umma2_commit_mc(&tmem_full_bar[acc]);
+        for (int sub = 0; sub < NSUB; ++sub, ++it) {
+          const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+          const int nkb = sub ? a.cblocks : num_kb;
+          T2_STAMP(1, it, 0);
+          ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 32);
+          ptx::tc_fence_after();
+          T2_STAMP(1, it, 1);
+          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          for (int kb = 0; kb < nkb; ++kb) {
+            if (!(T2_DBG_MODE(a) & 2)) ptx::mbar_wait(&full_bar[stage], phase, 33);
+            if (kb == 0) T2_STAMP(1, it, 2);
+            ptx::tc_fence_after();
+            const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + T2_A_BYTES);
+            if (ptx::elect_one_sync()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (!(T2_DBG_MODE(a) & 1)) ptx::umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              ptx::umma2_commit_mc(&empty_bar[stage]);
+              if (kb == nkb - 1) ptx::umma2_commit_mc(&tmem_full_bar[acc]);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          T2_STAMP(1, it, 3);
         }
-        T2_STAMP(1, it, 3);
       }
       // all remote arrivals of the last two accumulator uses must land before this CTA's barriers go away
       if (it >= 1) { const uint32_t j = it - 1; ptx::mbar_wait(&tmem_empty_bar[j & 1], (j >> 1) & 1, 34); }
@@ -216,18 +276,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const bool elected = (warp == 4 && lane == 0);
     const int sw = row & 7;
     constexpr int CHUNKS = BLOCK_N / 64;
-    const bool has_res = a.residual != nullptr;
     ptx::griddep_wait();  // before the first residual load / output store
     uint32_t it = 0, chunk_ctr = 0;      // chunk_ctr selects the staging buffer and the res_bar phase
-    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
-      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int m_tile = tile / a.num_n_tiles, n_tile = tile - m_tile * a.num_n_tiles;
       int b0, y0, x0, b1, y1, x1;          // this CTA's two 4x16 boxes (64 rows each)
       t2_decode_box(a, 4 * m_tile + 2 * (int)rank, b0, y0, x0);
       t2_decode_box(a, 4 * m_tile + 2 * (int)rank + 1, b1, y1, x1);
       const int n0 = n_tile * BLOCK_N;
-      const float* scale = a.scale + n0;
-      const float* bias = a.bias + n0;
+#pragma unroll
+      for (int sub = 0; sub < NSUB; ++sub, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const float* scale = (sub ? a.scale2 : a.scale) + n0;
+      const float* bias = (sub ? a.bias2 : a.bias) + n0;
+      const int relu = sub ? a.relu2 : a.relu;
+      const CUtensorMap* myp = sub ? &map_y2 : &map_y;
+      const bool has_res = !DS && a.residual != nullptr;   // the block-entry kernels carry no shortcut operand
 
       // elected thread only.  wait_group.read 1 = every TMA store but the newest has finished reading smem, so the buffers
       // of chunks ctr-2 and older -- i.e. (ctr+1) % 3 and ctr % 3 -- are free.
@@ -252,6 +316,58 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         continue;
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+      if (DS && sub == 0 && a.early_release) {
+        // drain the whole accumulator first (affine + ReLU + bf16 pack in registers), hand it back to the MMA warp, then stage and store
+        uint32_t pk[CHUNKS][16];
+#pragma unroll
+        for (int chunk = 0; chunk < CHUNKS; ++chunk) {
+          uint32_t r0[32];
+          ptx::tmem_ld_32x32(taddr + chunk * 64 + half * 32, r0);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            const int c = chunk * 64 + (half * 4 + gg) * 8;
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+            const float4 t1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[j] = fmaf(__uint_as_float(r0[gg * 8 + j]), sc[j], bi[j]);
+              if (relu) v[j] = fmaxf(v[j], 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pk[chunk][gg * 4 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+#pragma unroll
+        for (int chunk = 0; chunk < CHUNKS; ++chunk, ++chunk_ctr) {
+          const uint32_t bsel = chunk_ctr % 3;
+          uint8_t* my_row = staging + bsel * 16384 + row * 128;
+          if (elected) ptx::bulk_wait_group_read1();
+          ptx::named_bar_sync(1, T2_EPI_THREADS);  // staging[bsel] is free for everybody
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            const int g = half * 4 + gg;
+            *reinterpret_cast<uint4*>(my_row + (((g ^ sw) & 7) << 4)) =
+                make_uint4(pk[chunk][gg * 4], pk[chunk][gg * 4 + 1], pk[chunk][gg * 4 + 2], pk[chunk][gg * 4 + 3]);
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(1, T2_EPI_THREADS);
+          if (elected) {
+            const uint8_t* buf = staging + bsel * 16384;
+            ptx::tma_store_4d(myp, buf, n0 + chunk * 64, x0, y0, b0);
+            ptx::tma_store_4d(myp, buf + 8192, n0 + chunk * 64, x1, y1, b1);
+            ptx::bulk_commit_group();
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int chunk = 0; chunk < CHUNKS; ++chunk, ++chunk_ctr) {
         const uint32_t bsel = chunk_ctr % 3;
@@ -294,7 +410,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             unpack_bf16x2(rr.z, lo, hi); v[4] += lo; v[5] += hi;
             unpack_bf16x2(rr.w, lo, hi); v[6] += lo; v[7] += hi;
           }
-          if (a.relu) {
+          if (relu) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
           }
@@ -307,10 +423,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (elected && chunk == CHUNKS - 1) T2_STAMP(2, it, 7);
         if (elected) {
           const uint8_t* buf = staging + bsel * 16384;
-          ptx::tma_store_4d(&map_y, buf, n0 + chunk * 64, x0, y0, b0);         // clipped outside the image / batch
-          ptx::tma_store_4d(&map_y, buf + 8192, n0 + chunk * 64, x1, y1, b1);
+          ptx::tma_store_4d(myp, buf, n0 + chunk * 64, x0, y0, b0);         // clipped outside the image / batch
+          ptx::tma_store_4d(myp, buf + 8192, n0 + chunk * 64, x1, y1, b1);
           ptx::bulk_commit_group();
         }
+      }
       }
     }
     if (elected) ptx::bulk_wait_group0();
@@ -334,33 +451,45 @@ static long long* g_tc2_dbg = nullptr;
 extern "C" __attribute__((visibility("default"))) void hk_debug_set_tc2_timeline(long long* dev_buf) { g_tc2_dbg = dev_buf; }
 #endif
 
+bool conv_tc2h_applicable(const HkConvDesc& d);
+
 bool conv_tc2_applicable(const HkConvDesc& d) {
   static const bool disabled = getenv("HK_DISABLE_2CTA") != nullptr;
   return !disabled && d.out_c % 128 == 0 && d.in_c % 64 == 0 && (d.stride == 1 || d.stride == 2);
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool DS>
 static int launch_tc2(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& mres,
-                      const ConvTc2Args& a, cudaStream_t s) {
+                      const CUtensorMap& mw2, const CUtensorMap& my2, const ConvTc2Args& a, cudaStream_t s) {
   using Cfg = Tc2Cfg<BLOCK_N>;
   static int attr_dev_mask = 0;
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(attr_dev_mask & (1 << dev))) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): smem attribute (%d B): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
     attr_dev_mask |= (1 << dev);
   }
   const int total = a.num_m_tiles * a.num_n_tiles;
   int clusters = sm_count() / 2;
   if (clusters > total) clusters = total;
-  cudaError_t le = launch_pdl(conv_tc2_kernel<BLOCK_N>, dim3(2 * clusters), dim3(T2_THREADS), (size_t)Cfg::SMEM_BYTES, s, mx, mw, my, mres, a);
+  cudaError_t le = launch_pdl(conv_tc2_kernel<BLOCK_N, DS>, dim3(2 * clusters), dim3(T2_THREADS), (size_t)Cfg::SMEM_BYTES, s, mx, mw, my, mres,
+                              mw2, my2, a);
   if (le != cudaSuccess) return fail(HK_ERR_CUDA, "conv_tc2_kernel: %s", cudaGetErrorString(le));
   return check_launch("conv_tc2_kernel");
 }
 
-int conv_tc2_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
-                    const void* residual, void* y, cudaStream_t s) {
+// ds != nullptr: block-entry launch (conv1 + the 1x1 downsample conv of the same input, see the header)
+struct ConvTc2Ds {
+  const void* w;       // (Cout, Cin) bf16, K-major
+  const float* scale;
+  const float* bias;
+  void* y;             // (B, Ho, Wo, Cout) bf16
+  int relu;
+};
+
+static int conv_tc2_launch_impl(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
+                                const void* residual, void* y, const ConvTc2Ds* ds, cudaStream_t s) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled entry point not available");
   const long long boxes_all = (long long)ceil_div(d.out_w, T2_BOX_W) * ceil_div(d.out_h, T2_BOX_H) * d.batch;
@@ -377,32 +506,43 @@ int conv_tc2_launch(const HkConvDesc& d, const void* x, const void* w, const flo
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
   }
-  {
-    const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d.out_c};
-    const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  auto encode_w = [&](CUtensorMap* m, const void* wp, int k) -> CUresult {
+    const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)d.out_c};
+    const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
     const cuuint32_t box[2] = {64, (cuuint32_t)(block_n / 2)};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  {
+    CUresult r = encode_w(&mw, w, ktot);
     if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
   }
-  CUtensorMap my, mres;
-  {
+  auto encode_out = [&](CUtensorMap* m, const void* p) -> CUresult {
     const cuuint64_t dims[4] = {(cuuint64_t)d.out_c, (cuuint64_t)d.out_w, (cuuint64_t)d.out_h, (cuuint64_t)d.batch};
     const cuuint64_t strides[3] = {(cuuint64_t)d.out_c * 2, (cuuint64_t)d.out_w * d.out_c * 2, (cuuint64_t)d.out_h * d.out_w * d.out_c * 2};
     const cuuint32_t box[4] = {64, (cuuint32_t)T2_BOX_W, (cuuint32_t)T2_BOX_H, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&my, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUtensorMap my, mres;
+  {
+    CUresult r = encode_out(&my, y);
     if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled(output) failed: %d", (int)r);
     mres = my;
     if (residual) {
-      r = encode(&mres, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(residual), dims, strides, box, estr,
-                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      r = encode_out(&mres, residual);
       if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled(residual) failed: %d", (int)r);
     }
+  }
+  CUtensorMap mw2 = mw, my2 = my;
+  if (ds) {
+    CUresult r = encode_w(&mw2, ds->w, d.in_c);
+    if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled(downsample weights) failed: %d", (int)r);
+    r = encode_out(&my2, ds->y);
+    if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled(downsample output) failed: %d", (int)r);
   }
   ConvTc2Args a;
   a.scale = scale; a.bias = bias;
@@ -418,11 +558,44 @@ int conv_tc2_launch(const HkConvDesc& d, const void* x, const void* w, const flo
   a.num_m_tiles = (a.num_boxes + 3) / 4;
   a.num_n_tiles = d.out_c / block_n;
   a.cblocks = d.in_c / 64;
+  a.scale2 = ds ? ds->scale : scale;
+  a.bias2 = ds ? ds->bias : bias;
+  a.relu2 = ds ? ds->relu : 0;
+  // K-block order of the kernel this conv would run on by itself (conv_tc2h accumulates tap column by tap column)
+  a.s_major = ds && conv_tc2h_applicable(d);
+  { const char* e = getenv("HK_DS_EARLY"); a.early_release = !(e && e[0] == '0'); }   // A/B switch of the block-entry epilogue
 #ifdef HK_DIAG
   a.dbg = g_tc2_dbg;
   { const char* m = getenv("HK_TC2_DEBUG"); a.dbg_mode = m ? atoi(m) : 0; }
 #endif
-  return block_n == 256 ? launch_tc2<256>(mx, mw, my, mres, a, s) : launch_tc2<128>(mx, mw, my, mres, a, s);
+  if (ds) return block_n == 256 ? launch_tc2<256, true>(mx, mw, my, mres, mw2, my2, a, s) : launch_tc2<128, true>(mx, mw, my, mres, mw2, my2, a, s);
+  return block_n == 256 ? launch_tc2<256, false>(mx, mw, my, mres, mw2, my2, a, s) : launch_tc2<128, false>(mx, mw, my, mres, mw2, my2, a, s);
+}
+
+int conv_tc2_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
+                    const void* residual, void* y, cudaStream_t s) {
+  return conv_tc2_launch_impl(d, x, w, scale, bias, residual, y, nullptr, s);
 }
 
 }  // namespace hk
+
+// Block entry of a stride/channel-changing BasicBlock: y = relu?(scale*conv_kxk(x)+bias), y_ds = scale_ds*conv_1x1(x)+bias_ds in one launch.
+extern "C" int hk_conv_ds_fwd(const HkConvDesc* desc, const void* x, const void* w_packed, const float* scale, const float* bias, void* y,
+                              const void* w_ds_packed, const float* scale_ds, const float* bias_ds, void* y_ds, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(desc && x && w_packed && scale && bias && y && w_ds_packed && scale_ds && bias_ds && y_ds, "hk_conv_ds_fwd: null pointer");
+  const HkConvDesc& d = *desc;
+  HK_REQUIRE(d.algo == HK_CONV_TCGEN05 && d.in_dtype == HK_BF16 && d.out_dtype == HK_BF16 && !d.in_is_nchw,
+             "hk_conv_ds_fwd: tcgen05 path only (NHWC bf16 in and out)");
+  HK_REQUIRE(d.batch > 0 && d.in_h > 0 && d.in_w > 0 && d.kh == d.kw && (d.kh & 1) && d.dil > 0 && (d.stride == 1 || d.stride == 2),
+             "hk_conv_ds_fwd: bad descriptor");
+  HK_REQUIRE(d.pad == d.dil * (d.kh / 2), "hk_conv_ds_fwd: pad must equal dil*(k/2) (the 1x1 conv is the centre tap of the kxk one)");
+  HK_REQUIRE(d.out_h == (d.in_h - 1) / d.stride + 1 && d.out_w == (d.in_w - 1) / d.stride + 1, "hk_conv_ds_fwd: out_h/out_w inconsistent");
+  HK_REQUIRE(d.out_c % 128 == 0 && d.in_c % 64 == 0, "hk_conv_ds_fwd: needs out_c %% 128 == 0 and in_c %% 64 == 0");
+  HK_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(y) |
+               reinterpret_cast<uintptr_t>(w_ds_packed) | reinterpret_cast<uintptr_t>(y_ds)) & 15) == 0,
+             "hk_conv_ds_fwd: buffers must be 16-byte aligned");
+  HK_REQUIRE(y != y_ds && x != y && x != y_ds, "hk_conv_ds_fwd: buffers must not alias");
+  ConvTc2Ds ds{w_ds_packed, scale_ds, bias_ds, y_ds, 0};
+  return conv_tc2_launch_impl(d, x, w_packed, scale, bias, nullptr, y, &ds, as_stream(stream));
+}

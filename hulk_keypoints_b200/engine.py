@@ -106,6 +106,7 @@ class InferenceEngine:
         self.stride2_algo = HK_CONV_TCGEN05
         self.stem_on_tensor_cores = True  # bf16 mode: tcgen05 stem; False keeps the fp32 CUDA-core stem
         self.fuse_stem_pool = os.environ.get("HK_STEM_POOL", "1") != "0"   # A/B switch: 0 = stem_tc_kernel + maxpool3x3s2_kernel
+        self.fuse_downsample = os.environ.get("HK_FUSE_DS", "1") != "0"    # A/B switch: 0 = conv1 and the 1x1 downsample as two launches
         self._packed: Optional[Dict[str, _PackedConv]] = None
         self._packed_key = None
         self._plans: Dict[Tuple[int, int, int, int], _Plan] = {}
@@ -186,12 +187,20 @@ class InferenceEngine:
             ho, wo = ops.conv_out_hw(h, w, 3, c1.stride, c1.pad, c1.dil)
             free = [j for j in range(4) if j != cur]
             t = plan.view(free[0], ho, wo, planes)
-            self._conv(c1, x, t, relu=True); n += 1
-            if blk.downsample is not None:
+            ds = P.get(f"b{i}.ds")
+            if (ds is not None and self.fuse_downsample and c1.algo == HK_CONV_TCGEN05 and ds.algo == HK_CONV_TCGEN05
+                    and ds.stride == c1.stride and ops.conv_ds_supported(x, c1.w, ds.w, c1.stride, c1.pad, c1.dil)):
+                # block entry: conv1+bn1+relu and the 1x1 downsample+bn of the same input in one launch (centre-tap operand shared)
                 sc = plan.view(free[1], ho, wo, planes)
-                self._conv(P[f"b{i}.ds"], x, sc, relu=False); n += 1
+                ops.conv_ds(x, c1.w, c1.scale, c1.bias, ds.w, ds.scale, ds.bias, stride=c1.stride, pad=c1.pad, dil=c1.dil,
+                            relu=True, out=t, out_ds=sc); n += 1
             else:
-                sc = x
+                self._conv(c1, x, t, relu=True); n += 1
+                if ds is not None:
+                    sc = plan.view(free[1], ho, wo, planes)
+                    self._conv(ds, x, sc, relu=False); n += 1
+                else:
+                    sc = x
             y = plan.view(free[2], ho, wo, planes)
             self._conv(c2, t, y, relu=True, residual=sc); n += 1
             x, cur, h, w = y, free[2], ho, wo

@@ -73,6 +73,43 @@ def conv_bn_act(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, bi
     return out
 
 
+def conv_ds_supported(x: torch.Tensor, w_packed: torch.Tensor, w_ds_packed: torch.Tensor, stride: int, pad: int, dil: int) -> bool:
+    """Shapes hk_conv_ds_fwd takes: bf16 NHWC, odd square kernel with pad = dil*(k/2) (the 1x1 conv is its centre tap), Cout % 128 == 0."""
+    cout, kh, kw, cin = w_packed.shape
+    return (x.dtype == torch.bfloat16 and w_packed.dtype == torch.bfloat16 and kh == kw and kh % 2 == 1 and pad == dil * (kh // 2)
+            and stride in (1, 2) and cout % 128 == 0 and cin % 64 == 0 and tuple(w_ds_packed.shape) == (cout, 1, 1, cin))
+
+
+def conv_ds(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor,
+            w_ds_packed: torch.Tensor, scale_ds: torch.Tensor, bias_ds: torch.Tensor, *, stride: int, pad: int, dil: int,
+            relu: bool = True, out: Optional[torch.Tensor] = None, out_ds: Optional[torch.Tensor] = None):
+    """Entry of a stride/channel-changing BasicBlock in ONE launch (reference src/resnet.py:56-58 and :64-65 with :184-188):
+    out = relu(scale*conv_kxk(x)+bias), out_ds = scale_ds*conv_1x1(x)+bias_ds; the 1x1 conv reads the centre-tap operand of the
+    kxk one.  Bit-identical to two conv_bn_act calls.  x NHWC bf16; returns (out, out_ds), both (B,Ho,Wo,Cout) bf16."""
+    _need_cuda(x, w_packed, scale, bias, w_ds_packed, scale_ds, bias_ds, out, out_ds)
+    if not conv_ds_supported(x, w_packed, w_ds_packed, stride, pad, dil):
+        raise ValueError("conv_ds: unsupported shape (needs bf16 NHWC, odd k with pad = dil*(k/2), Cout % 128 == 0, Cin % 64 == 0, 1x1 ds weights)")
+    B, H, W, Cin = x.shape
+    cout, kh, kw, cin_w = w_packed.shape
+    if cin_w != Cin:
+        raise ValueError(f"weight cin {cin_w} != input channels {Cin}")
+    Ho, Wo = conv_out_hw(H, W, kh, stride, pad, dil)
+    outs = []
+    for o in (out, out_ds):
+        if o is None:
+            o = torch.empty((B, Ho, Wo, cout), device=x.device, dtype=torch.bfloat16)
+        elif tuple(o.shape) != (B, Ho, Wo, cout) or o.dtype != torch.bfloat16 or not o.is_contiguous():
+            raise ValueError(f"conv_ds outputs must be contiguous bf16 {(B, Ho, Wo, cout)} tensors")
+        outs.append(o)
+    if not (x.is_contiguous() and w_packed.is_contiguous() and w_ds_packed.is_contiguous()):
+        raise ValueError("conv_ds needs contiguous tensors")
+    d = HkConvDesc(B, H, W, Cin, Ho, Wo, cout, kh, kw, stride, pad, dil, int(relu), dtype_code(x.dtype),
+                   dtype_code(torch.bfloat16), 0, HK_CONV_TCGEN05)
+    check(lib().hk_conv_ds_fwd(C.byref(d), ptr(x), ptr(w_packed), ptr(scale), ptr(bias), ptr(outs[0]), ptr(w_ds_packed),
+                               ptr(scale_ds), ptr(bias_ds), ptr(outs[1]), stream_ptr()), "hk_conv_ds_fwd")
+    return outs[0], outs[1]
+
+
 def stem_pack_weights(w_oihw: torch.Tensor) -> torch.Tensor:
     """conv1.weight (64,3,7,7) fp32 -> the (64,256) bf16 K layout of the tensor-core stem (k = r*32 + s*4 + c)."""
     _need_cuda(w_oihw)

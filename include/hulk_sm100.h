@@ -98,6 +98,17 @@ HK_API int hk_conv_bn_act_fwd(const HkConvDesc* desc, const void* x, const void*
                        const float* scale, const float* bias, const void* residual_or_null,
                        void* y, void* stream);
 
+/* Entry of a stride/channel-changing BasicBlock in ONE launch: conv1+bn1+ReLU and the 1x1 downsample conv+bn of the same input.
+ * Replaces src/resnet.py:56-58 (conv1, bn1, relu) together with :64-65 / :184-188 (downsample = conv1x1(stride) + BatchNorm2d).
+ *   y    = relu?( scale    * conv_kxk(x; stride, pad, dil) + bias    )      desc->relu
+ *   y_ds =        scale_ds * conv_1x1(x; stride)           + bias_ds
+ * desc describes the kxk conv; it must be odd-sized with pad == dil*(k/2), so the 1x1 conv reads exactly its centre-tap operand
+ * (the kernel issues the downsample MMAs on the centre-tap boxes against w_ds: no second pass over x).  tcgen05 path only
+ * (bf16 NHWC, out_c % 128 == 0, in_c % 64 == 0, stride 1 or 2); w_ds_packed (out_c, 1, 1, in_c) bf16 from hk_pack_conv_weights.
+ * Bit-identical to two hk_conv_bn_act_fwd calls. */
+HK_API int hk_conv_ds_fwd(const HkConvDesc* desc, const void* x, const void* w_packed, const float* scale, const float* bias, void* y,
+                          const void* w_ds_packed, const float* scale_ds, const float* bias_ds, void* y_ds, void* stream);
+
 /* Stem on the tensor cores (bf16 mode): conv 7x7 s2 p3 (3->64) + folded BN + ReLU.
  * Replaces src/resnet.py:137-139,199-201.  x (B,3,H,W) fp32 NCHW -- the reference's input tensor -- is rounded to
  * bf16 on the fly; y (B,H/2,W/2,64) bf16 NHWC.  w_packed comes from hk_stem_pack_weights (conv1.weight (64,3,7,7)

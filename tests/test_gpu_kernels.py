@@ -528,3 +528,65 @@ def test_conv_tcgen05_haloed_operand_kernel(case):
         test_conv_tcgen05_vs_oracle(case)
     finally:
         os.environ.pop("HK_CONV_HALO", None)
+
+
+# ------------------------------------------------------------------ block entry: conv1 + 1x1 downsample in one launch (src/resnet.py:56-58,64-65,184-188)
+DS_CASES = [
+    # B, H, W, cin, cout, stride, dil
+    (2, 30, 40, 64, 128, 2, 1),      # layer2.0: 3x3 stride 2 + 1x1 stride 2
+    (1, 60, 80, 128, 256, 1, 2),     # layer3.0: dilation 2
+    (1, 60, 80, 256, 512, 1, 4),     # layer4.0: dilation 4, two N tiles of 256
+    (3, 21, 27, 128, 256, 1, 2),     # ragged boxes in both directions, odd tile count
+    (5, 120, 160, 64, 128, 2, 1),    # more work items than CTA pairs (several accumulator turns per cluster)
+    (1, 8, 16, 64, 128, 1, 1),       # a single 256-pixel tile, half of it out of range
+]
+
+
+@pytest.mark.parametrize("case", DS_CASES)
+@pytest.mark.parametrize("early", ["1", "0"])
+def test_conv_ds_block_entry(case, early):
+    """hk_conv_ds_fwd: both outputs bit-identical to two hk_conv_bn_act_fwd launches, and within one bf16 rounding of the fp64 conv on
+    the same bf16 operands.  early = the accumulator-release order of the conv1 epilogue (HK_DS_EARLY)."""
+    import os
+    B, H, W, cin, cout, stride, dil = case
+    g = torch.Generator().manual_seed(77)
+    x = (torch.randn(B, cin, H, W, generator=g)).to(torch.bfloat16)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    wd = torch.randn(cout, cin, 1, 1, generator=g) * (1.0 / cin) ** 0.5
+    s, b = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    sd, bd = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    xd = x.permute(0, 2, 3, 1).contiguous().to(dev())
+    wp, _, _ = ops.pack_conv_weights(w.to(dev()), None, 1e-5, torch.bfloat16)
+    wdp, _, _ = ops.pack_conv_weights(wd.to(dev()), None, 1e-5, torch.bfloat16)
+    sD, bD, sdD, bdD = s.to(dev()), b.to(dev()), sd.to(dev()), bd.to(dev())
+    assert ops.conv_ds_supported(xd, wp, wdp, stride, dil, dil)
+    os.environ["HK_DS_EARLY"] = early
+    try:
+        y, yds = ops.conv_ds(xd, wp, sD, bD, wdp, sdD, bdD, stride=stride, pad=dil, dil=dil, relu=True)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("HK_DS_EARLY", None)
+    # the two-launch path with its default routing (dilation <= 2, stride 1 runs on the haloed kernel: hk_conv_ds_fwd then accumulates
+    # its K blocks in that kernel's order, so the comparison is exact either way)
+    y2 = ops.conv_bn_act(xd, wp, sD, bD, stride=stride, pad=dil, dil=dil, relu=True)
+    yds2 = ops.conv_bn_act(xd, wdp, sdD, bdD, stride=stride, pad=0, dil=1, relu=False)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2), f"conv1 output differs from the separate launch: {(y.float() - y2.float()).abs().max().item()}"
+    assert torch.equal(yds, yds2), f"downsample output differs from the separate launch: {(yds.float() - yds2.float()).abs().max().item()}"
+    for got_t, ww, ss, bb, pad_, dil_, relu_ in ((y, w, s, b, dil, dil, True), (yds, wd, sd, bd, 0, 1, False)):
+        ref = _conv_ref(x.float(), ww.to(torch.bfloat16).float(), ss, bb, None, stride, pad_, dil_, relu_)
+        got = got_t.float().cpu().permute(0, 3, 1, 2).double()
+        err = (got - ref).abs()
+        tol = 2.0 ** -8 * ref.abs() + 1e-3 * max(1.0, ref.abs().max().item())
+        assert (err > tol).sum().item() == 0, f"max err {err.max().item():.4g}"
+
+
+def test_conv_ds_rejects_bad_shapes():
+    x = torch.zeros(1, 16, 16, 64, device=dev(), dtype=torch.bfloat16)
+    wp = torch.zeros(128, 3, 3, 64, device=dev(), dtype=torch.bfloat16)
+    wd = torch.zeros(128, 1, 1, 64, device=dev(), dtype=torch.bfloat16)
+    v = torch.zeros(128, device=dev())
+    with pytest.raises(ValueError):
+        ops.conv_ds(x, wp, v, v, wd, v, v, stride=1, pad=0, dil=1)       # pad != dil*(k/2): the 1x1 is not the centre tap
+    with pytest.raises(ValueError):
+        ops.conv_ds(x.float(), wp, v, v, wd, v, v, stride=1, pad=1, dil=1)  # fp32 activations: tcgen05 path only

@@ -146,6 +146,30 @@ def test_bf16_full_resolution_batch_and_graph_consistency(sd_cal):
     assert np.abs(h_eager[:1].cpu().numpy() - ref).mean() < 2e-2   # untrained flat-noise map: report-grade bound
 
 
+def test_fused_block_entry_and_stem_pool_leave_every_bit_unchanged(sd_cal):
+    """The fused launches (stem+maxpool, conv1 + 1x1 downsample of layer2.0/3.0/4.0) against the one-kernel-per-layer sequence:
+    identical heatmaps and keypoints, three launches fewer per fusion level."""
+    x = rand_img(13, 3, 96, 128).cuda()
+    m = make_model(sd_cal, "bf16")
+    eng = m.engine()
+    assert eng.fuse_downsample and eng.fuse_stem_pool
+    h_fused, kp_fused = eng.forward(x, decode=True)
+    n_fused = eng.plan_for(3, 96, 128).launches
+    m2 = make_model(sd_cal, "bf16")
+    e2 = m2.engine()
+    e2.fuse_downsample = False
+    h_ds, kp_ds = e2.forward(x, decode=True)
+    assert e2.plan_for(3, 96, 128).launches == n_fused + 3
+    m3 = make_model(sd_cal, "bf16")
+    e3 = m3.engine()
+    e3.fuse_downsample = False
+    e3.fuse_stem_pool = False
+    h_plain, kp_plain = e3.forward(x, decode=True)
+    assert e3.plan_for(3, 96, 128).launches == n_fused + 4
+    assert torch.equal(h_fused, h_ds) and torch.equal(h_fused, h_plain)
+    assert torch.equal(kp_fused, kp_ds) and torch.equal(kp_fused, kp_plain)
+
+
 def test_stride2_tensor_core_and_ffma_paths_agree(sd_cal):
     from hulk_keypoints_b200._lib import HK_CONV_FFMA
     m = make_model(sd_cal, "bf16")
