@@ -639,7 +639,7 @@ def measure_train_step(dev, H, W, rank=0, world=1, barrier=None, max_over_ranks=
             steps = 20
             ms, loss = timed(lambda: train_ops.train_step(model, opt, img, uv, sigma=8.0), steps)
             row = {"ms_per_step": ms, "images_per_sec": world * bsz / (ms * 1e-3), "loss": float(loss.item()),
-                   "gpu_launches_per_step": model.train_engine(bsz, H, W).launches + 1}
+                   "gpu_launches_per_step": (model.train_engine(bsz, H, W).split_launches() if world > 1 else model.train_engine(bsz, H, W).launches) + 1}
             if world > 1:
                 for _ in range(2):
                     train_ops.train_step(model, opt, img, uv, sigma=8.0, exchange=False)

@@ -32,7 +32,7 @@ EXPORTS = (
     "hk_head_bwd_workspace_bytes", "hk_head_bwd", "hk_sigmoid_fwd", "hk_sigmoid_bwd", "hk_pack_conv_weights_many",
     # round 2
     "hk_soft_argmax_workspace_bytes", "hk_soft_argmax", "hk_l1_normalize_dim1", "hk_stem_pool_fwd", "hk_stem_pool_fwd_u8",
-    "hk_conv_ds_fwd",
+    "hk_conv_ds_fwd", "hk_bn_acc_bytes", "hk_bn_stats_acc", "hk_bn_apply_fwd_acc", "hk_bn_bwd_acc",
 )
 
 
@@ -93,6 +93,14 @@ def _declare(lib):
     lib.hk_bn_train_stats.argtypes = [vp, ll, i, vp, vp, vp, vp, f, f, vp, vp, vp, vp, vp, sz, vp]
     lib.hk_bn_apply_fwd.restype = i
     lib.hk_bn_apply_fwd.argtypes = [vp, vp, vp, vp, i, vp, vp, ll, i, vp]
+    lib.hk_bn_acc_bytes.restype = sz
+    lib.hk_bn_acc_bytes.argtypes = [i]
+    lib.hk_bn_stats_acc.restype = i
+    lib.hk_bn_stats_acc.argtypes = [vp, ll, i, vp, vp]
+    lib.hk_bn_apply_fwd_acc.restype = i
+    lib.hk_bn_apply_fwd_acc.argtypes = [vp, vp, ll, i, vp, vp, vp, vp, f, f, vp, vp, vp, i, vp, vp, vp]
+    lib.hk_bn_bwd_acc.restype = i
+    lib.hk_bn_bwd_acc.argtypes = [vp, vp, i, vp, vp, vp, vp, ll, i, vp, vp, vp, i, vp, vp, vp]
     lib.hk_bn_train_bwd.restype = i
     lib.hk_bn_train_bwd.argtypes = [vp, vp, i, vp, vp, vp, vp, ll, i, vp, vp, i, vp, vp, vp, sz, vp]
     lib.hk_pack_conv_weights_dgrad.restype = i

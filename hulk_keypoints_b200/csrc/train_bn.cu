@@ -8,9 +8,13 @@
 //             dy = gamma*invstd * (d' - dbeta/N - xhat*dgamma/N)
 // All four kernels are HBM-bound streaming passes (16-byte vectors of 8 bf16 channels); the reductions are two-level
 // (fixed grid of per-block fp32 partials, then a double-precision finalize) and therefore deterministic -- no atomics.
+#include <cooperative_groups.h>
+
 #include "hk_common.cuh"
 
 namespace hk {
+
+namespace cg = cooperative_groups;
 
 constexpr int BN_THREADS = 256;
 constexpr int BN_MAX_BLOCKS = 592;  // 148 SMs x 4
@@ -33,6 +37,23 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
 
 // Block-level reduction of two per-thread 8-channel accumulators over the row lanes of the block, written as
 // partial[blockIdx][0..1][C].  Thread layout: cg = tid % CG (channel group of 8), ty = tid / CG.
+template <class Emit>
+__device__ __forceinline__ void block_reduce_2x8_emit(const float (&a)[8], const float (&b)[8], int C, Emit emit) {
+  __shared__ float sh[2 * BN_THREADS * 8];  // [2][rows][C] with rows*C = 256*8
+  const int CG = C >> 3, cg = threadIdx.x % CG, ty = threadIdx.x / CG, rows = BN_THREADS / CG;
+  float* s0 = sh + (ty * C + cg * 8);
+  float* s1 = s0 + BN_THREADS * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s0[j] = a[j]; s1[j] = b[j]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) {
+    const int which = c / C, ch = c - which * C;
+    const float* src = sh + which * BN_THREADS * 8 + ch;
+    float acc = 0.f;
+    for (int r = 0; r < rows; ++r) acc += src[r * C];
+    emit(c, acc);
+  }
+}
 __device__ __forceinline__ void block_reduce_2x8(const float (&a)[8], const float (&b)[8], int C, float* __restrict__ partial) {
   __shared__ float sh[2 * BN_THREADS * 8];  // [2][rows][C] with rows*C = 256*8
   const int CG = C >> 3, cg = threadIdx.x % CG, ty = threadIdx.x / CG, rows = BN_THREADS / CG;
@@ -253,6 +274,275 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const __nv_bfl
   }
 }
 
+
+// ================================================================================================================================
+// Accumulator variant (the training engine's path): the per-block partial sums go straight into per-channel 128-bit FIXED-POINT
+// accumulators with integer atomics.  Integer addition is associative, so the totals are exact sums of the fp32 block partials
+// whatever order the blocks retire in: deterministic like the two-level reduction above, but without the [blocks][2][C] scratch
+// and -- the point -- without a finalize launch: the apply kernels turn the accumulators into their per-channel coefficients in
+// their own prologue (each block: C channels over 256 threads; block 0 also writes the saved statistics / running stats /
+// parameter gradients).  BatchNorm forward = 2 launches instead of 3, backward = 2 instead of 3 (72 launches per train step).
+// Accumulators must be zero when the reduce kernel starts (the engine clears all of them with one memset node per graph).
+struct alignas(32) BnAcc {
+  unsigned long long lo, hi;   // two's-complement 128-bit integer, unit 2^-50
+  unsigned long long poison;   // != 0: a partial sum was Inf/NaN or beyond the accumulator range -> the total reads as NaN
+  unsigned long long pad;
+};
+constexpr int BN_ACC_FRAC_BITS = 50;
+constexpr int BN_ACC_MAX_C = 2048;
+
+__device__ __forceinline__ void bn_acc_add(BnAcc* a, float p) {
+  const uint32_t bits = __float_as_uint(p);
+  const uint32_t ex = (bits >> 23) & 0xffu;
+  uint32_t man = bits & 0x7fffffu;
+  if (ex == 0xffu) { atomicOr(&a->poison, 1ull); return; }
+  if (ex == 0u && man == 0u) return;
+  const int e = ex ? (int)ex : 1;
+  if (ex) man |= 0x800000u;
+  const int shift = e - 150 + BN_ACC_FRAC_BITS;     // p = man * 2^(e-150)
+  unsigned __int128 v;
+  if (shift >= 0) {
+    if (shift > 100) { atomicOr(&a->poison, 2ull); return; }   // |p| >= 2^74: far outside anything a finite BatchNorm produces
+    v = static_cast<unsigned __int128>(man) << shift;
+  } else {
+    if (shift <= -24) return;                        // below the accumulator's resolution (2^-50)
+    v = man >> (-shift);
+  }
+  if (bits >> 31) v = static_cast<unsigned __int128>(0) - v;
+  const unsigned long long lo = static_cast<unsigned long long>(v), hi = static_cast<unsigned long long>(v >> 64);
+  const unsigned long long old = atomicAdd(&a->lo, lo);
+  const unsigned long long hi2 = hi + ((old + lo) < lo ? 1ull : 0ull);   // carry out of the low word: exact whatever the order
+  if (hi2) atomicAdd(&a->hi, hi2);
+}
+
+__device__ __forceinline__ double bn_acc_read(const BnAcc* a) {
+  const unsigned long long lo = a->lo, hi = a->hi;
+  if (a->poison) return __longlong_as_double(0x7ff8000000000000ll);
+  unsigned __int128 v = (static_cast<unsigned __int128>(hi) << 64) | lo;
+  const bool neg = (hi >> 63) != 0;
+  if (neg) v = static_cast<unsigned __int128>(0) - v;
+  const double d = (static_cast<double>(static_cast<unsigned long long>(v >> 64)) * 18446744073709551616.0 +
+                    static_cast<double>(static_cast<unsigned long long>(v))) * (1.0 / 1125899906842624.0);   // 2^-50
+  return neg ? -d : d;
+}
+
+// Reduce kernels run as clusters of 8 CTAs: every CTA leaves its 2*C block sums in shared memory, CTA 0 of the cluster adds the eight
+// of them over DSMEM in rank order (fixed order: deterministic) and issues the atomics -- 1/8 of the atomic traffic of a per-CTA scheme
+// (at C = 512 and 592 blocks that was 1.2 M same-address L2 atomics per launch, ~8 us; now 74 clusters x 2 K).
+constexpr int BN_CLUSTER = 8;
+constexpr int BN_ACC_MAX_BLOCKS = 592;   // 74 clusters: four CTAs per SM, up to four 16-byte loads in flight per thread
+
+// Shared-memory footprints are kept small on purpose (dynamic, sized by C): these kernels share the SMs with the weight-gradient
+// kernels of the second stream (one 198 KB CTA per SM), and a BatchNorm block that does not fit next to one simply waits for it.
+__device__ __forceinline__ void bn_cluster_emit(const float (&a)[8], const float (&b)[8], int C, BnAcc* __restrict__ acc) {
+  extern __shared__ float s_tot[];   // [2*C]
+  block_reduce_2x8_emit(a, b, C, [&](int c, float v) { s_tot[c] = v; });
+  cg::cluster_group cluster = cg::this_cluster();
+  cluster.sync();
+  if (cluster.block_rank() == 0) {
+    for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) {
+      float t = s_tot[c];
+#pragma unroll
+      for (int r = 1; r < BN_CLUSTER; ++r) t += cluster.map_shared_rank(s_tot, r)[c];
+      bn_acc_add(acc + c, t);
+    }
+  }
+  cluster.sync();   // the peers' shared memory stays alive until CTA 0 has read it
+}
+
+__global__ void __cluster_dims__(BN_CLUSTER, 1, 1) __launch_bounds__(BN_THREADS)
+bn_stats_acc_kernel(const __nv_bfloat16* __restrict__ y, long long P, int C, BnAcc* __restrict__ acc) {
+  const int CG = C >> 3, cg_ = threadIdx.x % CG, ty = threadIdx.x / CG, rows = BN_THREADS / CG;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long step = (long long)gridDim.x * rows;
+  long long r = (long long)blockIdx.x * rows + ty;
+  const __nv_bfloat16* yp = y + cg_ * 8;
+  for (; r + 3 * step < P; r += 4 * step) {   // four independent 16-byte loads in flight per thread
+    Vec8 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = load8(yp + (r + u * step) * C);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += v[u].v[j]; q[j] = fmaf(v[u].v[j], v[u].v[j], q[j]); }
+    }
+  }
+  for (; r < P; r += step) {
+    const Vec8 v = load8(yp + r * C);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += v.v[j]; q[j] = fmaf(v.v[j], v.v[j], q[j]); }
+  }
+  bn_cluster_emit(s, q, C, acc);
+}
+
+// out = relu?(gamma*xhat + beta [+ residual]) with the batch statistics taken from the accumulators (sum y, sum y^2)
+__global__ void __launch_bounds__(BN_THREADS) bn_apply_fwd_acc_kernel(const __nv_bfloat16* __restrict__ y, const BnAcc* __restrict__ acc, long long P,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                     float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                                     float momentum, float eps, float* __restrict__ mean_out,
+                                                                     float* __restrict__ invstd_out, const __nv_bfloat16* __restrict__ residual,
+                                                                     int relu, __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ relu_bits,
+                                                                     long long nvec, int C) {
+  extern __shared__ float s_coef[];   // [2][C]
+  float* s_sc = s_coef;
+  float* s_sh = s_coef + C;
+  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+    const double n = (double)P;
+    const double mean = bn_acc_read(acc + c) / n;
+    double var = bn_acc_read(acc + C + c) / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+    s_sc[c] = g * invstd;
+    s_sh[c] = bt - (float)mean * g * invstd;
+    if (blockIdx.x == 0) {
+      mean_out[c] = (float)mean;
+      invstd_out[c] = invstd;
+      if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      if (running_var) {
+        const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+    }
+  }
+  __syncthreads();
+  const int cg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % (C >> 3));
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = s_sc[cg * 8 + j]; sh[j] = s_sh[cg * 8 + j]; }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const Vec8 v = load8(y + i * 8);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(v.v[j], sc[j], sh[j]);
+    if (residual) {
+      const Vec8 r = load8(residual + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += r.v[j];
+    }
+    if (relu) {
+      if (relu_bits) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m |= (o[j] > 0.f ? 1u : 0u) << j;
+        relu_bits[i] = (uint8_t)m;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+    store8(out + i * 8, o);
+  }
+}
+
+template <bool BITS>
+__global__ void __cluster_dims__(BN_CLUSTER, 1, 1) __launch_bounds__(BN_THREADS)
+bn_bwd_acc_kernel(const __nv_bfloat16* __restrict__ dout, const void* __restrict__ out_mask, const __nv_bfloat16* __restrict__ y,
+                  const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C, BnAcc* __restrict__ acc) {
+  const int CG = C >> 3, cg_ = threadIdx.x % CG, ty = threadIdx.x / CG, rows = BN_THREADS / CG;
+  float mu[8], is[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { mu[j] = mean[cg_ * 8 + j]; is[j] = invstd[cg_ * 8 + j]; }
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long step = (long long)gridDim.x * rows;
+  auto accumulate = [&](Vec8 d, const Vec8& v, uint32_t m, const Vec8& mv) {
+    if (out_mask) {
+      if constexpr (BITS) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d.v[j] = (m >> j) & 1u ? d.v[j] : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d.v[j] = mv.v[j] > 0.f ? d.v[j] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1[j] += d.v[j];
+      s2[j] = fmaf(d.v[j], (v.v[j] - mu[j]) * is[j], s2[j]);
+    }
+  };
+  long long r = (long long)blockIdx.x * rows + ty;
+  for (; r + step < P; r += 2 * step) {   // two rows = four to six independent 16-byte loads in flight per thread
+    const long long o0 = r * C + cg_ * 8, o1 = (r + step) * C + cg_ * 8;
+    const Vec8 d0 = load8(dout + o0), d1 = load8(dout + o1);
+    const Vec8 v0 = load8(y + o0), v1 = load8(y + o1);
+    uint32_t m0 = 0, m1 = 0;
+    Vec8 mv0 = {}, mv1 = {};
+    if (out_mask) {
+      if constexpr (BITS) {
+        m0 = static_cast<const uint8_t*>(out_mask)[o0 >> 3];
+        m1 = static_cast<const uint8_t*>(out_mask)[o1 >> 3];
+      } else {
+        mv0 = load8(static_cast<const __nv_bfloat16*>(out_mask) + o0);
+        mv1 = load8(static_cast<const __nv_bfloat16*>(out_mask) + o1);
+      }
+    }
+    accumulate(d0, v0, m0, mv0);
+    accumulate(d1, v1, m1, mv1);
+  }
+  for (; r < P; r += step) {
+    const long long off = r * C + cg_ * 8;
+    const Vec8 d = load8(dout + off);
+    const Vec8 v = load8(y + off);
+    uint32_t m = 0;
+    Vec8 mv = {};
+    if (out_mask) {
+      if constexpr (BITS) m = static_cast<const uint8_t*>(out_mask)[off >> 3];
+      else mv = load8(static_cast<const __nv_bfloat16*>(out_mask) + off);
+    }
+    accumulate(d, v, m, mv);
+  }
+  bn_cluster_emit(s1, s2, C, acc);
+}
+
+template <bool BITS>
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_acc_kernel(const __nv_bfloat16* __restrict__ dout, const void* __restrict__ out_mask,
+                                                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                                     const BnAcc* __restrict__ acc, long long P, float* __restrict__ dgamma,
+                                                                     float* __restrict__ dbeta, int accumulate, __nv_bfloat16* __restrict__ dy,
+                                                                     __nv_bfloat16* __restrict__ dmasked, long long nvec, int C) {
+  extern __shared__ float s_k3[];   // [3][C]
+  float* s_k[3] = {s_k3, s_k3 + C, s_k3 + 2 * C};
+  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+    const double s1 = bn_acc_read(acc + c), s2 = bn_acc_read(acc + C + c);
+    const float a = (gamma ? gamma[c] : 1.f) * invstd[c];
+    const float c1 = (float)(s1 / (double)P), c2 = (float)(s2 / (double)P);
+    const float k1 = -a * c2 * invstd[c];
+    s_k[0][c] = a;
+    s_k[1][c] = k1;
+    s_k[2][c] = -a * c1 - k1 * mean[c];
+    if (blockIdx.x == 0) {
+      if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s1;
+      if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s2;
+    }
+  }
+  __syncthreads();
+  const int c0 = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % (C >> 3)) * 8;
+  float k0[8], k1[8], k2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { k0[j] = s_k[0][c0 + j]; k1[j] = s_k[1][c0 + j]; k2[j] = s_k[2][c0 + j]; }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    Vec8 d = load8(dout + i * 8);
+    const Vec8 v = load8(y + i * 8);
+    if (out_mask) {
+      if constexpr (BITS) {
+        const uint32_t m = static_cast<const uint8_t*>(out_mask)[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d.v[j] = (m >> j) & 1u ? d.v[j] : 0.f;
+      } else {
+        const Vec8 m = load8(static_cast<const __nv_bfloat16*>(out_mask) + i * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d.v[j] = m.v[j] > 0.f ? d.v[j] : 0.f;
+      }
+    }
+    if (dmasked) store8(dmasked + i * 8, d.v);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(k0[j], d.v[j], fmaf(k1[j], v.v[j], k2[j]));
+    store8(dy + i * 8, o);
+  }
+}
+
 static int bn_grid_rows(long long P, int C) {
   const int rows = BN_THREADS / (C >> 3);
   long long blocks = ceil_div_ll(P, (long long)rows * 16);  // >= 16 row iterations per block: few partials to finalize
@@ -264,6 +554,38 @@ static int bn_grid_elems(long long nvec) {
   long long blocks = ceil_div_ll(nvec, BN_THREADS);
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  return (int)blocks;
+}
+// a whole number of 8-CTA clusters, at most one resident wave (and at most BN_ACC_MAX_BLOCKS CTAs)
+template <int TAG, class K>   // TAG: one cached occupancy per kernel instantiation (instantiations may share a function type)
+static int bn_grid_acc_rows(K kernel, long long P, int C, size_t smem) {
+  static int resident = 0;
+  if (resident == 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BN_THREADS, smem) != cudaSuccess || occ < 1) occ = 2;
+    resident = occ * sm_count() / BN_CLUSTER * BN_CLUSTER;
+    if (resident > BN_ACC_MAX_BLOCKS) resident = BN_ACC_MAX_BLOCKS;
+  }
+  const int rows = BN_THREADS / (C >> 3);
+  long long blocks = ceil_div_ll(P, (long long)rows * 16);
+  if (blocks > resident) blocks = resident;
+  blocks = ceil_div_ll(blocks, BN_CLUSTER) * BN_CLUSTER;
+  return (int)blocks;
+}
+// Grid of the accumulator apply kernels.  Every block pays the coefficient prologue, so few fat blocks; and a grid-stride loop over equal
+// shares finishes in whole waves only if the grid is a multiple of what is resident at once (a 1184-block grid at 5 resident blocks per
+// SM ran a full wave plus a 3/5 one: 1.4x the time of the 16-blocks-per-SM grid it replaced).
+template <int TAG, class K>
+static int bn_grid_apply(K kernel, long long nvec, size_t smem) {
+  static int resident = 0;   // per kernel instantiation
+  if (resident == 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BN_THREADS, smem) != cudaSuccess || occ < 1) occ = 4;
+    resident = occ * sm_count();
+  }
+  long long blocks = ceil_div_ll(nvec, (long long)BN_THREADS * 4);   // >= 4 vectors per thread
+  if (blocks >= resident) blocks = (blocks >= 2LL * resident) ? 2LL * resident : resident;
+  if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
 static bool bn_c_ok(int C) { return C >= 8 && C <= 2048 && (C & 7) == 0 && (BN_THREADS % (C >> 3)) == 0; }
@@ -296,7 +618,7 @@ int hk_bn_apply_fwd(const void* y, const float* scale, const float* shift, const
                     void* relu_bits_or_null, long long P, int C, void* stream) {
   using namespace hk;
   HK_REQUIRE(y && scale && shift && out, "hk_bn_apply_fwd: null pointer");
-  HK_REQUIRE(P > 0 && C >= 8 && (C & 7) == 0, "hk_bn_apply_fwd: bad shape");
+  HK_REQUIRE(P > 0 && bn_c_ok(C), "hk_bn_apply_fwd: unsupported shape P=%lld C=%d (C must be a power-of-two multiple of 8 up to 2048)", P, C);
   const long long nvec = P * (C >> 3);
   bn_apply_fwd_kernel<<<bn_grid_elems(nvec), BN_THREADS, 0, as_stream(stream)>>>(
       static_cast<const __nv_bfloat16*>(y), scale, shift, static_cast<const __nv_bfloat16*>(residual_or_null), relu,
@@ -332,6 +654,57 @@ int hk_bn_train_bwd(const void* dout, const void* out_mask_or_null, int mask_is_
     bn_bwd_apply_kernel<false><<<bn_grid_elems(nvec), BN_THREADS, 0, as_stream(stream)>>>(d, m, yy, mean, invstd, coef, static_cast<__nv_bfloat16*>(dy),
                                                                                         static_cast<__nv_bfloat16*>(dmasked_or_null), nvec, C);
   return check_launch("bn_bwd_apply_kernel");
+}
+
+size_t hk_bn_acc_bytes(int C) { return 2 * (size_t)C * sizeof(hk::BnAcc); }
+
+int hk_bn_stats_acc(const void* y, long long P, int C, void* acc, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(y && acc, "hk_bn_stats_acc: null pointer");
+  HK_REQUIRE(P > 0 && bn_c_ok(C), "hk_bn_stats_acc: unsupported shape P=%lld C=%d (C must be a power-of-two multiple of 8 up to 2048)", P, C);
+  HK_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(acc) & 31) == 0, "hk_bn_stats_acc: misaligned buffer");
+  bn_stats_acc_kernel<<<bn_grid_acc_rows<0>(bn_stats_acc_kernel, P, C, 2 * (size_t)C * 4), BN_THREADS, 2 * (size_t)C * 4, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y), P, C, static_cast<BnAcc*>(acc));
+  return check_launch("bn_stats_acc_kernel");
+}
+
+int hk_bn_apply_fwd_acc(const void* y, const void* acc, long long P, int C, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, float momentum, float eps, float* mean_out, float* invstd_out, const void* residual_or_null,
+                        int relu, void* out, void* relu_bits_or_null, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(y && acc && mean_out && invstd_out && out, "hk_bn_apply_fwd_acc: null pointer");
+  HK_REQUIRE(P > 0 && bn_c_ok(C), "hk_bn_apply_fwd_acc: unsupported shape P=%lld C=%d", P, C);
+  const long long nvec = P * (C >> 3);
+  bn_apply_fwd_acc_kernel<<<bn_grid_apply<0>(bn_apply_fwd_acc_kernel, nvec, 2 * (size_t)C * 4), BN_THREADS, 2 * (size_t)C * 4, as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), static_cast<const BnAcc*>(acc), P, gamma, beta, running_mean, running_var, momentum, eps, mean_out,
+      invstd_out, static_cast<const __nv_bfloat16*>(residual_or_null), relu, static_cast<__nv_bfloat16*>(out),
+      static_cast<uint8_t*>(relu_bits_or_null), nvec, C);
+  return check_launch("bn_apply_fwd_acc_kernel");
+}
+
+int hk_bn_bwd_acc(const void* dout, const void* out_mask_or_null, int mask_is_bits, const void* y, const float* mean, const float* invstd,
+                  const float* gamma, long long P, int C, void* acc, float* dgamma, float* dbeta, int accumulate, void* dy,
+                  void* dmasked_or_null, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(dout && y && mean && invstd && dy && acc, "hk_bn_bwd_acc: null pointer");
+  HK_REQUIRE(P > 0 && bn_c_ok(C), "hk_bn_bwd_acc: unsupported shape P=%lld C=%d", P, C);
+  HK_REQUIRE((reinterpret_cast<uintptr_t>(acc) & 31) == 0, "hk_bn_bwd_acc: misaligned accumulator buffer");
+  const __nv_bfloat16* d = static_cast<const __nv_bfloat16*>(dout);
+  const __nv_bfloat16* yy = static_cast<const __nv_bfloat16*>(y);
+  BnAcc* a = static_cast<BnAcc*>(acc);
+  const int blocks = mask_is_bits ? bn_grid_acc_rows<1>(bn_bwd_acc_kernel<true>, P, C, 2 * (size_t)C * 4) : bn_grid_acc_rows<2>(bn_bwd_acc_kernel<false>, P, C, 2 * (size_t)C * 4);
+  if (mask_is_bits) bn_bwd_acc_kernel<true><<<blocks, BN_THREADS, 2 * (size_t)C * 4, as_stream(stream)>>>(d, out_mask_or_null, yy, mean, invstd, P, C, a);
+  else bn_bwd_acc_kernel<false><<<blocks, BN_THREADS, 2 * (size_t)C * 4, as_stream(stream)>>>(d, out_mask_or_null, yy, mean, invstd, P, C, a);
+  int rc = check_launch("bn_bwd_acc_kernel");
+  if (rc) return rc;
+  const long long nvec = P * (C >> 3);
+  const int ablocks = mask_is_bits ? bn_grid_apply<1>(bn_bwd_apply_acc_kernel<true>, nvec, 3 * (size_t)C * 4) : bn_grid_apply<2>(bn_bwd_apply_acc_kernel<false>, nvec, 3 * (size_t)C * 4);
+  if (mask_is_bits)
+    bn_bwd_apply_acc_kernel<true><<<ablocks, BN_THREADS, 3 * (size_t)C * 4, as_stream(stream)>>>(d, out_mask_or_null, yy, mean, invstd, gamma, a, P, dgamma, dbeta, accumulate,
+                                                                               static_cast<__nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dmasked_or_null), nvec, C);
+  else
+    bn_bwd_apply_acc_kernel<false><<<ablocks, BN_THREADS, 3 * (size_t)C * 4, as_stream(stream)>>>(d, out_mask_or_null, yy, mean, invstd, gamma, a, P, dgamma, dbeta, accumulate,
+                                                                                static_cast<__nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dmasked_or_null), nvec, C);
+  return check_launch("bn_bwd_apply_acc_kernel");
 }
 
 }  // extern "C"

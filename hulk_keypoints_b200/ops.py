@@ -354,6 +354,51 @@ def bn_train_bwd(dout: torch.Tensor, out_mask: Optional[torch.Tensor], y: torch.
     return dy
 
 
+def bn_acc_bytes(C_: int) -> int:
+    """Bytes of the 2*C fixed-point accumulators of one BatchNorm reduction (hk_bn_stats_acc / hk_bn_bwd_acc); must be zeroed before use."""
+    return int(lib().hk_bn_acc_bytes(C_))
+
+
+def bn_stats_acc(y: torch.Tensor, acc: torch.Tensor) -> None:
+    """acc (zeroed, bn_acc_bytes(C) bytes) += per-channel (sum y, sum y^2) of y (...,C) bf16 NHWC: exact integer accumulation."""
+    _need_cuda(y, acc)
+    Cc = y.shape[-1]
+    if acc.numel() * acc.element_size() < bn_acc_bytes(Cc):
+        raise ValueError("accumulator buffer too small")
+    check(lib().hk_bn_stats_acc(ptr(y), C.c_longlong(y.numel() // Cc), Cc, ptr(acc), stream_ptr()), "hk_bn_stats_acc")
+
+
+def bn_apply_acc(y: torch.Tensor, acc: torch.Tensor, gamma, beta, running_mean, running_var, momentum: float, eps: float,
+                 mean: torch.Tensor, invstd: torch.Tensor, relu: bool, residual: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None, relu_bits: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Train-mode BatchNorm apply straight from the accumulators of bn_stats_acc: batch statistics (saved in mean / invstd), running
+    statistics, out = relu?(gamma*xhat + beta [+ residual]) -- no finalize launch in between."""
+    _need_cuda(y, acc, mean, invstd, residual, out, relu_bits)
+    Cc = y.shape[-1]
+    P = y.numel() // Cc
+    if out is None:
+        out = torch.empty_like(y)
+    if relu_bits is not None and (relu_bits.dtype != torch.uint8 or relu_bits.numel() < y.numel() // 8):
+        raise ValueError("relu_bits must be a uint8 tensor of numel/8 bytes")
+    check(lib().hk_bn_apply_fwd_acc(ptr(y), ptr(acc), C.c_longlong(P), Cc, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+                                    C.c_float(momentum), C.c_float(eps), ptr(mean), ptr(invstd), ptr(residual), int(relu), ptr(out),
+                                    ptr(relu_bits), stream_ptr()), "hk_bn_apply_fwd_acc")
+    return out
+
+
+def bn_bwd_acc(dout: torch.Tensor, out_mask: Optional[torch.Tensor], y: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor,
+               gamma: Optional[torch.Tensor], acc: torch.Tensor, dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor],
+               dy: torch.Tensor, dmasked: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """bn_train_bwd through zeroed accumulators (bn_acc_bytes(C)): reduce + apply, two launches."""
+    _need_cuda(dout, out_mask, y, mean, invstd, acc, dy, dmasked)
+    Cc = y.shape[-1]
+    P = y.numel() // Cc
+    bits = out_mask is not None and out_mask.dtype == torch.uint8
+    check(lib().hk_bn_bwd_acc(ptr(dout), ptr(out_mask), int(bits), ptr(y), ptr(mean), ptr(invstd), ptr(gamma), C.c_longlong(P), Cc, ptr(acc),
+                              ptr(dgamma), ptr(dbeta), int(accumulate), ptr(dy), ptr(dmasked), stream_ptr()), "hk_bn_bwd_acc")
+    return dy
+
+
 def pack_conv_weights_dgrad(w_oihw: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """OIHW fp32 -> (cin, kh, kw, cout) bf16 with flipped taps: the weights of the data-gradient convolution."""
     _need_cuda(w_oihw, out)

@@ -93,6 +93,19 @@ class TrainEngine:
             h, w = c1.Ho, c1.Wo
         self.h8, self.w8 = h, w
         self.convs: List[_ConvT] = [self.stem] + [c for b in self.blocks for c in (b[0], b[1], b[2]) if c is not None]
+        # BatchNorm reductions through exact fixed-point accumulators (hk_bn_stats_acc / hk_bn_bwd_acc): no finalize launches, 72 fewer
+        # launches per step.  One flat buffer per direction, sliced per conv in self.convs order (stem, then the blocks in order), so the
+        # early part of the two-phase backward (stem + blocks < split_block) is a prefix.  HK_BN_ACC=0: the three-launch path.
+        self.use_bn_acc = os.environ.get("HK_BN_ACC", "1") != "0"
+        offs_acc, tot = [], 0
+        for c in self.convs:
+            offs_acc.append(tot)
+            tot += ops.bn_acc_bytes(c.cout)
+        self.acc_fwd = torch.zeros(tot, device=dev, dtype=torch.uint8)
+        self.acc_bwd = torch.zeros(tot, device=dev, dtype=torch.uint8)
+        for c, o in zip(self.convs, offs_acc):
+            c.acc_f = self.acc_fwd[o:o + ops.bn_acc_bytes(c.cout)]
+            c.acc_b = self.acc_bwd[o:o + ops.bn_acc_bytes(c.cout)]
         K = self.K
         self.logits_lr = torch.empty((B, K, h, w), device=dev, dtype=torch.float32)
         self.logits_up = torch.empty((B, K, H, W), device=dev, dtype=torch.float32)
@@ -108,6 +121,7 @@ class TrainEngine:
         # first block of layer3: everything from here to the end of the parameter list (layer3, layer4, fc) is the "late" part
         self.split_block = 7
         first_late = self.blocks[self.split_block][0].conv.weight
+        self.acc_early_bytes = offs_acc[self.convs.index(self.blocks[self.split_block][0])]   # accumulators of the stem + early blocks
         self.late_offset = next(o for p, o in zip(self.params, offs) if p is first_late)
         self._bwd_state = None
         self._scratch: Dict[Tuple, torch.Tensor] = {}
@@ -181,6 +195,12 @@ class TrainEngine:
         """raw conv -> batch statistics (+ running stats) -> fused normalise (+ shortcut) (+ ReLU)."""
         ops.conv_bn_act(x, c.w_fwd, c.one_out, c.zero_out, stride=c.stride, pad=c.pad, dil=c.dil, relu=False, out=c.y)
         bn = c.bn
+        if self.use_bn_acc:
+            ops.bn_stats_acc(c.y, c.acc_f)
+            ops.bn_apply_acc(c.y, c.acc_f, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.momentum, bn.eps, c.mean, c.invstd,
+                             relu=relu, residual=residual, out=out, relu_bits=c.relu_bits if relu and self.use_relu_bits else None)
+            c.relu_out = out if relu else None
+            return 3
         ops.bn_train_stats(c.y, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.momentum, bn.eps, c.mean, c.invstd,
                            c.scale, c.shift, self.bn_ws if ws is None else ws)
         ops.bn_apply(c.y, c.scale, c.shift, relu=relu, residual=residual, out=out, relu_bits=c.relu_bits if relu and self.use_relu_bits else None)
@@ -206,6 +226,9 @@ class TrainEngine:
         """relu: the BN output went through a ReLU; its mask is c.relu_bits (written by the forward apply pass)."""
         bn = c.bn
         mask = None if not relu else (c.relu_bits if self.use_relu_bits else c.relu_out)
+        if self.use_bn_acc:
+            ops.bn_bwd_acc(dout, mask, c.y, c.mean, c.invstd, bn.weight.data, c.acc_b, self._g(bn.weight), self._g(bn.bias), dy, dmasked=dmasked)
+            return 2
         ops.bn_train_bwd(dout, mask, c.y, c.mean, c.invstd, bn.weight.data, self._g(bn.weight), self._g(bn.bias), dy,
                          self.bn_ws if ws is None else ws, dmasked=dmasked)
         return 3
@@ -265,13 +288,22 @@ class TrainEngine:
         check(lib().hk_stem_pack_weights(ptr(net.conv1.weight.data), ptr(self.stem_w), stream_ptr()), "hk_stem_pack_weights")
         self._on_wgrad_stream(self._pack_all)   # the block convs' weights are repacked while the stem, its BN and the maxpool run
         n += 2
+        if self.use_bn_acc:
+            self.acc_fwd.zero_()                # the forward accumulators of every BatchNorm of this step
+            n += 1
         # ---------------- forward (train mode) ----------------
         st = self.stem
         ops.stem_conv(self.x, self.stem_w, st.one_out, st.zero_out, relu=False, out=st.y)
         bn = st.bn
-        ops.bn_train_stats(st.y, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.momentum, bn.eps, st.mean, st.invstd,
-                           st.scale, st.shift, self.bn_ws)
-        ops.bn_apply(st.y, st.scale, st.shift, relu=True, out=self.a0, relu_bits=st.relu_bits if self.use_relu_bits else None)
+        if self.use_bn_acc:
+            ops.bn_stats_acc(st.y, st.acc_f)
+            ops.bn_apply_acc(st.y, st.acc_f, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.momentum, bn.eps, st.mean,
+                             st.invstd, relu=True, out=self.a0, relu_bits=st.relu_bits if self.use_relu_bits else None)
+            n -= 1
+        else:
+            ops.bn_train_stats(st.y, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.momentum, bn.eps, st.mean, st.invstd,
+                               st.scale, st.shift, self.bn_ws)
+            ops.bn_apply(st.y, st.scale, st.shift, relu=True, out=self.a0, relu_bits=st.relu_bits if self.use_relu_bits else None)
         st.relu_out = self.a0
         ops.maxpool3x3s2(self.a0, out=self.p0)
         self._join_wgrad_stream()               # packed weights ready
@@ -319,6 +351,10 @@ class TrainEngine:
         net, K, st = self.net, self.K, self.stem
         n = 0
         nb = len(self.blocks)
+        if self.use_bn_acc:   # the backward accumulators this part is going to fill
+            e = self.acc_early_bytes
+            (self.acc_bwd if part == "all" else self.acc_bwd[e:] if part == "late" else self.acc_bwd[:e]).zero_()
+            n += 1
         if part in ("all", "late"):
             feat = self.blocks[-1][5]
             fc_w = net.fc.weight.data[:K].view(K, 512)
@@ -423,17 +459,18 @@ class TrainEngine:
         """Eager, or capture-once / replay of one of the split graphs.  `name` "fwd" marks graphs that advance the BN buffers."""
         if name == "fwd":
             self.model.mark_weights_changed()   # BatchNorm running stats move (raw-pointer writes)
+        gname = name_key or name
+        counts = self.__dict__.setdefault("_split_launches", {})
         if not self.use_cuda_graph:
-            fn()
+            counts[gname] = fn()
             return
         key = self._key()
         graphs = self.__dict__.setdefault("_split_graphs", {})
-        gname = name_key or name
         ent = graphs.get(gname)
         if ent is None or ent[1] != key:
             if name == "fwd":  # the warm-up run advances the BN buffers once more than the captured replay: restore them
                 saved = [(c.bn.running_mean.clone(), c.bn.running_var.clone(), c.bn.num_batches_tracked.clone()) for c in self.convs]
-            fn()
+            counts[gname] = fn()
             torch.cuda.current_stream().synchronize()
             if name == "fwd":
                 for c, (m, v, t) in zip(self.convs, saved):
@@ -455,8 +492,9 @@ class TrainEngine:
         n = self.logits_up.numel()
 
         def fn():
-            self._enqueue_forward()
+            k = self._enqueue_forward()
             check(lib().hk_sigmoid_fwd(ptr(self.logits_up), ptr(self.heat), C.c_longlong(n), stream_ptr()), "hk_sigmoid_fwd")
+            return k + 1
 
         with torch.no_grad():
             self.x.copy_(img)
@@ -469,7 +507,7 @@ class TrainEngine:
 
         def fn():
             check(lib().hk_sigmoid_bwd(ptr(self.heat), ptr(self.g_heat), ptr(self.g_up), C.c_longlong(n), stream_ptr()), "hk_sigmoid_bwd")
-            self._enqueue_backward()
+            return 1 + self._enqueue_backward()
 
         with torch.no_grad():
             self.g_heat.copy_(grad_heat)
@@ -482,7 +520,7 @@ class TrainEngine:
             raise ValueError(f"expected a CUDA image batch of shape {(self.B, 3, self.H, self.W)}")
 
         def fn():
-            self._enqueue_forward(); self._enqueue_loss(); self._enqueue_backward("late")
+            return self._enqueue_forward() + self._enqueue_loss() + self._enqueue_backward("late")
 
         with torch.no_grad():
             self.x.copy_(img)
@@ -495,6 +533,10 @@ class TrainEngine:
         """Phase 2: backward of layer2, layer1 and the stem (gradients flat_grad[:late_offset])."""
         with torch.no_grad():
             self._run("bwd_early", lambda: self._enqueue_backward("early"))
+
+    def split_launches(self) -> int:
+        """Kernel launches of the split graphs captured so far (two-phase data-parallel step: "late" + "bwd_early")."""
+        return int(sum(v or 0 for v in self.__dict__.get("_split_launches", {}).values()))
 
     def grad(self, p: torch.nn.Parameter) -> torch.Tensor:
         return self.grad_of[id(p)]

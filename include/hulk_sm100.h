@@ -231,6 +231,24 @@ HK_API int hk_bn_train_bwd(const void* dout, const void* out_mask_or_null, int m
                            const float* gamma, long long P, int C, float* dgamma, float* dbeta, int accumulate, void* dy,
                            void* dmasked_or_null, void* ws, size_t ws_bytes, void* stream);
 
+/* The same three BatchNorm steps without the finalize launches (the training engine's path; 2 + 2 launches per BatchNorm instead of
+ * 3 + 3).  The reduce kernels add their per-block fp32 partial sums into per-channel 128-bit fixed-point accumulators with integer
+ * atomics (exact, hence independent of the order the blocks retire in: deterministic), and the apply kernels derive their per-channel
+ * coefficients from the accumulators in their own prologue.  acc: hk_bn_acc_bytes(C) bytes (2*C accumulators of 32 bytes), 32-byte
+ * aligned, ZERO when the reduce kernel starts (one cudaMemsetAsync over all accumulators of a step); forward and backward of one
+ * BatchNorm use different accumulator buffers.
+ *   hk_bn_stats_acc     : acc[0..C) += sum_p y, acc[C..2C) += sum_p y^2
+ *   hk_bn_apply_fwd_acc : mean/invstd (saved for the backward) + running stats from acc, then out = relu?(gamma*xhat + beta [+ residual])
+ *   hk_bn_bwd_acc       : acc += (sum d', sum d'*xhat), then dgamma/dbeta and dy (+ d') exactly as hk_bn_train_bwd */
+HK_API size_t hk_bn_acc_bytes(int C);
+HK_API int hk_bn_stats_acc(const void* y, long long P, int C, void* acc, void* stream);
+HK_API int hk_bn_apply_fwd_acc(const void* y, const void* acc, long long P, int C, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float momentum, float eps, float* mean_out, float* invstd_out,
+                               const void* residual_or_null, int relu, void* out, void* relu_bits_or_null, void* stream);
+HK_API int hk_bn_bwd_acc(const void* dout, const void* out_mask_or_null, int mask_is_bits, const void* y, const float* mean,
+                         const float* invstd, const float* gamma, long long P, int C, void* acc, float* dgamma, float* dbeta,
+                         int accumulate, void* dy, void* dmasked_or_null, void* stream);
+
 /* All convs of the network repacked in ONE launch (the training step repacks every step).  items_dev: device array of HkPackItem;
  * w_dgrad may be NULL (stem: no data gradient).  max_elems = max over items of cout*cin*khw. */
 typedef struct HkPackItem {

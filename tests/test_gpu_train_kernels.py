@@ -96,6 +96,79 @@ def test_bn_train_backward_matches_autograd(C_, with_relu):
     assert rel_err(dgamma, g32.grad) < 1e-3 and rel_err(dbeta, b32.grad) < 1e-3
 
 
+# ------------------------------------------------------------------ BatchNorm through exact fixed-point accumulators (no finalize launch)
+@pytest.mark.parametrize("C_,shape,relu", [(64, (2, 24, 40), True), (128, (3, 15, 20), False), (512, (2, 8, 16), True), (64, (4, 120, 160), True)])
+def test_bn_accumulator_path_matches_three_launch_path(C_, shape, relu):
+    """hk_bn_stats_acc + hk_bn_apply_fwd_acc and hk_bn_bwd_acc against hk_bn_train_stats / hk_bn_apply_fwd / hk_bn_train_bwd on the same
+    operands: statistics to fp32 rounding (the accumulators add the block partials exactly, the three-launch path adds them in fp32 and
+    double), outputs to one bf16 ulp where a coefficient moved, ReLU masks and d' exactly; and bit-reproducible run to run."""
+    torch.manual_seed(3 * C_ + shape[0])
+    B, H, W = shape
+    y = bf(torch.randn(B, H, W, C_, device=DEV) * 2.0 + 0.7)
+    res = bf(torch.randn(B, H, W, C_, device=DEV))
+    dout = bf(torch.randn(B, H, W, C_, device=DEV) * 1e-3)
+    gamma, beta = torch.rand(C_, device=DEV) + 0.5, torch.randn(C_, device=DEV) * 0.1
+    rm0, rv0 = torch.randn(C_, device=DEV) * 0.1, torch.rand(C_, device=DEV) + 0.5
+    ws = ops.bn_workspace(C_, DEV)
+    # three-launch path
+    rm, rv = rm0.clone(), rv0.clone()
+    mean, invstd, scale, shift = (torch.empty(C_, device=DEV) for _ in range(4))
+    ops.bn_train_stats(y, gamma, beta, rm, rv, 0.1, 1e-5, mean, invstd, scale, shift, ws)
+    bits = torch.zeros(y.numel() // 8, device=DEV, dtype=torch.uint8)
+    out = ops.bn_apply(y, scale, shift, relu=relu, residual=res, relu_bits=bits if relu else None)
+    dg, db, dy, dm = torch.empty(C_, device=DEV), torch.empty(C_, device=DEV), torch.empty_like(y), torch.empty_like(y)
+    ops.bn_train_bwd(dout, bits if relu else None, y, mean, invstd, gamma, dg, db, dy, ws, dmasked=dm)
+
+    def acc_path():
+        rm2, rv2 = rm0.clone(), rv0.clone()
+        mean2, invstd2 = torch.empty(C_, device=DEV), torch.empty(C_, device=DEV)
+        acc_f = torch.zeros(ops.bn_acc_bytes(C_), device=DEV, dtype=torch.uint8)
+        acc_b = torch.zeros(ops.bn_acc_bytes(C_), device=DEV, dtype=torch.uint8)
+        ops.bn_stats_acc(y, acc_f)
+        bits2 = torch.zeros(y.numel() // 8, device=DEV, dtype=torch.uint8)
+        out2 = ops.bn_apply_acc(y, acc_f, gamma, beta, rm2, rv2, 0.1, 1e-5, mean2, invstd2, relu=relu, residual=res,
+                                relu_bits=bits2 if relu else None)
+        dg2, db2, dy2, dm2 = torch.empty(C_, device=DEV), torch.empty(C_, device=DEV), torch.empty_like(y), torch.empty_like(y)
+        ops.bn_bwd_acc(dout, bits2 if relu else None, y, mean2, invstd2, gamma, acc_b, dg2, db2, dy2, dmasked=dm2)
+        torch.cuda.synchronize()
+        return rm2, rv2, mean2, invstd2, bits2, out2, dg2, db2, dy2, dm2
+
+    a = acc_path()
+    b = acc_path()
+    for t1, t2 in zip(a, b):
+        assert torch.equal(t1, t2)                                     # atomics, yet bit-reproducible
+    rm2, rv2, mean2, invstd2, bits2, out2, dg2, db2, dy2, dm2 = a
+    assert torch.allclose(mean2, mean, rtol=2e-6, atol=1e-6) and torch.allclose(invstd2, invstd, rtol=2e-6)
+    assert torch.allclose(rm2, rm, rtol=2e-6, atol=1e-6) and torch.allclose(rv2, rv, rtol=2e-6)
+    d_out = (out2.float() - out.float()).abs()
+    assert (d_out <= 2.0 ** -7 * out.float().abs() + 1e-6).all()          # at most one bf16 ulp
+    assert (d_out > 0).float().mean().item() < 0.02
+    if relu:
+        assert (bits2 != bits).float().mean().item() < 1e-3
+    else:
+        assert torch.equal(dm2, dm)
+    assert rel_err(dg2, dg) < 1e-4 and rel_err(db2, db) < 1e-4 and rel_err(dy2.float(), dy.float()) < 2e-3
+
+
+def test_bn_accumulator_poison_and_exactness():
+    """Inf/NaN anywhere in a channel reads back as NaN statistics for that channel only; a channel of exactly representable values gives
+    the exact mean (the integer accumulators add the block partials without rounding)."""
+    C_ = 64
+    y = torch.zeros(2, 16, 16, C_, device=DEV)
+    y[..., 1] = 3.0
+    y[0, 3, 5, 2] = float("inf")
+    y[..., 4] = torch.arange(512, device=DEV, dtype=torch.float32).view(2, 16, 16) - 200.0
+    y = bf(y)
+    acc = torch.zeros(ops.bn_acc_bytes(C_), device=DEV, dtype=torch.uint8)
+    ops.bn_stats_acc(y, acc)
+    mean, invstd = torch.empty(C_, device=DEV), torch.empty(C_, device=DEV)
+    ops.bn_apply_acc(y, acc, None, None, None, None, 0.1, 1e-5, mean, invstd, relu=False)
+    torch.cuda.synchronize()
+    assert mean[0].item() == 0.0 and mean[1].item() == 3.0 and torch.isnan(mean[2]).item()
+    assert mean[4].item() == y[..., 4].double().mean().item()
+    assert not torch.isnan(mean[3]).item() and abs(invstd[1].item() - 1.0 / (1e-5 ** 0.5)) / (1.0 / (1e-5 ** 0.5)) < 1e-6
+
+
 # ------------------------------------------------------------------ conv data gradient = forward kernel on repacked weights
 @pytest.mark.parametrize("cin,cout,k,dil,hw", [(64, 64, 3, 1, (24, 32)), (128, 128, 3, 1, (16, 32)), (128, 256, 3, 2, (16, 32)),
                                                (256, 256, 3, 2, (12, 16)), (512, 512, 3, 4, (12, 16)), (256, 512, 1, 1, (12, 16))])

@@ -1,5 +1,6 @@
-"""Summarise an .ncu-rep (read here, no GPU needed) into a small CSV for profiles/.
-Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_prof.csv"""
+"""Summarise an .ncu-rep -- or the `ncu -i rep --page raw --csv` dump of one, made on the GPU box when the report itself is too large to
+bring back -- into a small CSV for profiles/ (no GPU needed).
+Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep|prof_raw.csv profiles/r01_prof.csv"""
 import csv
 import io
 import subprocess
@@ -12,12 +13,17 @@ METRICS = [
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
     "sm__cycles_elapsed.avg", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
-    "smsp__inst_executed.sum",
+    "smsp__inst_executed.sum", "smsp__cycles_active.avg", "sm__inst_executed_pipe_uniform.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
 ]
 
 
 def main(rep, out):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):
+        with open(rep) as f:
+            raw = "".join(l for l in f if not l.startswith("=="))
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = [hdr.index(m) for m in METRICS if m in hdr]
