@@ -283,16 +283,19 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const ConvTcA
 
 bool conv_tc2_applicable(const HkConvDesc& d);
 int conv_tc2_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
-                    const void* residual, void* y, cudaStream_t s);
+                    const void* residual, void* y, void* bn_acc, cudaStream_t s);
 bool conv_tc2h_applicable(const HkConvDesc& d);
 int conv_tc2h_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
-                     const void* residual, void* y, cudaStream_t s);
+                     const void* residual, void* y, void* bn_acc, cudaStream_t s);
 bool conv_tc_c64_applicable(const HkConvDesc& d);
 int conv_tc_c64_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
-                       const void* residual, void* y, cudaStream_t s);
+                       const void* residual, void* y, void* bn_acc, cudaStream_t s);
 
+// bn_acc != nullptr: the epilogue also adds per-channel sum y / sum y^2 of the stored outputs to the accumulators (train-mode BatchNorm
+// statistics; specialised kernels only -- *stats_done tells the caller whether it still has to run the stand-alone reduction)
 int conv_tc_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
-                   const void* residual, void* y, cudaStream_t s) {
+                   const void* residual, void* y, cudaStream_t s, void* bn_acc = nullptr, bool* stats_done = nullptr) {
+  if (stats_done) *stats_done = false;
   HK_REQUIRE(d.in_dtype == HK_BF16 && d.out_dtype == HK_BF16 && !d.in_is_nchw, "conv(tcgen05): needs NHWC bf16 in and out");
   HK_REQUIRE(d.in_c % TC_BLOCK_K == 0, "conv(tcgen05): in_c=%d must be a multiple of 64", d.in_c);
   HK_REQUIRE(d.out_c % 64 == 0, "conv(tcgen05): out_c=%d must be a multiple of 64", d.out_c);
@@ -305,11 +308,12 @@ int conv_tc_launch(const HkConvDesc& d, const void* x, const void* w, const floa
 
   // layer1 shape (3x3, 64 -> 64, stride 1): resident weights + haloed boxes, 3.6x less L2->SM traffic
   const bool specialised = d.algo != HK_CONV_TCGEN05_1CTA;
-  if (specialised && conv_tc_c64_applicable(d)) return conv_tc_c64_launch(d, x, w, scale, bias, residual, y, s);
+  if (stats_done) *stats_done = bn_acc && specialised && (conv_tc_c64_applicable(d) || conv_tc2_applicable(d));
+  if (specialised && conv_tc_c64_applicable(d)) return conv_tc_c64_launch(d, x, w, scale, bias, residual, y, bn_acc, s);
   // operand-traffic-bound 3x3 shapes: CTA-pair kernel with one haloed activation box per horizontal tap
-  if (specialised && conv_tc2_applicable(d) && conv_tc2h_applicable(d)) return conv_tc2h_launch(d, x, w, scale, bias, residual, y, s);
+  if (specialised && conv_tc2_applicable(d) && conv_tc2h_applicable(d)) return conv_tc2h_launch(d, x, w, scale, bias, residual, y, bn_acc, s);
   // Cout >= 128: CTA-pair kernel (cta_group::2, M=256), half the weight tile per SM
-  if (specialised && conv_tc2_applicable(d)) return conv_tc2_launch(d, x, w, scale, bias, residual, y, s);
+  if (specialised && conv_tc2_applicable(d)) return conv_tc2_launch(d, x, w, scale, bias, residual, y, bn_acc, s);
 
   const int block_n = d.out_c % 256 == 0 ? 256 : (d.out_c % 128 == 0 ? 128 : 64);
   const int ktot = d.kh * d.kw * d.in_c;
@@ -377,4 +381,27 @@ extern "C" int hk_conv_bn_act_fwd(const HkConvDesc* desc, const void* x, const v
   if (d.algo == HK_CONV_TCGEN05 || d.algo == HK_CONV_TCGEN05_1CTA) return conv_tc_launch(d, x, w_packed, scale, bias, residual_or_null, y, as_stream(stream));
   if (d.algo == HK_CONV_FFMA) return conv_ffma_launch(d, x, w_packed, scale, bias, residual_or_null, y, as_stream(stream));
   return fail(HK_ERR_BAD_ARG, "hk_conv_bn_act_fwd: unknown algo %d", d.algo);
+}
+
+// Train-mode forward of one conv + the statistics pass of its BatchNorm: y = conv(x) (raw: the caller passes scale = 1, bias = 0) and
+// acc += per-channel (sum y, sum y^2) of the bf16 values stored, gathered in the conv epilogue (hk_bn_acc.cuh) -- the activation is not
+// read again for its statistics.  Shapes outside the specialised tcgen05 kernels run the conv and then hk_bn_stats_acc (two launches).
+extern "C" int hk_bn_stats_acc(const void* y, long long P, int C, void* acc, void* stream);
+extern "C" int hk_conv_bn_stats_fwd(const HkConvDesc* desc, const void* x, const void* w_packed, const float* scale, const float* bias,
+                                    void* y, void* acc, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(desc && x && w_packed && scale && bias && y && acc, "hk_conv_bn_stats_fwd: null pointer");
+  const HkConvDesc& d = *desc;
+  HK_REQUIRE(d.algo == HK_CONV_TCGEN05 && d.in_dtype == HK_BF16 && d.out_dtype == HK_BF16 && !d.in_is_nchw && !d.relu,
+             "hk_conv_bn_stats_fwd: tcgen05 path only (NHWC bf16 in and out, no ReLU: BatchNorm sees the raw conv output)");
+  HK_REQUIRE(d.batch > 0 && d.in_h > 0 && d.in_w > 0 && d.in_c > 0 && d.out_c > 0 && d.kh > 0 && d.kw > 0 && d.stride > 0 && d.dil > 0 && d.pad >= 0,
+             "hk_conv_bn_stats_fwd: bad descriptor");
+  const int eh = d.dil * (d.kh - 1) + 1, ew = d.dil * (d.kw - 1) + 1;
+  HK_REQUIRE(d.out_h == (d.in_h + 2 * d.pad - eh) / d.stride + 1 && d.out_w == (d.in_w + 2 * d.pad - ew) / d.stride + 1,
+             "hk_conv_bn_stats_fwd: out_h/out_w (%d,%d) inconsistent with the descriptor", d.out_h, d.out_w);
+  HK_REQUIRE((reinterpret_cast<uintptr_t>(acc) & 31) == 0, "hk_conv_bn_stats_fwd: accumulators must be 32-byte aligned");
+  bool done = false;
+  int rc = conv_tc_launch(d, x, w_packed, scale, bias, nullptr, y, as_stream(stream), acc, &done);
+  if (rc || done) return rc;
+  return hk_bn_stats_acc(y, (long long)d.batch * d.out_h * d.out_w, d.out_c, acc, stream);
 }

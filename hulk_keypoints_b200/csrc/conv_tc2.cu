@@ -32,6 +32,7 @@
 #include <stdlib.h>
 
 #include "hk_common.cuh"
+#include "hk_bn_acc.cuh"
 #include "hk_ptx.cuh"
 #include "hk_ptx2.cuh"
 
@@ -55,6 +56,7 @@ struct ConvTc2Args {
   const float* scale2;   // DS kernels only: folded BN of the 1x1 downsample conv, ReLU flag of its epilogue (0 in the reference)
   const float* bias2;
   int relu2, early_release, s_major;
+  BnAcc* bn_acc;         // STATS kernels only: [2][Cout] accumulators of sum y / sum y^2 over the stored bf16 outputs (train-mode BatchNorm)
 #ifdef HK_DIAG  // diagnostics build only (python -m hulk_keypoints_b200.build --diag -> libhulk_sm100_diag.so); never in the shipped library
   int dbg_mode;    // HK_TC2_DEBUG bit flags: 1 = skip the MMAs, 2 = skip the TMA operand loads, 4 = skip the epilogue body (results are garbage)
   long long* dbg;  // optional timeline of cluster 0's leader CTA (tools/diag_tc2_timeline.py)
@@ -96,7 +98,7 @@ __device__ __forceinline__ void t2_decode_box(const ConvTc2Args& a, int box, int
   }
 }
 
-template <int BLOCK_N, bool DS>
+template <int BLOCK_N, bool DS, bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res,
@@ -276,6 +278,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const bool elected = (warp == 4 && lane == 0);
     const int sw = row & 7;
     constexpr int CHUNKS = BLOCK_N / 64;
+    const int et = (int)threadIdx.x - 128;   // epilogue thread 0..255
+    EpiStats stats;
+    if (STATS) epi_stats_init(stats, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256), a.Cout, et);
     ptx::griddep_wait();  // before the first residual load / output store
     uint32_t it = 0, chunk_ctr = 0;      // chunk_ctr selects the staging buffer and the res_bar phase
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
@@ -284,6 +289,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       t2_decode_box(a, 4 * m_tile + 2 * (int)rank, b0, y0, x0);
       t2_decode_box(a, 4 * m_tile + 2 * (int)rank + 1, b1, y1, x1);
       const int n0 = n_tile * BLOCK_N;
+      int nvalid = 0;   // STATS: how many of this thread's 16 staged rows (one image row of one box) lie inside the image
+      if (STATS) {
+        const int rg = et >> 5, second = rg >> 2;
+        const int bb = second ? b1 : b0, yy = (second ? y1 : y0) + (rg & 3), xx = second ? x1 : x0;
+        if (bb < a.B && yy < a.Ho) nvalid = min(16, max(0, a.Wo - xx));
+      }
 #pragma unroll
       for (int sub = 0; sub < NSUB; ++sub, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -377,6 +388,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (has_res && chunk + 1 < CHUNKS) issue_residual(chunk + 1, chunk_ctr + 1);  // one chunk ahead
         }
         ptx::named_bar_sync(1, T2_EPI_THREADS);  // staging[bsel] is free for everybody (elected passed its wait_group)
+        if (STATS) epi_stats_reduce_prev(stats, et);
         if (elected && chunk == 0) T2_STAMP(2, it, 2);
         uint32_t r0[32];
         ptx::tmem_ld_32x32(taddr + chunk * 64 + half * 32, r0);
@@ -427,9 +439,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           ptx::tma_store_4d(myp, buf + 8192, n0 + chunk * 64, x1, y1, b1);
           ptx::bulk_commit_group();
         }
+        if (STATS) epi_stats_chunk(stats, staging + bsel * 16384, et, nvalid, n0 + chunk * 64);
       }
       }
     }
+    if (STATS) epi_stats_flush(stats, et, a.Cout, a.bn_acc, [] { ptx::named_bar_sync(1, T2_EPI_THREADS); });
     if (elected) ptx::bulk_wait_group0();
   }
 
@@ -458,22 +472,24 @@ bool conv_tc2_applicable(const HkConvDesc& d) {
   return !disabled && d.out_c % 128 == 0 && d.in_c % 64 == 0 && (d.stride == 1 || d.stride == 2);
 }
 
-template <int BLOCK_N, bool DS>
+template <int BLOCK_N, bool DS, bool STATS>
 static int launch_tc2(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& mres,
                       const CUtensorMap& mw2, const CUtensorMap& my2, const ConvTc2Args& a, cudaStream_t s) {
   using Cfg = Tc2Cfg<BLOCK_N>;
-  static int attr_dev_mask = 0;
+  const int smem_bytes = Cfg::SMEM_BYTES + (STATS ? epi_stats_smem_bytes(a.Cout) : 0);
+  if (smem_bytes > 227 * 1024) return fail(HK_ERR_BAD_ARG, "conv(tcgen05,2cta): %d bytes of shared memory needed", smem_bytes);
+  static int attr_smem[16] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!(attr_dev_mask & (1 << dev))) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): smem attribute (%d B): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-    attr_dev_mask |= (1 << dev);
+  if (dev < 16 && attr_smem[dev] < smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, DS, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): smem attribute (%d B): %s", smem_bytes, cudaGetErrorString(e));
+    attr_smem[dev] = smem_bytes;
   }
   const int total = a.num_m_tiles * a.num_n_tiles;
   int clusters = sm_count() / 2;
   if (clusters > total) clusters = total;
-  cudaError_t le = launch_pdl(conv_tc2_kernel<BLOCK_N, DS>, dim3(2 * clusters), dim3(T2_THREADS), (size_t)Cfg::SMEM_BYTES, s, mx, mw, my, mres,
+  cudaError_t le = launch_pdl(conv_tc2_kernel<BLOCK_N, DS, STATS>, dim3(2 * clusters), dim3(T2_THREADS), (size_t)smem_bytes, s, mx, mw, my, mres,
                               mw2, my2, a);
   if (le != cudaSuccess) return fail(HK_ERR_CUDA, "conv_tc2_kernel: %s", cudaGetErrorString(le));
   return check_launch("conv_tc2_kernel");
@@ -489,7 +505,7 @@ struct ConvTc2Ds {
 };
 
 static int conv_tc2_launch_impl(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
-                                const void* residual, void* y, const ConvTc2Ds* ds, cudaStream_t s) {
+                                const void* residual, void* y, const ConvTc2Ds* ds, void* bn_acc, cudaStream_t s) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled entry point not available");
   const long long boxes_all = (long long)ceil_div(d.out_w, T2_BOX_W) * ceil_div(d.out_h, T2_BOX_H) * d.batch;
@@ -568,13 +584,15 @@ static int conv_tc2_launch_impl(const HkConvDesc& d, const void* x, const void* 
   a.dbg = g_tc2_dbg;
   { const char* m = getenv("HK_TC2_DEBUG"); a.dbg_mode = m ? atoi(m) : 0; }
 #endif
-  if (ds) return block_n == 256 ? launch_tc2<256, true>(mx, mw, my, mres, mw2, my2, a, s) : launch_tc2<128, true>(mx, mw, my, mres, mw2, my2, a, s);
-  return block_n == 256 ? launch_tc2<256, false>(mx, mw, my, mres, mw2, my2, a, s) : launch_tc2<128, false>(mx, mw, my, mres, mw2, my2, a, s);
+  a.bn_acc = static_cast<BnAcc*>(bn_acc);
+  if (ds) return block_n == 256 ? launch_tc2<256, true, false>(mx, mw, my, mres, mw2, my2, a, s) : launch_tc2<128, true, false>(mx, mw, my, mres, mw2, my2, a, s);
+  if (bn_acc) return block_n == 256 ? launch_tc2<256, false, true>(mx, mw, my, mres, mw2, my2, a, s) : launch_tc2<128, false, true>(mx, mw, my, mres, mw2, my2, a, s);
+  return block_n == 256 ? launch_tc2<256, false, false>(mx, mw, my, mres, mw2, my2, a, s) : launch_tc2<128, false, false>(mx, mw, my, mres, mw2, my2, a, s);
 }
 
 int conv_tc2_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
-                    const void* residual, void* y, cudaStream_t s) {
-  return conv_tc2_launch_impl(d, x, w, scale, bias, residual, y, nullptr, s);
+                    const void* residual, void* y, void* bn_acc, cudaStream_t s) {
+  return conv_tc2_launch_impl(d, x, w, scale, bias, residual, y, nullptr, bn_acc, s);
 }
 
 }  // namespace hk
@@ -597,5 +615,5 @@ extern "C" int hk_conv_ds_fwd(const HkConvDesc* desc, const void* x, const void*
              "hk_conv_ds_fwd: buffers must be 16-byte aligned");
   HK_REQUIRE(y != y_ds && x != y && x != y_ds, "hk_conv_ds_fwd: buffers must not alias");
   ConvTc2Ds ds{w_ds_packed, scale_ds, bias_ds, y_ds, 0};
-  return conv_tc2_launch_impl(d, x, w_packed, scale, bias, nullptr, y, &ds, as_stream(stream));
+  return conv_tc2_launch_impl(d, x, w_packed, scale, bias, nullptr, y, &ds, nullptr, as_stream(stream));
 }

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include "hk_common.cuh"
+#include "hk_bn_acc.cuh"
 #include "hk_ptx.cuh"
 #include "hk_ptx2.cuh"
 
@@ -40,6 +41,7 @@ struct ConvTc2hArgs {
   int strip_first, num_strips, strips_per_img, strip_y0;  // 4x32 strips: index range [strip_first, strip_first + num_strips)
   int num_m_tiles, num_n_tiles, cblocks;  // m tile = 2 patches (one per CTA)
   int a_slot_bytes, a_bytes_full, a_bytes_strip, a_slots, b_slots;
+  BnAcc* bn_acc;   // STATS kernels only: [2][Cout] accumulators of sum y / sum y^2 over the stored bf16 outputs (train-mode BatchNorm)
 };
 
 __device__ __forceinline__ void th_decode_patch(const ConvTc2hArgs& a, int patch, int& b, int& y0, int& x0) {
@@ -61,7 +63,7 @@ __device__ __forceinline__ void th_decode_patch(const ConvTc2hArgs& a, int patch
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TH_THREADS, 1)
 conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res,
@@ -212,6 +214,9 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int sw = row & 7;
     constexpr int CHUNKS = BLOCK_N / 64;
     const bool has_res = a.residual != nullptr;
+    const int et = (int)threadIdx.x - 128;   // epilogue thread 0..255
+    EpiStats stats;
+    if (STATS) epi_stats_init(stats, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + 512), a.Cout, et);
     ptx::griddep_wait();  // before the first residual load / output store
     uint32_t it = 0, chunk_ctr = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
@@ -225,6 +230,12 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const int n0 = n_tile * BLOCK_N;
       const float* scale = a.scale + n0;
       const float* bias = a.bias + n0;
+      int nvalid = 0;   // STATS: how many of this thread's 16 staged rows (16 pixels of one image row) lie inside the image
+      if (STATS) {
+        const int rg = et >> 5;
+        const int yy = y0 + (strip ? rg >> 1 : rg), xx = x0 + (strip ? (rg & 1) * 16 : 0);
+        if (b < a.B && yy < a.Ho) nvalid = min(16, max(0, a.Wo - xx));
+      }
       auto issue_residual = [&](int chunk, uint32_t ctr) {
         const uint32_t bsel = ctr % 3;
         ptx::mbar_arrive_expect_tx(&res_bar[bsel], 16384);
@@ -246,6 +257,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           if (has_res && chunk + 1 < CHUNKS) issue_residual(chunk + 1, chunk_ctr + 1);
         }
         ptx::named_bar_sync(1, TH_EPI_THREADS);
+        if (STATS) epi_stats_reduce_prev(stats, et);
         uint32_t r0[32];
         ptx::tmem_ld_32x32(taddr + chunk * 64 + half * 32, r0);
         ptx::tmem_ld_wait();
@@ -288,8 +300,10 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           ptx::tma_store_4d(myp, staging + bsel * 16384, n0 + chunk * 64, x0, y0, b);  // clipped outside the image / batch
           ptx::bulk_commit_group();
         }
+        if (STATS) epi_stats_chunk(stats, staging + bsel * 16384, et, nvalid, n0 + chunk * 64);
       }
     }
+    if (STATS) epi_stats_flush(stats, et, a.Cout, a.bn_acc, [] { ptx::named_bar_sync(1, TH_EPI_THREADS); });
     if (elected) ptx::bulk_wait_group0();
   }
 
@@ -319,11 +333,12 @@ bool conv_tc2h_applicable(const HkConvDesc& d) {
   return d.dil <= 2;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool STATS>
 static int launch_tc2h(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& mres,
                        const CUtensorMap& mxs, const CUtensorMap& mys, const CUtensorMap& mress, ConvTc2hArgs& a, cudaStream_t s) {
   constexpr int B_BYTES = (BLOCK_N / 2) * 128;
-  const int budget = 227 * 1024 - 1024 - TH_STAGING_BYTES - 512;
+  const int stats_bytes = STATS ? epi_stats_smem_bytes(a.Cout) : 0;
+  const int budget = 227 * 1024 - 1024 - TH_STAGING_BYTES - 512 - stats_bytes;
   int na = 3, nb = (budget - na * a.a_slot_bytes) / B_BYTES;
   if (nb > TH_MAX_B) {  // room to spare: one more haloed box in flight
     nb = TH_MAX_B;
@@ -332,26 +347,26 @@ static int launch_tc2h(const CUtensorMap& mx, const CUtensorMap& mw, const CUten
   if (nb < 3) return fail(HK_ERR_BAD_ARG, "conv(tcgen05,halo): shared memory budget too small");
   a.a_slots = na;
   a.b_slots = nb;
-  const int smem = 1024 + na * a.a_slot_bytes + nb * B_BYTES + TH_STAGING_BYTES + 512;
+  const int smem = 1024 + na * a.a_slot_bytes + nb * B_BYTES + TH_STAGING_BYTES + 512 + stats_bytes;
   static int attr_smem[16] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && attr_smem[dev] < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2h_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2h_kernel<BLOCK_N, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail(HK_ERR_CUDA, "conv(tcgen05,halo): smem attribute (%d B): %s", smem, cudaGetErrorString(e));
     attr_smem[dev] = smem;
   }
   const int total = a.num_m_tiles * a.num_n_tiles;
   int clusters = sm_count() / 2;
   if (clusters > total) clusters = total;
-  cudaError_t le = launch_pdl(conv_tc2h_kernel<BLOCK_N>, dim3(2 * clusters), dim3(TH_THREADS), (size_t)smem, s, mx, mw, my, mres, mxs, mys,
+  cudaError_t le = launch_pdl(conv_tc2h_kernel<BLOCK_N, STATS>, dim3(2 * clusters), dim3(TH_THREADS), (size_t)smem, s, mx, mw, my, mres, mxs, mys,
                               mress, a);
   if (le != cudaSuccess) return fail(HK_ERR_CUDA, "conv_tc2h_kernel: %s", cudaGetErrorString(le));
   return check_launch("conv_tc2h_kernel");
 }
 
 int conv_tc2h_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias, const void* residual,
-                     void* y, cudaStream_t s) {
+                     void* y, void* bn_acc, cudaStream_t s) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return fail(HK_ERR_CUDA, "conv(tcgen05,halo): cuTensorMapEncodeTiled entry point not available");
   // patch geometry: 8x16 patches over the rows that fill whole patch rows, 4x32 strips over a remainder of 1..4 rows (see the header)
@@ -451,7 +466,9 @@ int conv_tc2h_launch(const HkConvDesc& d, const void* x, const void* w, const fl
   a.a_bytes_full = box_rows * TH_ROW_BYTES;
   a.a_bytes_strip = strip_box_rows * 2 * TH_ROW_BYTES;
   a.a_slot_bytes = use_strips && a.a_bytes_strip > a.a_bytes_full ? a.a_bytes_strip : a.a_bytes_full;
-  return block_n == 256 ? launch_tc2h<256>(mx, mw, my, mres, mxs, mys, mress, a, s) : launch_tc2h<128>(mx, mw, my, mres, mxs, mys, mress, a, s);
+  a.bn_acc = static_cast<BnAcc*>(bn_acc);
+  if (bn_acc) return block_n == 256 ? launch_tc2h<256, true>(mx, mw, my, mres, mxs, mys, mress, a, s) : launch_tc2h<128, true>(mx, mw, my, mres, mxs, mys, mress, a, s);
+  return block_n == 256 ? launch_tc2h<256, false>(mx, mw, my, mres, mxs, mys, mress, a, s) : launch_tc2h<128, false>(mx, mw, my, mres, mxs, mys, mress, a, s);
 }
 
 }  // namespace hk

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "hk_common.cuh"
+#include "hk_bn_acc.cuh"
 #include "hk_ptx.cuh"
 
 namespace hk {
@@ -40,6 +41,7 @@ struct ConvC64Args {
   int box_rows, patch_bytes;  // 8 + 2*dil rows; box_rows * 2048
   int has_residual;
   int slots;  // number of patch slots in the ring
+  BnAcc* bn_acc;  // STATS kernel only: [2][64] accumulators of sum y / sum y^2 over the stored bf16 outputs (train-mode BatchNorm)
 #ifdef HK_DIAG
   long long* dbg;  // optional timeline of CTA 0 (tools/diag_c64_timeline.py); diagnostics build only
 #endif
@@ -52,6 +54,7 @@ struct ConvC64Args {
 #endif
 constexpr int C64_STAGING_BYTES = 128 * 128;  // one output tile: 128 pixels x 64 ch bf16 (two of them: tiles alternate)
 
+template <bool STATS>
 __global__ void __launch_bounds__(C64_THREADS, 1)
 conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                    const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res, const ConvC64Args a) {
@@ -182,6 +185,9 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     ptx::griddep_wait();  // before the first residual load / output store
     const bool leader = (warp == 4 && lane == 0);
     const int sw = row & 7;
+    const int et = (int)threadIdx.x - 128;   // epilogue thread 0..255
+    EpiStats stats;
+    if (STATS) epi_stats_init(stats, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 1024), C64_C, et);
     uint32_t it = 0;
     auto tile_origin = [&](int tile, int& b, int& y0, int& x0) {
       b = tile / a.tiles_per_img;
@@ -215,6 +221,7 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
       }
       ptx::named_bar_sync(1, C64_EPI_THREADS);  // this tile's staging buffer is free of stores (the next tile's residual is in flight)
+      if (STATS) epi_stats_reduce_prev(stats, et);
       if (leader) C64_STAMP(2, (int)it, 1);
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 25);
       ptx::tc_fence_after();
@@ -264,7 +271,14 @@ conv_tc_c64_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         ptx::tma_store_4d(&map_y, stage_buf, 0, x0, y0, b);  // rows / columns beyond the image are clipped
         ptx::bulk_commit_group();
       }
+      if (STATS) {   // this thread's 16 staged rows = 16 pixels of image row y0 + (et >> 5)
+        int b, y0, x0;
+        tile_origin(tile, b, y0, x0);
+        const int nvalid = (y0 + (et >> 5) < a.H) ? min(16, max(0, a.W - x0)) : 0;
+        epi_stats_chunk(stats, stage_buf, et, nvalid, 0);
+      }
     }
+    if (STATS) epi_stats_flush(stats, et, C64_C, a.bn_acc, [] { ptx::named_bar_sync(1, C64_EPI_THREADS); });
     if (leader) ptx::bulk_wait_group0();
   }
 
@@ -296,7 +310,7 @@ bool conv_tc_c64_applicable(const HkConvDesc& d) {
 }
 
 int conv_tc_c64_launch(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
-                       const void* residual, void* y, cudaStream_t s) {
+                       const void* residual, void* y, void* bn_acc, cudaStream_t s) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return fail(HK_ERR_CUDA, "conv(tcgen05,c64): cuTensorMapEncodeTiled entry point not available");
   const int box_rows = C64_TILE_H + 2 * d.dil;
@@ -354,22 +368,27 @@ int conv_tc_c64_launch(const HkConvDesc& d, const void* x, const void* w, const 
   a.num_tiles = (int)nt;
   a.box_rows = box_rows;
   a.patch_bytes = box_rows * C64_ROW_BYTES;
-  const int fixed = 1024 + C64_W_BYTES + 2 * C64_STAGING_BYTES + 1024;  // alignment slack, weights, staging, barriers + scale/bias
+  a.bn_acc = static_cast<BnAcc*>(bn_acc);
+  // alignment slack, weights, staging, barriers + scale/bias (1 KB), the epilogue's statistics scratch (STATS kernel)
+  const int fixed = 1024 + C64_W_BYTES + 2 * C64_STAGING_BYTES + 1024 + (bn_acc ? epi_stats_smem_bytes(C64_C) : 0);
   int slots = (227 * 1024 - fixed) / a.patch_bytes;
   if (slots > C64_MAX_SLOTS) slots = C64_MAX_SLOTS;
   a.slots = slots;
   const int smem = fixed + slots * a.patch_bytes;
-  static int attr_smem[16] = {0};
+  static int attr_smem[2][16] = {{0}, {0}};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 16 && attr_smem[dev] < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int which = bn_acc ? 1 : 0;
+  if (dev < 16 && attr_smem[which][dev] < smem) {
+    cudaError_t e = bn_acc ? cudaFuncSetAttribute(conv_tc_c64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                           : cudaFuncSetAttribute(conv_tc_c64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail(HK_ERR_CUDA, "conv(tcgen05,c64): smem attribute (%d B): %s", smem, cudaGetErrorString(e));
-    attr_smem[dev] = smem;
+    attr_smem[which][dev] = smem;
   }
   int grid = sm_count();
   if (grid > a.num_tiles) grid = a.num_tiles;
-  cudaError_t le = launch_pdl(conv_tc_c64_kernel, dim3(grid), dim3(C64_THREADS), (size_t)smem, s, mx, mw, my, mres, a);
+  cudaError_t le = bn_acc ? launch_pdl(conv_tc_c64_kernel<true>, dim3(grid), dim3(C64_THREADS), (size_t)smem, s, mx, mw, my, mres, a)
+                          : launch_pdl(conv_tc_c64_kernel<false>, dim3(grid), dim3(C64_THREADS), (size_t)smem, s, mx, mw, my, mres, a);
   if (le != cudaSuccess) return fail(HK_ERR_CUDA, "conv_tc_c64_kernel: %s", cudaGetErrorString(le));
   return check_launch("conv_tc_c64_kernel");
 }

@@ -11,6 +11,7 @@
 #include <cooperative_groups.h>
 
 #include "hk_common.cuh"
+#include "hk_bn_acc.cuh"
 
 namespace hk {
 
@@ -283,48 +284,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const __nv_bfl
 // their own prologue (each block: C channels over 256 threads; block 0 also writes the saved statistics / running stats /
 // parameter gradients).  BatchNorm forward = 2 launches instead of 3, backward = 2 instead of 3 (72 launches per train step).
 // Accumulators must be zero when the reduce kernel starts (the engine clears all of them with one memset node per graph).
-struct alignas(32) BnAcc {
-  unsigned long long lo, hi;   // two's-complement 128-bit integer, unit 2^-50
-  unsigned long long poison;   // != 0: a partial sum was Inf/NaN or beyond the accumulator range -> the total reads as NaN
-  unsigned long long pad;
-};
-constexpr int BN_ACC_FRAC_BITS = 50;
 constexpr int BN_ACC_MAX_C = 2048;
-
-__device__ __forceinline__ void bn_acc_add(BnAcc* a, float p) {
-  const uint32_t bits = __float_as_uint(p);
-  const uint32_t ex = (bits >> 23) & 0xffu;
-  uint32_t man = bits & 0x7fffffu;
-  if (ex == 0xffu) { atomicOr(&a->poison, 1ull); return; }
-  if (ex == 0u && man == 0u) return;
-  const int e = ex ? (int)ex : 1;
-  if (ex) man |= 0x800000u;
-  const int shift = e - 150 + BN_ACC_FRAC_BITS;     // p = man * 2^(e-150)
-  unsigned __int128 v;
-  if (shift >= 0) {
-    if (shift > 100) { atomicOr(&a->poison, 2ull); return; }   // |p| >= 2^74: far outside anything a finite BatchNorm produces
-    v = static_cast<unsigned __int128>(man) << shift;
-  } else {
-    if (shift <= -24) return;                        // below the accumulator's resolution (2^-50)
-    v = man >> (-shift);
-  }
-  if (bits >> 31) v = static_cast<unsigned __int128>(0) - v;
-  const unsigned long long lo = static_cast<unsigned long long>(v), hi = static_cast<unsigned long long>(v >> 64);
-  const unsigned long long old = atomicAdd(&a->lo, lo);
-  const unsigned long long hi2 = hi + ((old + lo) < lo ? 1ull : 0ull);   // carry out of the low word: exact whatever the order
-  if (hi2) atomicAdd(&a->hi, hi2);
-}
-
-__device__ __forceinline__ double bn_acc_read(const BnAcc* a) {
-  const unsigned long long lo = a->lo, hi = a->hi;
-  if (a->poison) return __longlong_as_double(0x7ff8000000000000ll);
-  unsigned __int128 v = (static_cast<unsigned __int128>(hi) << 64) | lo;
-  const bool neg = (hi >> 63) != 0;
-  if (neg) v = static_cast<unsigned __int128>(0) - v;
-  const double d = (static_cast<double>(static_cast<unsigned long long>(v >> 64)) * 18446744073709551616.0 +
-                    static_cast<double>(static_cast<unsigned long long>(v))) * (1.0 / 1125899906842624.0);   // 2^-50
-  return neg ? -d : d;
-}
 
 // Reduce kernels run as clusters of 8 CTAs: every CTA leaves its 2*C block sums in shared memory, CTA 0 of the cluster adds the eight
 // of them over DSMEM in rank order (fixed order: deterministic) and issues the atomics -- 1/8 of the atomic traffic of a per-CTA scheme

@@ -354,6 +354,30 @@ def bn_train_bwd(dout: torch.Tensor, out_mask: Optional[torch.Tensor], y: torch.
     return dy
 
 
+def conv_bn_stats(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, acc: torch.Tensor, *,
+                  stride: int, pad: int, dil: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Raw conv (tcgen05) + the BatchNorm statistics of its output in one launch: acc (zeroed, bn_acc_bytes(cout)) += per-channel
+    (sum y, sum y^2) of the stored bf16 values, gathered in the conv epilogue.  x NHWC bf16; scale/bias are the caller's ones/zeros."""
+    _need_cuda(x, w_packed, scale, bias, acc, out)
+    B, H, W, Cin = x.shape
+    cout, kh, kw, cin_w = w_packed.shape
+    if cin_w != Cin:
+        raise ValueError(f"weight cin {cin_w} != input channels {Cin}")
+    Ho, Wo = conv_out_hw(H, W, kh, stride, pad, dil)
+    if out is None:
+        out = torch.empty((B, Ho, Wo, cout), device=x.device, dtype=torch.bfloat16)
+    elif tuple(out.shape) != (B, Ho, Wo, cout) or out.dtype != torch.bfloat16:
+        raise ValueError(f"out must be a bf16 {(B, Ho, Wo, cout)} tensor")
+    if not (x.is_contiguous() and w_packed.is_contiguous() and out.is_contiguous()) or x.dtype != torch.bfloat16:
+        raise ValueError("conv_bn_stats needs contiguous bf16 NHWC tensors")
+    if acc.numel() * acc.element_size() < bn_acc_bytes(cout):
+        raise ValueError("accumulator buffer too small")
+    d = HkConvDesc(B, H, W, Cin, Ho, Wo, cout, kh, kw, stride, pad, dil, 0, dtype_code(x.dtype), dtype_code(out.dtype), 0, HK_CONV_TCGEN05)
+    check(lib().hk_conv_bn_stats_fwd(C.byref(d), ptr(x), ptr(w_packed), ptr(scale), ptr(bias), ptr(out), ptr(acc), stream_ptr()),
+          "hk_conv_bn_stats_fwd")
+    return out
+
+
 def bn_acc_bytes(C_: int) -> int:
     """Bytes of the 2*C fixed-point accumulators of one BatchNorm reduction (hk_bn_stats_acc / hk_bn_bwd_acc); must be zeroed before use."""
     return int(lib().hk_bn_acc_bytes(C_))

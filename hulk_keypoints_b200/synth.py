@@ -97,7 +97,7 @@ def fit_synthetic(model, steps: int, B: int, H: int, W: int, lr: float = 1e-3, w
 # eval-mode heatmaps -- BatchNorm on running statistics -- swing from checkpoint to checkpoint: tools/diag_ftrn_quality.py).
 FIXTURES = {
     # BASELINE configs[1]/[3] shape: K=4 at config.py resolution
-    "k4_480x640": dict(K=4, B=4, H=480, W=640, steps=450, decay_after=0.6, lr=1e-3, weight_decay=1e-4, sigma=8.0, model_seed=0, data_seed=42),
+    "k4_480x640": dict(K=4, B=4, H=480, W=640, steps=400, decay_after=0.6, lr=1e-3, weight_decay=1e-4, sigma=8.0, model_seed=0, data_seed=42),
     # BASELINE configs[4] (960x1280, K up to 32): trained at 240x320 (the net is fully convolutional; discs keep their pixel size)
     "k32_240x320": dict(K=32, B=4, H=240, W=320, steps=1200, decay_after=0.6, lr=1e-3, weight_decay=1e-4, sigma=8.0, model_seed=0, data_seed=43),
     # smoke()-sized

@@ -97,6 +97,9 @@ class TrainEngine:
         # launches per step.  One flat buffer per direction, sliced per conv in self.convs order (stem, then the blocks in order), so the
         # early part of the two-phase backward (stem + blocks < split_block) is a prefix.  HK_BN_ACC=0: the three-launch path.
         self.use_bn_acc = os.environ.get("HK_BN_ACC", "1") != "0"
+        # ... and the forward statistics gathered in the conv epilogues (hk_conv_bn_stats_fwd): 36 launches and one read of every raw conv
+        # output fewer.  HK_CONV_STATS=0: stand-alone hk_bn_stats_acc.
+        self.fuse_conv_stats = os.environ.get("HK_CONV_STATS", "1") != "0"
         offs_acc, tot = [], 0
         for c in self.convs:
             offs_acc.append(tot)
@@ -193,8 +196,17 @@ class TrainEngine:
 
     def _conv_bn(self, c: _ConvT, x, out, relu: bool, residual=None, ws=None) -> int:
         """raw conv -> batch statistics (+ running stats) -> fused normalise (+ shortcut) (+ ReLU)."""
-        ops.conv_bn_act(x, c.w_fwd, c.one_out, c.zero_out, stride=c.stride, pad=c.pad, dil=c.dil, relu=False, out=c.y)
         bn = c.bn
+        if self.use_bn_acc and self.fuse_conv_stats and c.k == 3 and c.cout >= 256:
+            # the conv epilogue gathers sum y / sum y^2 of the tile it stores: no statistics pass over the activation.  Only where the
+            # epilogue hides under a long mainloop (3x3 convs of layers 3-4: 36 / 72 K blocks per tile); the 64/128-channel layers and
+            # the 1x1 downsample convs are epilogue-bound and lose more than the stand-alone reduction costs (measured per launch)
+            ops.conv_bn_stats(x, c.w_fwd, c.one_out, c.zero_out, c.acc_f, stride=c.stride, pad=c.pad, dil=c.dil, out=c.y)
+            ops.bn_apply_acc(c.y, c.acc_f, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.momentum, bn.eps, c.mean, c.invstd,
+                             relu=relu, residual=residual, out=out, relu_bits=c.relu_bits if relu and self.use_relu_bits else None)
+            c.relu_out = out if relu else None
+            return 2
+        ops.conv_bn_act(x, c.w_fwd, c.one_out, c.zero_out, stride=c.stride, pad=c.pad, dil=c.dil, relu=False, out=c.y)
         if self.use_bn_acc:
             ops.bn_stats_acc(c.y, c.acc_f)
             ops.bn_apply_acc(c.y, c.acc_f, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.momentum, bn.eps, c.mean, c.invstd,

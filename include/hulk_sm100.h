@@ -249,6 +249,14 @@ HK_API int hk_bn_bwd_acc(const void* dout, const void* out_mask_or_null, int mas
                          const float* invstd, const float* gamma, long long P, int C, void* acc, float* dgamma, float* dbeta,
                          int accumulate, void* dy, void* dmasked_or_null, void* stream);
 
+/* Train-mode forward of one conv + the statistics pass of its BatchNorm in ONE launch (src/resnet.py:56-57,60-61 under model.train()):
+ * y = conv(x) (raw output: pass scale = 1, bias = 0; desc->relu must be 0) and acc += per-channel (sum y, sum y^2) of the bf16 values
+ * stored, gathered in the epilogue of the tcgen05 kernel from the staged output tile -- the activation is not read again for its
+ * statistics.  acc as for hk_bn_stats_acc (zeroed, hk_bn_acc_bytes(out_c)); follow with hk_bn_apply_fwd_acc.  tcgen05 path only; a shape
+ * outside the specialised kernels runs the conv followed by hk_bn_stats_acc. */
+HK_API int hk_conv_bn_stats_fwd(const HkConvDesc* desc, const void* x, const void* w_packed, const float* scale, const float* bias,
+                                void* y, void* acc, void* stream);
+
 /* All convs of the network repacked in ONE launch (the training step repacks every step).  items_dev: device array of HkPackItem;
  * w_dgrad may be NULL (stem: no data gradient).  max_elems = max over items of cout*cin*khw. */
 typedef struct HkPackItem {

@@ -289,3 +289,55 @@ def test_head_logits_forward_and_backward_match_autograd(K):
     ops.head_bwd(g, feat, w_fc, dfeat, dw, db)
     assert rel_err(dw, w32.grad) < 1e-4 and rel_err(db, b32.grad) < 1e-4
     assert rel_err(nchw(dfeat.float()), f32.grad) < 5e-3         # bf16 rounding of dfeat
+
+
+# ------------------------------------------------------------------ conv + BatchNorm statistics in one launch (epilogue-gathered sums)
+CONV_STATS_CASES = [
+    # B, H, W, cin, cout, k, stride, dil     -> kernel
+    (2, 24, 32, 64, 64, 3, 1, 1),      # conv_tc_c64 (layer1)
+    (3, 21, 27, 64, 64, 3, 1, 1),      # conv_tc_c64, ragged tiles in both directions
+    (2, 30, 40, 64, 128, 3, 2, 1),     # conv_tc2<128> (layer2.0 conv1, stride 2)
+    (2, 30, 40, 64, 128, 1, 2, 1),     # conv_tc2<128> (1x1 downsample)
+    (2, 60, 80, 128, 128, 3, 1, 1),    # conv_tc2h<128> with strip patches (60 rows)
+    (1, 27, 21, 128, 256, 3, 1, 2),    # conv_tc2h, ragged
+    (2, 60, 80, 256, 256, 3, 1, 2),    # conv_tc2h<256>
+    (1, 60, 80, 256, 512, 3, 1, 4),    # conv_tc2<256>, two N tiles
+    (4, 60, 80, 512, 512, 3, 1, 4),    # conv_tc2, more tiles than CTA pairs
+    (1, 16, 16, 256, 512, 1, 1, 1),    # 1x1 downsample of layer4
+]
+
+
+@pytest.mark.parametrize("case", CONV_STATS_CASES)
+def test_conv_epilogue_statistics_match_standalone_reduction(case):
+    """hk_conv_bn_stats_fwd: the conv output is bit-identical to hk_conv_bn_act_fwd and the accumulated (sum y, sum y^2) equal what
+    hk_bn_stats_acc computes from that output -- read back through hk_bn_apply_fwd_acc as (mean, invstd) -- to fp32 rounding of the
+    partial sums (different partition of the pixels into partial sums); bit-reproducible run to run."""
+    B, H, W, cin, cout, k, stride, dil = case
+    g = torch.Generator().manual_seed(5 + cin + cout)
+    pad = dil * (k - 1) // 2
+    x = bf((torch.randn(B, H, W, cin, generator=g) + 0.3).to(DEV))
+    w = (torch.randn(cout, cin, k, k, generator=g) * (2.0 / (k * k * cin)) ** 0.5).to(DEV)
+    wp, _, _ = ops.pack_conv_weights(w, None, 1e-5, torch.bfloat16)
+    one, zero = torch.ones(cout, device=DEV), torch.zeros(cout, device=DEV)
+    y_ref = ops.conv_bn_act(x, wp, one, zero, stride=stride, pad=pad, dil=dil, relu=False)
+    acc_ref = torch.zeros(ops.bn_acc_bytes(cout), device=DEV, dtype=torch.uint8)
+    ops.bn_stats_acc(y_ref, acc_ref)
+
+    def fused():
+        acc = torch.zeros(ops.bn_acc_bytes(cout), device=DEV, dtype=torch.uint8)
+        y = ops.conv_bn_stats(x, wp, one, zero, acc, stride=stride, pad=pad, dil=dil)
+        torch.cuda.synchronize()
+        return y, acc
+
+    y1, acc1 = fused()
+    y2, acc2 = fused()
+    assert torch.equal(y1, y_ref) and torch.equal(y1, y2)
+    assert torch.equal(acc1, acc2)                                   # deterministic
+    stats = []
+    for acc in (acc_ref, acc1):
+        mean, invstd = torch.empty(cout, device=DEV), torch.empty(cout, device=DEV)
+        ops.bn_apply_acc(y_ref, acc, None, None, None, None, 0.1, 1e-5, mean, invstd, relu=False)
+        stats.append((mean.clone(), invstd.clone()))
+    y32 = y_ref.float().reshape(-1, cout)
+    assert torch.allclose(stats[1][0], y32.double().mean(0).float(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(stats[1][0], stats[0][0], rtol=2e-6, atol=1e-6) and torch.allclose(stats[1][1], stats[0][1], rtol=1e-5)
