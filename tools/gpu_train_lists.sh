@@ -6,5 +6,6 @@ for B in 4 32; do
   HK_TRAIN_NO_GRAPH=1 $CMD > gpurun_out/train_plain_b$B.log 2>&1 &&
   HK_TRAIN_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 4000 --csv --log-file gpurun_out/train_launches_b$B.csv $CMD > gpurun_out/ncu_train_b$B.log 2>&1
   echo "B=$B launch list rc=$?"
+  python tools/train_list_summary.py gpurun_out/train_launches_b$B.csv --last-step gpurun_out/train_step_b${B}_launches.csv 2>&1 | head -32
   timeout 300 python bench_train.py --steps 20 --warmup 3 --batch $B > gpurun_out/train_b$B.log 2>&1; tail -1 gpurun_out/train_b$B.log | cut -c1-200
 done
