@@ -534,7 +534,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": f"KeypointsGauss (ResnetDilated-34, OS8) eval forward + argmax decode, batch {B} per GPU, "
-                               f"{H}x{W}, K={K_KEYPOINTS}, random-init weights (BASELINE.json configs[1])",
+                               f"{H}x{W}, K={K_KEYPOINTS}, random-init weights (BASELINE.json {'configs[1]' if (B, H, W) == (64, 480, 640) else 'configs[4]' if (H, W) == (960, 1280) else 'configs[1] at another shape'})",
                    "batch_per_gpu": B, "height": H, "width": W, "precision": args.precision,
                    "l2": f"per-step activations {B * 4.9:.0f}+ MB exceed the 126 MB L2 (no explicit flush)",
                    "parallelism": f"batch-sharded x{world}, no collective", "cuda_graph": not args.no_graph},
