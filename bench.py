@@ -315,7 +315,9 @@ def per_launch_breakdown(engine, plan, decode=True):
         timed("maxpool", 0.0, lambda: ops.maxpool3x3s2(plan.stem, out=x))
         rows[-1]["bytes"] = B * 64.0 * 2 * (plan.h2 * plan.w2 + plan.h4 * plan.w4)
     h, w = plan.h4, plan.w4
-    for i, blk in enumerate(net.blocks()):
+    blocks = list(net.blocks())
+    nblocks, head_done = len(blocks), False
+    for i, blk in enumerate(blocks):
         c1, c2 = P[f"b{i}.c1"], P[f"b{i}.c2"]
         planes, cin = c1.w.shape[0], c1.w.shape[3]
         ho, wo = ops.conv_out_hw(h, w, 3, c1.stride, c1.pad, c1.dil)
@@ -340,14 +342,26 @@ def per_launch_breakdown(engine, plan, decode=True):
             timed(f"b{i}.c1", 2.0 * B * ho * wo * planes * cin * 9, lambda: engine._conv(c1, xin, t, relu=True))
             rows[-1]["algo"] = c1.algo
             sc = x
+        if (i == nblocks - 1 and engine.fuse_head and c2.algo == 0 and ops.conv_head_supported(t, c2.w, engine._fc_w, c2.stride)
+                and (ho, wo) == (plan.h8, plan.w8)):
+            # last conv + the K scoring rows in one launch (engine._enqueue); the feature map is never written
+            timed(f"b{i}.c2+fc", 2.0 * B * ho * wo * planes * (planes * 9 + engine.K),
+                  lambda: ops.conv_head(t, c2.w, c2.scale, c2.bias, engine._fc_w, engine._fc_b, plan.logits, stride=c2.stride, pad=c2.pad,
+                                        dil=c2.dil, relu=True, residual=sc))
+            rows[-1]["algo"] = c2.algo
+            timed("upsample", 0.0, lambda: ops.head_upsample(plan.logits, plan.H, plan.W, heat=plan.heat, fast=True))
+            rows[-1]["bytes"] = B * engine.K * (plan.H * plan.W + ho * wo) * 4.0      # fp32 logits read + fp32 heatmaps written
+            head_done = True
+            break
         y = plan.view(free[2], ho, wo, planes)
         timed(f"b{i}.c2", 2.0 * B * ho * wo * planes * planes * 9, lambda: engine._conv(c2, t, y, relu=True, residual=sc))
         rows[-1]["algo"] = c2.algo
         x, cur, h, w = y, free[2], ho, wo
     xf = x
-    timed("head", 2.0 * B * h * w * engine.K * 512,
-          lambda: ops.head(xf, engine._fc_w, engine._fc_b, plan.H, plan.W, heat=plan.heat, logits_ws=plan.logits))
-    rows[-1]["bytes"] = B * (512.0 * h * w * 2 + engine.K * plan.H * plan.W * 4.0)   # bf16 features read + fp32 heatmaps written
+    if not head_done:
+        timed("head", 2.0 * B * h * w * engine.K * 512,
+              lambda: ops.head(xf, engine._fc_w, engine._fc_b, plan.H, plan.W, heat=plan.heat, logits_ws=plan.logits))
+        rows[-1]["bytes"] = B * (512.0 * h * w * 2 + engine.K * plan.H * plan.W * 4.0)   # bf16 features read + fp32 heatmaps written
     if decode:
         timed("decode", 0.0, lambda: ops.argmax_decode(plan.heat, yx=plan.yx, maxval=plan.maxval, ws=plan.argmax_ws, want_max=True))
         rows[-1]["bytes"] = B * engine.K * plan.H * plan.W * 4.0

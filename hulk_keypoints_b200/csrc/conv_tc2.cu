@@ -28,6 +28,13 @@
 // protocol is unchanged (sub-tiles simply take consecutive accumulator turns); sub 1's epilogue hides under the next item's conv1
 // mainloop.  Sub 0's epilogue would otherwise hold its accumulator through the short sub-1 mainloop and stall the next conv1, so in
 // DS mode it drains all of its TMEM columns into packed bf16 registers first, releases the accumulator, and only then stages/stores.
+//
+// HEAD = true (the network's LAST conv, reference src/resnet.py:60-67 of layer4[2] + the 1x1 scoring conv `fc` at :215 restricted to the K
+// live rows of src/model.py:21): the feature map is consumed by nothing but that 1x1 conv, so the epilogue multiplies its finished rows
+// (conv + BN + shortcut + ReLU, rounded to bf16 exactly as they would have been stored) with the K x Cout scoring weights and adds the
+// K partial logits of each pixel to the (B,K,Ho,Wo) fp32 logits -- the (B,Ho,Wo,512) feature map is never written, and the stand-alone
+// head_logits_kernel (one full read of it) disappears.  Each pixel receives exactly two contributions (the two 256-column N tiles) on a
+// zero-initialised buffer, and fp32 addition is commutative, so the result does not depend on their order.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -56,6 +63,10 @@ struct ConvTc2Args {
   const float* scale2;   // DS kernels only: folded BN of the 1x1 downsample conv, ReLU flag of its epilogue (0 in the reference)
   const float* bias2;
   int relu2, early_release, s_major;
+  const float* head_w;   // HEAD kernels only: (head_k, Cout) fp32 scoring weights, (head_k) bias, (B, head_k, Ho, Wo) fp32 logits (zero on entry)
+  const float* head_b;
+  float* head_logits;
+  int head_k;
   BnAcc* bn_acc;         // STATS kernels only: [2][Cout] accumulators of sum y / sum y^2 over the stored bf16 outputs (train-mode BatchNorm)
 #ifdef HK_DIAG  // diagnostics build only (python -m hulk_keypoints_b200.build --diag -> libhulk_sm100_diag.so); never in the shipped library
   int dbg_mode;    // HK_TC2_DEBUG bit flags: 1 = skip the MMAs, 2 = skip the TMA operand loads, 4 = skip the epilogue body (results are garbage)
@@ -98,7 +109,10 @@ __device__ __forceinline__ void t2_decode_box(const ConvTc2Args& a, int box, int
   }
 }
 
-template <int BLOCK_N, bool DS, bool STATS>
+constexpr int T2_HEAD_MAX_K = 8;
+constexpr int T2_HEAD_SMEM_BYTES = T2_HEAD_MAX_K * 256 * 4 + 128 * T2_HEAD_MAX_K * 4;   // weight slice of one N tile + the half-row exchange
+
+template <int BLOCK_N, bool DS, bool STATS, bool HEAD = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res,
@@ -281,6 +295,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const int et = (int)threadIdx.x - 128;   // epilogue thread 0..255
     EpiStats stats;
     if (STATS) epi_stats_init(stats, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256), a.Cout, et);
+    int head_loaded = -1;   // HEAD: N tile whose scoring-weight slice is in shared memory
     ptx::griddep_wait();  // before the first residual load / output store
     uint32_t it = 0, chunk_ctr = 0;      // chunk_ctr selects the staging buffer and the res_bar phase
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
@@ -379,6 +394,92 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
         continue;
       }
+      if (HEAD) {
+        // ---- last conv of the network: rows go straight into the K scoring dot products, nothing is stored ----
+        float* hw = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [head_k][256]: scoring weights of this N tile
+        float* hx = hw + T2_HEAD_MAX_K * 256;                                                  // [128 rows][head_k]: upper-half partial sums
+        const int K = a.head_k;
+        if (n_tile != head_loaded) {   // cluster-uniform (in practice once: the cluster stride is even, so a cluster keeps its N tile)
+          ptx::named_bar_sync(1, T2_EPI_THREADS);   // nobody still reads the previous slice
+          for (int i = et; i < K * 256; i += T2_EPI_THREADS) hw[i] = __ldg(a.head_w + (size_t)(i >> 8) * a.Cout + n0 + (i & 255));
+          head_loaded = n_tile;                      // visible to everybody after the first chunk's barrier
+        }
+        float p[T2_HEAD_MAX_K];
+#pragma unroll
+        for (int k = 0; k < T2_HEAD_MAX_K; ++k) p[k] = 0.f;
+#pragma unroll 1
+        for (int chunk = 0; chunk < CHUNKS; ++chunk, ++chunk_ctr) {
+          const uint32_t bsel = chunk_ctr % 3;
+          const uint8_t* my_row = staging + bsel * 16384 + row * 128;
+          // one barrier per chunk: everybody has finished chunk-1, hence the reads of the buffer the elected thread refills next
+          ptx::named_bar_sync(1, T2_EPI_THREADS);
+          if (elected && has_res && chunk + 1 < CHUNKS) issue_residual(chunk + 1, chunk_ctr + 1);
+          uint32_t r0[32];
+          ptx::tmem_ld_32x32(taddr + chunk * 64 + half * 32, r0);
+          ptx::tmem_ld_wait();
+          if (chunk == CHUNKS - 1) {
+            ptx::tc_fence_before();
+            ptx::mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+          }
+          if (has_res) ptx::mbar_wait(&res_bar[bsel], (chunk_ctr / 3) & 1, 37);
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            const int g = half * 4 + gg;
+            const int c = chunk * 64 + g * 8;
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+            const float4 t1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float bi[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r0[gg * 8 + j]), sc[j], bi[j]);
+            if (has_res) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(my_row + (((g ^ sw) & 7) << 4));
+              float lo, hi;
+              unpack_bf16x2(rr.x, lo, hi); v[0] += lo; v[1] += hi;
+              unpack_bf16x2(rr.y, lo, hi); v[2] += lo; v[3] += hi;
+              unpack_bf16x2(rr.z, lo, hi); v[4] += lo; v[5] += hi;
+              unpack_bf16x2(rr.w, lo, hi); v[6] += lo; v[7] += hi;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (relu) v[j] = fmaxf(v[j], 0.f);
+              v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));   // the value the feature map would have held
+            }
+#pragma unroll
+            for (int k = 0; k < T2_HEAD_MAX_K; ++k) {
+              if (k < K) {
+                const float4 w0 = *reinterpret_cast<const float4*>(hw + k * 256 + c);       // same address for the whole warp: broadcast
+                const float4 w1 = *reinterpret_cast<const float4*>(hw + k * 256 + c + 4);
+                float acc_k = p[k];
+                acc_k = fmaf(v[0], w0.x, acc_k); acc_k = fmaf(v[1], w0.y, acc_k); acc_k = fmaf(v[2], w0.z, acc_k); acc_k = fmaf(v[3], w0.w, acc_k);
+                acc_k = fmaf(v[4], w1.x, acc_k); acc_k = fmaf(v[5], w1.y, acc_k); acc_k = fmaf(v[6], w1.z, acc_k); acc_k = fmaf(v[7], w1.w, acc_k);
+                p[k] = acc_k;
+              }
+            }
+          }
+        }
+        // the two 32-column halves of a row live in different warps: the upper half hands its sums over, the lower half finishes the pixel
+        if (half == 1) {
+#pragma unroll
+          for (int k = 0; k < T2_HEAD_MAX_K; ++k)
+            if (k < K) hx[row * T2_HEAD_MAX_K + k] = p[k];
+        }
+        ptx::named_bar_sync(1, T2_EPI_THREADS);
+        if (half == 0) {
+          const int second = row >> 6, rr = row & 63;
+          const int pb = second ? b1 : b0, py = (second ? y1 : y0) + (rr >> 4), px = (second ? x1 : x0) + (rr & 15);
+          if (pb < a.B && py < a.Ho && px < a.Wo) {
+            float* dst = a.head_logits + (((size_t)pb * K) * a.Ho + py) * a.Wo + px;
+#pragma unroll
+            for (int k = 0; k < T2_HEAD_MAX_K; ++k)
+              if (k < K) atomicAdd(dst + (size_t)k * a.Ho * a.Wo, p[k] + hx[row * T2_HEAD_MAX_K + k] + (n_tile == 0 ? __ldg(a.head_b + k) : 0.f));
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int chunk = 0; chunk < CHUNKS; ++chunk, ++chunk_ctr) {
         const uint32_t bsel = chunk_ctr % 3;
@@ -472,30 +573,37 @@ bool conv_tc2_applicable(const HkConvDesc& d) {
   return !disabled && d.out_c % 128 == 0 && d.in_c % 64 == 0 && (d.stride == 1 || d.stride == 2);
 }
 
-template <int BLOCK_N, bool DS, bool STATS>
+template <int BLOCK_N, bool DS, bool STATS, bool HEAD = false>
 static int launch_tc2(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& mres,
                       const CUtensorMap& mw2, const CUtensorMap& my2, const ConvTc2Args& a, cudaStream_t s) {
   using Cfg = Tc2Cfg<BLOCK_N>;
-  const int smem_bytes = Cfg::SMEM_BYTES + (STATS ? epi_stats_smem_bytes(a.Cout) : 0);
+  const int smem_bytes = Cfg::SMEM_BYTES + (STATS ? epi_stats_smem_bytes(a.Cout) : 0) + (HEAD ? T2_HEAD_SMEM_BYTES : 0);
   if (smem_bytes > 227 * 1024) return fail(HK_ERR_BAD_ARG, "conv(tcgen05,2cta): %d bytes of shared memory needed", smem_bytes);
   static int attr_smem[16] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && attr_smem[dev] < smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, DS, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, DS, STATS, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): smem attribute (%d B): %s", smem_bytes, cudaGetErrorString(e));
     attr_smem[dev] = smem_bytes;
   }
   const int total = a.num_m_tiles * a.num_n_tiles;
   int clusters = sm_count() / 2;
   if (clusters > total) clusters = total;
-  cudaError_t le = launch_pdl(conv_tc2_kernel<BLOCK_N, DS, STATS>, dim3(2 * clusters), dim3(T2_THREADS), (size_t)smem_bytes, s, mx, mw, my, mres,
+  cudaError_t le = launch_pdl(conv_tc2_kernel<BLOCK_N, DS, STATS, HEAD>, dim3(2 * clusters), dim3(T2_THREADS), (size_t)smem_bytes, s, mx, mw, my, mres,
                               mw2, my2, a);
   if (le != cudaSuccess) return fail(HK_ERR_CUDA, "conv_tc2_kernel: %s", cudaGetErrorString(le));
   return check_launch("conv_tc2_kernel");
 }
 
 // ds != nullptr: block-entry launch (conv1 + the 1x1 downsample conv of the same input, see the header)
+struct ConvTc2Head {
+  const float* w;      // (K, Cout) fp32
+  const float* b;      // (K)
+  float* logits;       // (B, K, Ho, Wo) fp32, zero on entry
+  int K;
+};
+
 struct ConvTc2Ds {
   const void* w;       // (Cout, Cin) bf16, K-major
   const float* scale;
@@ -505,11 +613,13 @@ struct ConvTc2Ds {
 };
 
 static int conv_tc2_launch_impl(const HkConvDesc& d, const void* x, const void* w, const float* scale, const float* bias,
-                                const void* residual, void* y, const ConvTc2Ds* ds, void* bn_acc, cudaStream_t s) {
+                                const void* residual, void* y, const ConvTc2Ds* ds, void* bn_acc, cudaStream_t s,
+                                const ConvTc2Head* head = nullptr) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled entry point not available");
   const long long boxes_all = (long long)ceil_div(d.out_w, T2_BOX_W) * ceil_div(d.out_h, T2_BOX_H) * d.batch;
-  const int block_n = pick_block_n_pair(d.out_c, (boxes_all + 3) / 4);
+  // HEAD: 256-column tiles always -- exactly two N tiles (Cout = 512) must add into every logit for the sum to be order-independent
+  const int block_n = head ? 256 : pick_block_n_pair(d.out_c, (boxes_all + 3) / 4);
   const int ktot = d.kh * d.kw * d.in_c;
   CUtensorMap mx, mw;
   {
@@ -545,7 +655,7 @@ static int conv_tc2_launch_impl(const HkConvDesc& d, const void* x, const void* 
   };
   CUtensorMap my, mres;
   {
-    CUresult r = encode_out(&my, y);
+    CUresult r = encode_out(&my, y ? y : residual);   // HEAD: nothing is stored; the map only has to be well-formed
     if (r != CUDA_SUCCESS) return fail(HK_ERR_CUDA, "conv(tcgen05,2cta): cuTensorMapEncodeTiled(output) failed: %d", (int)r);
     mres = my;
     if (residual) {
@@ -585,6 +695,11 @@ static int conv_tc2_launch_impl(const HkConvDesc& d, const void* x, const void* 
   { const char* m = getenv("HK_TC2_DEBUG"); a.dbg_mode = m ? atoi(m) : 0; }
 #endif
   a.bn_acc = static_cast<BnAcc*>(bn_acc);
+  a.head_w = head ? head->w : nullptr;
+  a.head_b = head ? head->b : nullptr;
+  a.head_logits = head ? head->logits : nullptr;
+  a.head_k = head ? head->K : 0;
+  if (head) return launch_tc2<256, false, false, true>(mx, mw, my, mres, mw2, my2, a, s);
   if (ds) return block_n == 256 ? launch_tc2<256, true, false>(mx, mw, my, mres, mw2, my2, a, s) : launch_tc2<128, true, false>(mx, mw, my, mres, mw2, my2, a, s);
   if (bn_acc) return block_n == 256 ? launch_tc2<256, false, true>(mx, mw, my, mres, mw2, my2, a, s) : launch_tc2<128, false, true>(mx, mw, my, mres, mw2, my2, a, s);
   return block_n == 256 ? launch_tc2<256, false, false>(mx, mw, my, mres, mw2, my2, a, s) : launch_tc2<128, false, false>(mx, mw, my, mres, mw2, my2, a, s);
@@ -616,4 +731,27 @@ extern "C" int hk_conv_ds_fwd(const HkConvDesc* desc, const void* x, const void*
   HK_REQUIRE(y != y_ds && x != y && x != y_ds, "hk_conv_ds_fwd: buffers must not alias");
   ConvTc2Ds ds{w_ds_packed, scale_ds, bias_ds, y_ds, 0};
   return conv_tc2_launch_impl(d, x, w_packed, scale, bias, nullptr, y, &ds, nullptr, as_stream(stream));
+}
+
+// Last conv of the network fused with the K live rows of the scoring conv (see the header): logits += fc_w[:, n-tile] . relu(scale*conv(x)
+// + bias + residual) per pixel.  logits (B, K, out_h, out_w) fp32 must be ZERO on entry (two N tiles add into every element).
+extern "C" int hk_conv_head_fwd(const HkConvDesc* desc, const void* x, const void* w_packed, const float* scale, const float* bias,
+                                const void* residual_or_null, const float* w_fc, const float* b_fc, int K, float* logits, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(desc && x && w_packed && scale && bias && w_fc && b_fc && logits, "hk_conv_head_fwd: null pointer");
+  const HkConvDesc& d = *desc;
+  HK_REQUIRE(d.algo == HK_CONV_TCGEN05 && d.in_dtype == HK_BF16 && d.out_dtype == HK_BF16 && !d.in_is_nchw,
+             "hk_conv_head_fwd: tcgen05 path only (NHWC bf16 activations)");
+  HK_REQUIRE(d.batch > 0 && d.in_h > 0 && d.in_w > 0 && d.kh > 0 && d.kw > 0 && d.dil > 0 && d.pad >= 0 && d.stride == 1, "hk_conv_head_fwd: bad descriptor");
+  const int eh = d.dil * (d.kh - 1) + 1, ew = d.dil * (d.kw - 1) + 1;
+  HK_REQUIRE(d.out_h == d.in_h + 2 * d.pad - eh + 1 && d.out_w == d.in_w + 2 * d.pad - ew + 1, "hk_conv_head_fwd: out_h/out_w inconsistent");
+  HK_REQUIRE(d.out_c == 512 && d.in_c % 64 == 0, "hk_conv_head_fwd: needs out_c == 512 (two 256-column tiles) and in_c %% 64 == 0");
+  HK_REQUIRE(K >= 1 && K <= T2_HEAD_MAX_K, "hk_conv_head_fwd: K=%d outside 1..%d (use hk_conv_bn_act_fwd + hk_head_fwd)", K, T2_HEAD_MAX_K);
+  HK_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(residual_or_null)) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(w_fc) & 15) == 0,
+             "hk_conv_head_fwd: buffers must be 16-byte aligned");
+  ConvTc2Head head{w_fc, b_fc, logits, K};
+  // (the output tensor map is built over the residual / input buffer: HEAD kernels never store through it)
+  return conv_tc2_launch_impl(d, x, w_packed, scale, bias, residual_or_null, const_cast<void*>(residual_or_null ? residual_or_null : x), nullptr, nullptr,
+                              as_stream(stream), &head);
 }

@@ -268,6 +268,17 @@ static void launch_logits(const void* feat, const float* w_fc, const float* b_fc
 
 static int head_fwd_impl(const void* feat, int feat_dtype, const float* w_fc, const float* b_fc, float* logits_ws, float* heat, int B,
                          int K, int C, int h, int w, int H, int W, bool sigmoid, void* stream);
+static int head_upsample_impl(const float* logits_ws, float* heat, int B, int K, int h, int w, int H, int W, bool sigmoid, bool fast, void* stream);
+
+// x8 bilinear upsample (align_corners=True) + sigmoid of (B,K,h,w) fp32 logits that are already there -- the second half of hk_head_fwd,
+// for logits produced by hk_conv_head_fwd.  fast != 0: the throughput-mode arithmetic of the bf16 path; 0: ATen's exact operation order.
+extern "C" int hk_head_upsample_fwd(const float* logits, float* heat, int B, int K, int h, int w, int H, int W, int fast, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(logits && heat, "hk_head_upsample_fwd: null pointer");
+  HK_REQUIRE(B > 0 && K > 0 && h > 0 && w > 0 && H > 0 && W > 0, "hk_head_upsample_fwd: bad shape");
+  HK_REQUIRE((reinterpret_cast<uintptr_t>(heat) & 15) == 0, "hk_head_upsample_fwd: heat must be 16-byte aligned");
+  return head_upsample_impl(logits, heat, B, K, h, w, H, W, true, fast != 0, stream);
+}
 
 extern "C" int hk_head_fwd(const void* feat, int feat_dtype, const float* w_fc, const float* b_fc, float* logits_ws,
                            float* heat, int B, int K, int C, int h, int w, int H, int W, void* stream) {
@@ -296,6 +307,12 @@ static int head_fwd_impl(const void* feat, int feat_dtype, const float* w_fc, co
   else launch_logits<float>(feat, w_fc, b_fc, logits_ws, pixels, h * w, K, C, s);
   int rc = check_launch("head_logits_kernel");
   if (rc) return rc;
+  return head_upsample_impl(logits_ws, heat, B, K, h, w, H, W, sigmoid, feat_dtype == HK_BF16, stream);
+}
+
+static int head_upsample_impl(const float* logits_ws, float* heat, int B, int K, int h, int w, int H, int W, bool sigmoid, bool fast, void* stream) {
+  using namespace hk;
+  cudaStream_t s = as_stream(stream);
   // ATen area_pixel_compute_scale(align_corners=True): (in - 1) / (out - 1) in float, 0 when out == 1
   const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
@@ -307,14 +324,14 @@ static int head_fwd_impl(const void* feat, int feat_dtype, const float* w_fc, co
   // bf16 features = throughput mode: separable lerp + ex2/rcp-approx sigmoid; fp32 features = correctness mode
   if (!sigmoid)  // training: upsampled logits in ATen's exact operation order; the sigmoid lives in hk_bce_fwd_bwd
     head_upsample_sigmoid_kernel<false, false><<<grid, threads, (size_t)2 * w * sizeof(float), s>>>(logits_ws, heat, h, w, H, W, wq, ry, rx);
-  else if (feat_dtype == HK_BF16 && 3.0f * rx < 1.0f) {   // (the rows kernel assumes <= 3 source columns per 4 outputs)
+  else if (fast && 3.0f * rx < 1.0f) {   // (the rows kernel assumes <= 3 source columns per 4 outputs)
     const int nsrc = (int)(ry * (float)kHeadRows) + 3;
     const dim3 grid2(ceil_div(H, kHeadRows), B * K);
     const size_t smem = (size_t)nsrc * w * sizeof(float);
     HK_REQUIRE(smem <= 48 * 1024, "hk_head_fwd: low-res row too wide for the staging buffer");
     head_upsample_rows_kernel<<<grid2, threads, smem, s>>>(logits_ws, heat, h, w, H, W, wq, ry, rx, nsrc);
     return check_launch("head_upsample_rows_kernel");
-  } else if (feat_dtype == HK_BF16)
+  } else if (fast)
     head_upsample_sigmoid_kernel<true><<<grid, threads, (size_t)w * sizeof(float), s>>>(logits_ws, heat, h, w, H, W, wq, ry, rx);
   else
     head_upsample_sigmoid_kernel<false><<<grid, threads, (size_t)2 * w * sizeof(float), s>>>(logits_ws, heat, h, w, H, W, wq, ry, rx);

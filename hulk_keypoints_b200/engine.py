@@ -106,6 +106,7 @@ class InferenceEngine:
         self.stride2_algo = HK_CONV_TCGEN05
         self.stem_on_tensor_cores = True  # bf16 mode: tcgen05 stem; False keeps the fp32 CUDA-core stem
         self.fuse_stem_pool = os.environ.get("HK_STEM_POOL", "1") != "0"   # A/B switch: 0 = stem_tc_kernel + maxpool3x3s2_kernel
+        self.fuse_head = os.environ.get("HK_FUSE_HEAD", "1") != "0"        # A/B switch: 0 = last conv writes the feature map, head_logits_kernel reads it
         self.fuse_downsample = os.environ.get("HK_FUSE_DS", "1") != "0"    # A/B switch: 0 = conv1 and the 1x1 downsample as two launches
         self._packed: Optional[Dict[str, _PackedConv]] = None
         self._packed_key = None
@@ -181,7 +182,9 @@ class InferenceEngine:
                 self._conv(P["stem"], plan.x, plan.stem, relu=True, in_is_nchw=True); n += 1
             ops.maxpool3x3s2(plan.stem, out=x); n += 1
         h, w = plan.h4, plan.w4
-        for i, blk in enumerate(net.blocks()):
+        blocks = list(net.blocks())
+        nblocks, head_done = len(blocks), False
+        for i, blk in enumerate(blocks):
             c1, c2 = P[f"b{i}.c1"], P[f"b{i}.c2"]
             planes = c1.w.shape[0]
             ho, wo = ops.conv_out_hw(h, w, 3, c1.stride, c1.pad, c1.dil)
@@ -201,10 +204,19 @@ class InferenceEngine:
                     self._conv(ds, x, sc, relu=False); n += 1
                 else:
                     sc = x
+            if (i == nblocks - 1 and self.fuse_head and c2.algo == HK_CONV_TCGEN05 and ops.conv_head_supported(t, c2.w, self._fc_w, c2.stride)
+                    and (ho, wo) == (plan.h8, plan.w8)):
+                # last conv of the network: its rows go straight into the K scoring dot products, the feature map is never written
+                ops.conv_head(t, c2.w, c2.scale, c2.bias, self._fc_w, self._fc_b, plan.logits, stride=c2.stride, pad=c2.pad, dil=c2.dil,
+                              relu=True, residual=sc); n += 1          # (+ a memset node for the logits)
+                ops.head_upsample(plan.logits, plan.H, plan.W, heat=plan.heat, fast=True); n += 1
+                head_done = True
+                break
             y = plan.view(free[2], ho, wo, planes)
             self._conv(c2, t, y, relu=True, residual=sc); n += 1
             x, cur, h, w = y, free[2], ho, wo
-        ops.head(x, self._fc_w, self._fc_b, plan.H, plan.W, heat=plan.heat, logits_ws=plan.logits); n += 2
+        if not head_done:
+            ops.head(x, self._fc_w, self._fc_b, plan.H, plan.W, heat=plan.heat, logits_ws=plan.logits); n += 2
         if decode:
             ops.argmax_decode(plan.heat, yx=plan.yx, maxval=plan.maxval, ws=plan.argmax_ws, want_max=True); n += 2
         return n

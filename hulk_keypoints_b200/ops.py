@@ -203,6 +203,52 @@ def head(feat: torch.Tensor, w_fc: torch.Tensor, b_fc: torch.Tensor, H: int, W: 
     return heat
 
 
+HEAD_FUSED_MAX_K = 8
+
+
+def conv_head_supported(x: torch.Tensor, w_packed: torch.Tensor, w_fc: torch.Tensor, stride: int) -> bool:
+    """Shapes hk_conv_head_fwd takes: bf16 NHWC input, 512 output channels, stride 1, at most HEAD_FUSED_MAX_K scoring rows."""
+    return (x.dtype == torch.bfloat16 and w_packed.dtype == torch.bfloat16 and w_packed.shape[0] == 512 and w_packed.shape[3] % 64 == 0
+            and stride == 1 and 1 <= w_fc.shape[0] <= HEAD_FUSED_MAX_K and w_fc.shape[1] == 512 and w_fc.dtype == torch.float32)
+
+
+def conv_head(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, w_fc: torch.Tensor, b_fc: torch.Tensor,
+              logits: torch.Tensor, *, stride: int, pad: int, dil: int, relu: bool = True, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The network's last conv (+ BN + shortcut + ReLU) fused with the K live rows of the 1x1 scoring conv: the epilogue adds
+    w_fc . row (+ b_fc) into `logits` (B,K,Ho,Wo) fp32, which this call zeroes first; the 512-channel feature map is never written."""
+    _need_cuda(x, w_packed, scale, bias, w_fc, b_fc, logits, residual)
+    if not conv_head_supported(x, w_packed, w_fc, stride):
+        raise ValueError("conv_head: unsupported shape (needs bf16 NHWC, 512 output channels, stride 1, 1..8 fp32 scoring rows)")
+    B, H, W, Cin = x.shape
+    cout, kh, kw, cin_w = w_packed.shape
+    if cin_w != Cin:
+        raise ValueError(f"weight cin {cin_w} != input channels {Cin}")
+    Ho, Wo = conv_out_hw(H, W, kh, stride, pad, dil)
+    K = w_fc.shape[0]
+    if tuple(logits.shape) != (B, K, Ho, Wo) or logits.dtype != torch.float32 or not logits.is_contiguous():
+        raise ValueError(f"logits must be a contiguous fp32 {(B, K, Ho, Wo)} tensor")
+    if residual is not None and (tuple(residual.shape) != (B, Ho, Wo, cout) or residual.dtype != torch.bfloat16 or not residual.is_contiguous()):
+        raise ValueError("residual must be a contiguous bf16 tensor of the conv's output shape")
+    if not (x.is_contiguous() and w_packed.is_contiguous() and w_fc.is_contiguous() and b_fc.is_contiguous()):
+        raise ValueError("conv_head needs contiguous tensors")
+    logits.zero_()
+    d = HkConvDesc(B, H, W, Cin, Ho, Wo, cout, kh, kw, stride, pad, dil, int(relu), dtype_code(x.dtype), dtype_code(torch.bfloat16), 0,
+                   HK_CONV_TCGEN05)
+    check(lib().hk_conv_head_fwd(C.byref(d), ptr(x), ptr(w_packed), ptr(scale), ptr(bias), ptr(residual), ptr(w_fc), ptr(b_fc), K, ptr(logits),
+                                 stream_ptr()), "hk_conv_head_fwd")
+    return logits
+
+
+def head_upsample(logits: torch.Tensor, H: int, W: int, heat: Optional[torch.Tensor] = None, fast: bool = True) -> torch.Tensor:
+    """(B,K,h,w) fp32 logits -> sigmoid(x8 bilinear upsample, align_corners=True) (B,K,H,W) fp32: the second half of head()."""
+    _need_cuda(logits, heat)
+    B, K, h, w = logits.shape
+    if heat is None:
+        heat = torch.empty((B, K, H, W), device=logits.device, dtype=torch.float32)
+    check(lib().hk_head_upsample_fwd(ptr(logits), ptr(heat), B, K, h, w, H, W, int(fast), stream_ptr()), "hk_head_upsample_fwd")
+    return heat
+
+
 def argmax_workspace_bytes(B: int, K: int, H: int, W: int) -> int:
     return int(lib().hk_argmax_workspace_bytes(B, K, H, W))
 

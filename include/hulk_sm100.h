@@ -148,6 +148,18 @@ HK_API int hk_maxpool3x3s2_fwd(const void* x, void* y, int dtype, int batch, int
 HK_API int hk_head_fwd(const void* feat, int feat_dtype, const float* w_fc, const float* b_fc,
                 float* logits_ws, float* heat, int B, int K, int C, int h, int w, int H, int W,
                 void* stream);
+/* The same head with the scoring conv folded into the LAST backbone conv (inference, K <= 8):
+ *   hk_conv_head_fwd     : layer4[2].conv2 + bn2 + shortcut + ReLU (src/resnet.py:60-67) and the K live rows of `fc` (src/resnet.py:215,
+ *                          src/model.py:21) in one tcgen05 launch.  The epilogue multiplies each finished row -- rounded to bf16 exactly as the
+ *                          feature map would have stored it -- with w_fc (K, out_c) fp32 and adds the K partial sums to logits
+ *                          (B, K, out_h, out_w) fp32; the (B, out_h, out_w, 512) feature map is never written or re-read.  logits must be
+ *                          ZERO on entry (each element receives the two 256-column tiles' contributions; fp32 addition is commutative,
+ *                          so the result is independent of their order).  Needs out_c == 512, stride 1, bf16 NHWC.
+ *   hk_head_upsample_fwd : x8 bilinear upsample (align_corners=True, src/resnet_dilated.py:27) + sigmoid of such logits -> heat (B,K,H,W). */
+HK_API int hk_conv_head_fwd(const HkConvDesc* desc, const void* x, const void* w_packed, const float* scale, const float* bias,
+                            const void* residual_or_null, const float* w_fc, const float* b_fc, int K, float* logits, void* stream);
+HK_API int hk_head_upsample_fwd(const float* logits, float* heat, int B, int K, int h, int w, int H, int W, int fast, void* stream);
+
 
 /* ---- decode ----
  * Per-keypoint argmax with first-index tie-break.  Replaces src/prediction.py:46

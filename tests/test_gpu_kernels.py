@@ -590,3 +590,64 @@ def test_conv_ds_rejects_bad_shapes():
         ops.conv_ds(x, wp, v, v, wd, v, v, stride=1, pad=0, dil=1)       # pad != dil*(k/2): the 1x1 is not the centre tap
     with pytest.raises(ValueError):
         ops.conv_ds(x.float(), wp, v, v, wd, v, v, stride=1, pad=1, dil=1)  # fp32 activations: tcgen05 path only
+
+
+# ------------------------------------------------------------------ last conv + scoring rows in one launch (src/resnet.py:60-67,215; src/model.py:21)
+HEAD_CASES = [
+    # B, H, W, cin, K, dil, residual
+    (1, 16, 16, 512, 4, 4, True),      # one 256-pixel tile per N tile
+    (2, 60, 80, 512, 4, 4, True),      # layer4[2].conv2 at config.py resolution (feature map 60x80)
+    (3, 21, 27, 256, 8, 2, True),      # ragged boxes, K = 8, another dilation / Cin
+    (1, 13, 9, 512, 1, 1, False),      # K = 1, no shortcut, a single partial tile
+    (5, 60, 80, 512, 3, 4, True),      # more work items than CTA pairs
+]
+
+
+@pytest.mark.parametrize("case", HEAD_CASES)
+def test_conv_head_fused_logits(case):
+    """hk_conv_head_fwd against hk_conv_bn_act_fwd followed by the fc rows applied (in fp64) to the bf16 feature map it stores: the fused
+    epilogue rounds each row to bf16 exactly as the feature map would have held it, so only the fp32 summation order differs.  Also
+    bit-reproducible run to run (two commutative contributions per logit) and equal, to fp32 rounding, to hk_head_fwd's logits."""
+    B, H, W, cin, K, dil, residual = case
+    g = torch.Generator().manual_seed(100 + cin + K)
+    x = torch.randn(B, H, W, cin, generator=g).to(dev()).to(torch.bfloat16)
+    w = (torch.randn(512, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5).to(dev())
+    s, b = (torch.rand(512, generator=g) + 0.5).to(dev()), (torch.randn(512, generator=g) * 0.1).to(dev())
+    res = torch.randn(B, H, W, 512, generator=g).to(dev()).to(torch.bfloat16) if residual else None
+    w_fc = (torch.randn(K, 512, generator=g) * 0.05).to(dev())
+    b_fc = (torch.randn(K, generator=g) * 0.1).to(dev())
+    wp, _, _ = ops.pack_conv_weights(w, None, 1e-5, torch.bfloat16)
+    assert ops.conv_head_supported(x, wp, w_fc, 1)
+    import os
+    os.environ["HK_CONV_HALO"] = "0"   # the reference feature map from the same (plain CTA-pair) kernel: the haloed one accumulates its K
+    try:                               # blocks in another order, which moves a few bf16 roundings of the feature map by one ulp
+        feat = ops.conv_bn_act(x, wp, s, b, stride=1, pad=dil, dil=dil, relu=True, residual=res)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("HK_CONV_HALO", None)
+    ref = torch.einsum("bhwc,kc->bkhw", feat.double(), w_fc.double()) + b_fc.double().view(1, K, 1, 1)
+    logits = torch.full((B, K, H, W), float("nan"), device=dev())
+    ops.conv_head(x, wp, s, b, w_fc, b_fc, logits, stride=1, pad=dil, dil=dil, relu=True, residual=res)
+    torch.cuda.synchronize()
+    first = logits.clone()
+    ops.conv_head(x, wp, s, b, w_fc, b_fc, logits, stride=1, pad=dil, dil=dil, relu=True, residual=res)
+    torch.cuda.synchronize()
+    assert torch.equal(first, logits)
+    err = (logits.double() - ref).abs()
+    bound = 1e-5 * (feat.double().abs().unsqueeze(1) * w_fc.double().abs().view(1, K, 1, 1, 512)).sum(-1) + 1e-6   # fp32 accumulation of 512 terms
+    assert (err <= bound).all(), f"max err {err.max().item():.3g} (bound {bound.max().item():.3g})"
+    # and the two-kernel head produces the same heatmaps to fp32 rounding of the logits
+    heat2 = ops.head(feat, w_fc, b_fc, 8 * (H - 1) + 8, 8 * (W - 1) + 8)
+    heat1 = ops.head_upsample(logits, 8 * (H - 1) + 8, 8 * (W - 1) + 8)
+    assert (heat1 - heat2).abs().max().item() < 2e-6
+
+
+def test_conv_head_rejects_unsupported():
+    x = torch.zeros(1, 16, 16, 64, device=dev(), dtype=torch.bfloat16)
+    wp = torch.zeros(512, 3, 3, 64, device=dev(), dtype=torch.bfloat16)
+    v = torch.zeros(512, device=dev())
+    with pytest.raises(ValueError):   # nine scoring rows: beyond the fused epilogue's register budget
+        ops.conv_head(x, wp, v, v, torch.zeros(9, 512, device=dev()), torch.zeros(9, device=dev()), torch.zeros(1, 9, 16, 16, device=dev()),
+                      stride=1, pad=1, dil=1)
+    wp256 = torch.zeros(256, 3, 3, 64, device=dev(), dtype=torch.bfloat16)
+    assert not ops.conv_head_supported(x, wp256, torch.zeros(4, 512, device=dev()), 1)

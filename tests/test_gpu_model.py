@@ -170,6 +170,27 @@ def test_fused_block_entry_and_stem_pool_leave_every_bit_unchanged(sd_cal):
     assert torch.equal(kp_fused, kp_ds) and torch.equal(kp_fused, kp_plain)
 
 
+def test_head_fused_into_last_conv_matches_two_kernel_head(sd_trained):
+    """fuse_head (the last conv's epilogue computes the K scoring rows; no feature map, no head_logits_kernel) against the
+    feature-map path: one launch fewer, heatmaps equal to fp32 summation order of the 512-term dot products, same keypoints."""
+    sd, (H, W) = sd_trained
+    x = rand_img(17, 3, H, W).cuda()
+    m = make_model(sd, "bf16")
+    eng = m.engine()
+    assert eng.fuse_head
+    h1, kp1 = eng.forward(x, decode=True)
+    n1 = eng.plan_for(3, H, W).launches
+    m2 = make_model(sd, "bf16")
+    e2 = m2.engine()
+    e2.fuse_head = False
+    h2, kp2 = e2.forward(x, decode=True)
+    assert e2.plan_for(3, H, W).launches == n1 + 1
+    assert (h1 - h2).abs().max().item() < 5e-6
+    assert torch.equal(kp1, kp2)
+    h1b, _ = eng.forward(x, decode=True)      # graph replay: the logits are re-zeroed inside the graph
+    assert torch.equal(h1, h1b)
+
+
 def test_stride2_tensor_core_and_ffma_paths_agree(sd_cal):
     from hulk_keypoints_b200._lib import HK_CONV_FFMA
     m = make_model(sd_cal, "bf16")
