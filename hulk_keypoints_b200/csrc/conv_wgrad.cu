@@ -31,7 +31,11 @@ struct WgradArgs {
   int B, Ho, Wo, Cout, Cin, kh, kw, stride, pad, dil;
   int tiles_x, tiles_per_img, num_boxes;
   int m_tiles, n_tiles, taps, ksplit, boxes_per_split;
-  int cout64;  // Cout == 64: the single 64-channel dY box is loaded twice (rows 64..127 of the accumulator are ignored)
+  int cout64;  // Cout == 64: the single 64-channel dY box is loaded twice (rows 64..127 of the accumulator are ignored) ...
+  int tap_pairs;  // ... or, stride 1: TWO taps per unit.  dW_t[co,ci] = sum_p dY[p,co] X[p+off_t,ci] = sum_q dY[q-off_t,co] X[q,ci]: the shift moves
+                  // to dY, rows 0..63 of the A operand are dY shifted for tap 2u and rows 64..127 dY shifted for tap 2u+1, B is the unshifted X
+                  // box -- all 128 accumulator rows do useful work (5 units instead of 9 per K split for a 3x3 conv)
+  int tap_units;  // units along the tap axis: taps, or ceil(taps / 2) with tap_pairs
 };
 
 template <int BLOCK_N>
@@ -60,8 +64,8 @@ __device__ __forceinline__ void wg_decode_unit(const WgradArgs& a, int u, int& k
   u /= a.n_tiles;
   m = u % a.m_tiles;
   u /= a.m_tiles;
-  tap = u % a.taps;
-  ks = u / a.taps;
+  tap = u % a.tap_units;
+  ks = u / a.tap_units;
 }
 __device__ __forceinline__ void wg_decode_box(const WgradArgs& a, int box, int& b, int& y0, int& x0) {
   b = box / a.tiles_per_img;
@@ -85,7 +89,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-  const int total_units = a.ksplit * a.taps * a.m_tiles * a.n_tiles;
+  const int total_units = a.ksplit * a.tap_units * a.m_tiles * a.n_tiles;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_dy);
@@ -117,8 +121,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       int ks, tap, m, n;
       wg_decode_unit(a, u, ks, tap, m, n);
-      const int r = tap / a.kw, s = tap - r * a.kw;
+      // tap_pairs: `tap` is a pair index; the two taps' shifts go to the two dY boxes, X stays put
+      const int t0 = a.tap_pairs ? 2 * tap : tap, t1 = a.tap_pairs ? min(2 * tap + 1, a.taps - 1) : tap;
+      const int r = t0 / a.kw, s = t0 - r * a.kw;
       const int dy = r * a.dil - a.pad, dx = s * a.dil - a.pad;
+      const int r1 = t1 / a.kw, s1 = t1 - r1 * a.kw;
+      const int dy1 = r1 * a.dil - a.pad, dx1 = s1 * a.dil - a.pad;
+      const int ax0 = a.tap_pairs ? -dx : 0, ay0 = a.tap_pairs ? -dy : 0, ax1 = a.tap_pairs ? -dx1 : 0, ay1 = a.tap_pairs ? -dy1 : 0;
+      const int bdx = a.tap_pairs ? 0 : dx, bdy = a.tap_pairs ? 0 : dy;
       const int box_lo = ks * a.boxes_per_split;
       const int box_hi = min(box_lo + a.boxes_per_split, a.num_boxes);
       const int co0 = m * 128, co1 = a.cout64 ? 0 : co0 + 64;
@@ -129,12 +139,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         if (ptx::elect_one_sync()) {
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          ptx::tma_load_4d(sa, &map_dy, &full_bar[stage], co0, x0, y0, b);
-          ptx::tma_load_4d(sa + WG_BOX_BYTES, &map_dy, &full_bar[stage], co1, x0, y0, b);
+          ptx::tma_load_4d(sa, &map_dy, &full_bar[stage], co0, x0 + ax0, y0 + ay0, b);
+          ptx::tma_load_4d(sa + WG_BOX_BYTES, &map_dy, &full_bar[stage], co1, x0 + ax1, y0 + ay1, b);
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
-            ptx::tma_load_4d(sa + WG_A_BYTES + j * WG_BOX_BYTES, &map_x, &full_bar[stage], n * BLOCK_N + j * 64, x0 * a.stride + dx,
-                             y0 * a.stride + dy, b);
+            ptx::tma_load_4d(sa + WG_A_BYTES + j * WG_BOX_BYTES, &map_x, &full_bar[stage], n * BLOCK_N + j * 64, x0 * a.stride + bdx,
+                             y0 * a.stride + bdy, b);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -146,7 +156,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     uint32_t stage = 0, phase = 0, it = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      const int ks = u / (a.taps * a.m_tiles * a.n_tiles);
+      const int ks = u / (a.tap_units * a.m_tiles * a.n_tiles);
       const int box_lo = ks * a.boxes_per_split;
       const int nbox = min(box_lo + a.boxes_per_split, a.num_boxes) - box_lo;
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 42);
@@ -178,9 +188,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       int ks, tap, m, n;
       wg_decode_unit(a, u, ks, tap, m, n);
-      const int co = m * 128 + row;
-      const bool valid = co < a.Cout && !(a.cout64 && row >= 64);
-      float* dst = a.ws + (((size_t)ks * a.Cout + co) * a.taps + tap) * a.Cin + (size_t)n * BLOCK_N;
+      int co = m * 128 + row;
+      bool valid = co < a.Cout && !(a.cout64 && row >= 64);
+      if (a.tap_pairs) {   // rows 0..63: tap 2u, rows 64..127: tap 2u+1 (absent for the last unit of an odd tap count)
+        const int second = row >> 6;
+        co = row & 63;
+        tap = 2 * tap + second;
+        valid = tap < a.taps;
+      }
+      float* dst = a.ws + (((size_t)ks * a.Cout + co) * a.taps + (valid ? tap : 0)) * a.Cin + (size_t)n * BLOCK_N;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 44);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
@@ -232,7 +248,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode_fn();
 
 struct WgradPlan {
-  int block_n, m_tiles, n_tiles, taps, ksplit, boxes_per_split, num_boxes, tiles_x, tiles_per_img;
+  int block_n, m_tiles, n_tiles, taps, ksplit, boxes_per_split, num_boxes, tiles_x, tiles_per_img, tap_pairs, tap_units;
 };
 static WgradPlan wgrad_plan(const HkConvDesc& d) {
   WgradPlan p;
@@ -240,10 +256,14 @@ static WgradPlan wgrad_plan(const HkConvDesc& d) {
   p.m_tiles = d.out_c <= 64 ? 1 : d.out_c / 128;
   p.n_tiles = d.in_c / p.block_n;
   p.taps = d.kh * d.kw;
+  // two taps per unit (the shift on dY): the 64-output-channel convs at stride 1 with equal input / output grids, i.e. layer 1
+  static const bool pairs_off = [] { const char* e = getenv("HK_WGRAD_TAP_PAIRS"); return e && e[0] == '0'; }();
+  p.tap_pairs = (!pairs_off && d.out_c == 64 && d.stride == 1 && d.in_h == d.out_h && d.in_w == d.out_w && p.taps > 1) ? 1 : 0;
+  p.tap_units = p.tap_pairs ? (p.taps + 1) / 2 : p.taps;
   p.tiles_x = ceil_div(d.out_w, WG_BOX_W);
   p.tiles_per_img = p.tiles_x * ceil_div(d.out_h, WG_BOX_H);
   p.num_boxes = p.tiles_per_img * d.batch;
-  const int base = p.taps * p.m_tiles * p.n_tiles;
+  const int base = p.tap_units * p.m_tiles * p.n_tiles;
   int ks = (2 * sm_count()) / base;
   if (ks < 1) ks = 1;
   const int max_ks = p.num_boxes / 4 > 0 ? p.num_boxes / 4 : 1;  // at least 4 pipeline stages of work per unit
@@ -264,7 +284,7 @@ static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const Wgr
     if (e != cudaSuccess) return fail(HK_ERR_CUDA, "conv wgrad: smem attribute (%d B): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
     attr_dev_mask |= (1 << dev);
   }
-  const int total = a.ksplit * a.taps * a.m_tiles * a.n_tiles;
+  const int total = a.ksplit * a.tap_units * a.m_tiles * a.n_tiles;
   int grid = sm_count();
   if (grid > total) grid = total;
   conv_wgrad_kernel<BLOCK_N><<<grid, WG_THREADS, Cfg::SMEM_BYTES, s>>>(mdy, mx, a);
@@ -325,6 +345,8 @@ int hk_conv_wgrad(const HkConvDesc* desc, const void* x, const void* dy, float* 
   a.tiles_x = p.tiles_x; a.tiles_per_img = p.tiles_per_img; a.num_boxes = p.num_boxes;
   a.m_tiles = p.m_tiles; a.n_tiles = p.n_tiles; a.taps = p.taps; a.ksplit = p.ksplit; a.boxes_per_split = p.boxes_per_split;
   a.cout64 = d.out_c == 64 ? 1 : 0;
+  a.tap_pairs = p.tap_pairs;
+  a.tap_units = p.tap_units;
   cudaStream_t s = as_stream(stream);
   int rc;
   switch (p.block_n) {

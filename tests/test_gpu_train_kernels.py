@@ -207,7 +207,9 @@ def test_conv_dgrad_stride2_via_zero_insertion(k):
 
 # ------------------------------------------------------------------ conv weight gradient (tcgen05, MN-major operands)
 @pytest.mark.parametrize("cin,cout,k,stride,dil,B,hw", [
-    (64, 64, 3, 1, 1, 2, (24, 32)),      # layer1 shape (Cout = 64: duplicated M rows)
+    (64, 64, 3, 1, 1, 2, (24, 32)),      # layer1 shape (Cout = 64: two taps per unit, the shift on dY)
+    (64, 64, 3, 1, 1, 3, (21, 27)),      # the same with ragged tiles: zero-filled dY boxes on every side
+    (64, 64, 3, 1, 2, 2, (24, 32)),      # ... and dilation 2
     (64, 128, 3, 2, 1, 2, (24, 32)),     # layer2.0.conv1 (stride 2 through the tensor map's element strides)
     (64, 128, 1, 2, 1, 2, (24, 32)),     # layer2.0.downsample
     (128, 128, 3, 1, 1, 3, (12, 16)),
