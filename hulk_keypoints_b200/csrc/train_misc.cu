@@ -5,6 +5,8 @@
 //     of the K-row 1x1 scoring conv                       (autograd of src/resnet_dilated.py:27, src/resnet.py:215)
 //   * stem weight gradient (7x7 s2, Cin=3): CUDA-core kernel, the K dimension (147) is too thin for TMA im2col
 // All deterministic (gather formulations / fixed-order partial sums; no atomics).
+#include <stdlib.h>
+
 #include "hk_common.cuh"
 
 namespace hk {
@@ -154,6 +156,63 @@ __global__ void __launch_bounds__(128) upsample_bwd_kernel(const float* __restri
     acc = fmaf(rowacc, wy, acc);
   }
   dl[idx] = acc;
+}
+
+// The same transpose, separable and coalesced (round 2): one CTA per (map, low-res row y).  Phase 1: v[X] = sum_Y wy(Y, y) * g[m, Y, X] over the
+// <= ~2*scale+3 high-res rows that touch y, every thread owning 4 consecutive X (float4 row reads); phase 2: dl[m, y, x] = sum_X wx(X, x) *
+// v[X] from shared memory.  Each high-res row is read by the two CTAs whose low-res rows it feeds.  The one-thread-per-pixel kernel above
+// spent ~4 k instructions per output on index arithmetic over 18 x 18 candidates with stride-8 loads: 190 us at batch 32 where this
+// takes ~1/3 of that.  (Summation order: rows first, then columns.)
+__global__ void __launch_bounds__(256) upsample_bwd_rows_kernel(const float* __restrict__ g, float* __restrict__ dl, int h, int w, int H, int W,
+                                                               float ry, float rx) {
+  extern __shared__ float v_row[];   // W floats (+ padding to a multiple of 4)
+  const int y = blockIdx.x, m = blockIdx.y;
+  const float inv_ry = ry > 0.f ? 1.f / ry : 0.f, inv_rx = rx > 0.f ? 1.f / rx : 0.f;
+  const int Ylo = ry > 0.f ? max(0, (int)floorf((float)(y - 1) * inv_ry) - 1) : 0;
+  const int Yhi = ry > 0.f ? min(H - 1, (int)ceilf((float)(y + 1) * inv_ry) + 1) : H - 1;
+  const float* gm = g + (size_t)m * H * W;
+  const bool vec = (W & 3) == 0;
+  for (int X4 = threadIdx.x * 4; X4 < W; X4 += blockDim.x * 4) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int Y = Ylo; Y <= Yhi; ++Y) {
+      const float sy = ry * (float)Y;
+      const int y0 = min((int)sy, h - 1);
+      const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+      const float ly = sy - (float)y0, hy = 1.0f - ly;
+      float wy = 0.f;
+      if (y0 == y) wy += hy;
+      if (y1 == y) wy += ly;
+      if (wy == 0.f) continue;   // CTA-uniform
+      const float* row = gm + (size_t)Y * W + X4;
+      if (vec) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(row));
+        a0 = fmaf(q.x, wy, a0); a1 = fmaf(q.y, wy, a1); a2 = fmaf(q.z, wy, a2); a3 = fmaf(q.w, wy, a3);
+      } else {
+        a0 = fmaf(__ldg(row), wy, a0);
+        if (X4 + 1 < W) a1 = fmaf(__ldg(row + 1), wy, a1);
+        if (X4 + 2 < W) a2 = fmaf(__ldg(row + 2), wy, a2);
+        if (X4 + 3 < W) a3 = fmaf(__ldg(row + 3), wy, a3);
+      }
+    }
+    v_row[X4] = a0; v_row[X4 + 1] = a1; v_row[X4 + 2] = a2; v_row[X4 + 3] = a3;
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < w; x += blockDim.x) {
+    const int Xlo = rx > 0.f ? max(0, (int)floorf((float)(x - 1) * inv_rx) - 1) : 0;
+    const int Xhi = rx > 0.f ? min(W - 1, (int)ceilf((float)(x + 1) * inv_rx) + 1) : W - 1;
+    float acc = 0.f;
+    for (int X = Xlo; X <= Xhi; ++X) {
+      const float sx = rx * (float)X;
+      const int x0 = min((int)sx, w - 1);
+      const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+      const float lx = sx - (float)x0, hx = 1.0f - lx;
+      float wx = 0.f;
+      if (x0 == x) wx += hx;
+      if (x1 == x) wx += lx;
+      if (wx != 0.f) acc = fmaf(v_row[X], wx, acc);
+    }
+    dl[((size_t)m * h + y) * w + x] = acc;
+  }
 }
 
 // dfeat[p, c] = sum_k dl[b, k, pix] * w[k, c]   (bf16 NHWC out); one thread per (pixel, 8 channels)
@@ -323,8 +382,16 @@ int hk_head_bwd(const float* g_up, const void* feat, const float* w_fc, float* d
   const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
   const int n = B * K * h * w;
-  upsample_bwd_kernel<<<ceil_div(n, 128), 128, 0, s>>>(g_up, dlogits_ws, B * K, h, w, H, W, ry, rx);
-  int rc = check_launch("upsample_bwd_kernel");
+  int rc;
+  static const bool old_upsample_bwd = [] { const char* e = getenv("HK_UPSAMPLE_BWD_ROWS"); return e && e[0] == '0'; }();   // A/B switch
+  const size_t vbytes = (size_t)((W + 3) / 4 * 4) * sizeof(float);
+  if (!old_upsample_bwd && h <= 65535 && B * K <= 65535 && vbytes <= 48 * 1024 && (reinterpret_cast<uintptr_t>(g_up) & 15) == 0) {
+    upsample_bwd_rows_kernel<<<dim3(h, B * K), 256, vbytes, s>>>(g_up, dlogits_ws, h, w, H, W, ry, rx);
+    rc = check_launch("upsample_bwd_rows_kernel");
+  } else {
+    upsample_bwd_kernel<<<ceil_div(n, 128), 128, 0, s>>>(g_up, dlogits_ws, B * K, h, w, H, W, ry, rx);
+    rc = check_launch("upsample_bwd_kernel");
+  }
   if (rc) return rc;
   const int hw = h * w;
   fc_bwd_dfeat_kernel<<<grid_for((long long)B * hw * (C >> 3), 256), 256, 0, s>>>(dlogits_ws, w_fc, static_cast<__nv_bfloat16*>(dfeat), B, K,

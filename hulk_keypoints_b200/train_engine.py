@@ -177,11 +177,19 @@ class TrainEngine:
             self._pack_items = torch.from_numpy(arr.view(np.uint8).copy()).to(self.device)
             self._pack_key = key
             self._pack_max = max(c.cout * c.cin * c.k * c.k for c in self.convs[1:])
+            self._pack_khw = max(c.k * c.k for c in self.convs[1:])
+            # shared-memory tiled repack (contiguous reads, 64-byte writes) when every conv tiles 64 x 32; HK_PACK_TILED=0: element-wise kernel
+            self._pack_tiled = (os.environ.get("HK_PACK_TILED", "1") != "0"
+                                and all(c.cout % 64 == 0 and c.cin % 32 == 0 for c in self.convs[1:]))
             for c in self.convs:  # scale = 1 / bias = 0 of the raw convs: constant
                 c.one_out.fill_(1.0)
                 c.zero_out.zero_()
-        check(lib().hk_pack_conv_weights_many(ptr(self._pack_items), len(self.convs) - 1, C.c_longlong(self._pack_max), stream_ptr()),
-              "hk_pack_conv_weights_many")
+        if self._pack_tiled:
+            check(lib().hk_pack_conv_weights_many_tiled(ptr(self._pack_items), len(self.convs) - 1, self._pack_khw, C.c_longlong(self._pack_max),
+                                                        stream_ptr()), "hk_pack_conv_weights_many_tiled")
+        else:
+            check(lib().hk_pack_conv_weights_many(ptr(self._pack_items), len(self.convs) - 1, C.c_longlong(self._pack_max), stream_ptr()),
+                  "hk_pack_conv_weights_many")
         return 1
 
     def _pack(self, c: _ConvT, with_dgrad: bool) -> int:

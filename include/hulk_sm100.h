@@ -278,6 +278,10 @@ typedef struct HkPackItem {
   int32_t cout, cin, khw, reserved;
 } HkPackItem;
 HK_API int hk_pack_conv_weights_many(const HkPackItem* items_dev, int n_items, long long max_elems, void* stream);
+/* The same through shared-memory tiles (64 output x 32 input channels x all taps per CTA: contiguous source runs, 64-byte destination
+ * runs in both layouts; ~3x faster).  Every item needs cout % 64 == 0, cin % 32 == 0 and khw <= max_khw. */
+HK_API int hk_pack_conv_weights_many_tiled(const HkPackItem* items_dev, int n_items, int max_khw, long long max_elems, void* stream);
+
 /* Conv weights for the data gradient: (cout,cin,kh,kw) fp32 -> (cin, kh, kw, cout) bf16 with the taps flipped. */
 HK_API int hk_pack_conv_weights_dgrad(const float* w_oihw, int cout, int cin, int kh, int kw, void* w_out, void* stream);
 /* (B,h,w,C) bf16 -> (B,2h,2w,C) with the values at even (y,x) and zeros elsewhere: the data gradient of a stride-2 conv is the
