@@ -32,7 +32,7 @@ EXPORTS = (
     "hk_head_bwd_workspace_bytes", "hk_head_bwd", "hk_sigmoid_fwd", "hk_sigmoid_bwd", "hk_pack_conv_weights_many",
     # round 2
     "hk_soft_argmax_workspace_bytes", "hk_soft_argmax", "hk_l1_normalize_dim1", "hk_stem_pool_fwd", "hk_stem_pool_fwd_u8",
-    "hk_conv_ds_fwd", "hk_bn_acc_bytes", "hk_bn_stats_acc", "hk_bn_apply_fwd_acc", "hk_bn_bwd_acc", "hk_conv_bn_stats_fwd", "hk_conv_head_fwd", "hk_head_upsample_fwd", "hk_pack_conv_weights_many_tiled",
+    "hk_conv_ds_fwd", "hk_bn_acc_bytes", "hk_bn_stats_acc", "hk_bn_apply_fwd_acc", "hk_bn_bwd_acc", "hk_conv_bn_stats_fwd", "hk_conv_head_fwd", "hk_head_upsample_fwd", "hk_pack_conv_weights_many_tiled", "hk_maxpool3x3s2_fwd_idx", "hk_maxpool3x3s2_bwd_idx",
 )
 
 
@@ -62,6 +62,10 @@ def _declare(lib):
     lib.hk_conv_bn_stats_fwd.argtypes = [C.POINTER(HkConvDesc), vp, vp, vp, vp, vp, vp, vp]
     lib.hk_pack_conv_weights_many_tiled.restype = i
     lib.hk_pack_conv_weights_many_tiled.argtypes = [vp, i, i, C.c_longlong, vp]
+    lib.hk_maxpool3x3s2_fwd_idx.restype = i
+    lib.hk_maxpool3x3s2_fwd_idx.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp]
+    lib.hk_maxpool3x3s2_bwd_idx.restype = i
+    lib.hk_maxpool3x3s2_bwd_idx.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp]
     lib.hk_conv_head_fwd.restype = i
     lib.hk_conv_head_fwd.argtypes = [C.POINTER(HkConvDesc), vp, vp, vp, vp, vp, vp, vp, i, vp, vp]
     lib.hk_head_upsample_fwd.restype = i

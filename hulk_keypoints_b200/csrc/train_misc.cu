@@ -26,8 +26,10 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
 // pass 1: idx[b,oy,ox,c] = tap (r*3+s) of the first maximum of the window in (r, s) scan order among in-bounds taps -- the element
 //         ATen's max_pool2d_with_indices routes the gradient to;
 // pass 2: dx[b,iy,ix,c] = sum over the (<= 4) windows containing (iy,ix) of dout[window] * [idx[window] == my tap]   (gather).
+// ymax != nullptr: also store the window maxima, i.e. this IS the forward max-pool of the training step (one pass over the stem map
+// instead of a forward pass plus this one in the backward).
 __global__ void __launch_bounds__(256) maxpool_argmax_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ idx, int B, int H, int W,
-                                                            int C, int Ho, int Wo) {
+                                                            int C, int Ho, int Wo, __nv_bfloat16* __restrict__ ymax = nullptr) {
   const int CG = C >> 3;
   const long long total = (long long)B * Ho * Wo * CG;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -60,6 +62,7 @@ __global__ void __launch_bounds__(256) maxpool_argmax_kernel(const __nv_bfloat16
     packed.x = (uint32_t)who[0] | ((uint32_t)who[1] << 8) | ((uint32_t)who[2] << 16) | ((uint32_t)who[3] << 24);
     packed.y = (uint32_t)who[4] | ((uint32_t)who[5] << 8) | ((uint32_t)who[6] << 16) | ((uint32_t)who[7] << 24);
     *reinterpret_cast<uint2*>(idx + i * 8) = packed;
+    if (ymax) st8(ymax + i * 8, best);
   }
 }
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ idx,
@@ -352,6 +355,29 @@ int hk_maxpool3x3s2_bwd(const void* dout, const void* x, void* dx, int B, int H,
   const long long total = (long long)B * H * W * (C >> 3);
   maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dout),
                                                                          static_cast<const uint8_t*>(idx_ws),
+                                                                         static_cast<__nv_bfloat16*>(dx), B, H, W, C, Ho, Wo);
+  return check_launch("maxpool_bwd_kernel");
+}
+
+// Training-step max-pool in two halves: the forward also records which tap of every window won (ATen's max_pool2d_with_indices rule: first
+// maximum in scan order), the backward is then the gather alone.
+int hk_maxpool3x3s2_fwd_idx(const void* x, void* y, void* idx, int B, int H, int W, int C, int Ho, int Wo, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(x && y && idx, "hk_maxpool3x3s2_fwd_idx: null pointer");
+  HK_REQUIRE(B > 0 && H > 0 && W > 0 && C >= 8 && (C & 7) == 0 && Ho == (H + 2 - 3) / 2 + 1 && Wo == (W + 2 - 3) / 2 + 1,
+             "hk_maxpool3x3s2_fwd_idx: bad shape");
+  maxpool_argmax_kernel<<<grid_for((long long)B * Ho * Wo * (C >> 3), 256), 256, 0, as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(idx), B, H, W, C, Ho, Wo, static_cast<__nv_bfloat16*>(y));
+  return check_launch("maxpool_argmax_kernel");
+}
+
+int hk_maxpool3x3s2_bwd_idx(const void* dout, const void* idx, void* dx, int B, int H, int W, int C, int Ho, int Wo, void* stream) {
+  using namespace hk;
+  HK_REQUIRE(dout && idx && dx, "hk_maxpool3x3s2_bwd_idx: null pointer");
+  HK_REQUIRE(B > 0 && H > 0 && W > 0 && C >= 8 && (C & 7) == 0 && Ho == (H + 2 - 3) / 2 + 1 && Wo == (W + 2 - 3) / 2 + 1,
+             "hk_maxpool3x3s2_bwd_idx: bad shape");
+  const long long total = (long long)B * H * W * (C >> 3);
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dout), static_cast<const uint8_t*>(idx),
                                                                          static_cast<__nv_bfloat16*>(dx), B, H, W, C, Ho, Wo);
   return check_launch("maxpool_bwd_kernel");
 }

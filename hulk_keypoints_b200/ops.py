@@ -543,6 +543,33 @@ def maxpool3x3s2_bwd(dout: torch.Tensor, x: torch.Tensor, dx: Optional[torch.Ten
     return dx
 
 
+def maxpool3x3s2_fwd_idx(x: torch.Tensor, out: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None):
+    """MaxPool2d(3,2,1) forward on bf16 NHWC that also records the winning tap of every window (uint8, B*Ho*Wo*C) -> (out, idx)."""
+    _need_cuda(x, out, idx)
+    B, H, W, Cc = x.shape
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    if x.dtype != torch.bfloat16 or not x.is_contiguous():
+        raise ValueError("maxpool3x3s2_fwd_idx needs a contiguous bf16 NHWC tensor")
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cc), device=x.device, dtype=torch.bfloat16)
+    if idx is None:
+        idx = torch.empty(B * Ho * Wo * Cc, device=x.device, dtype=torch.uint8)
+    if tuple(out.shape) != (B, Ho, Wo, Cc) or idx.numel() < B * Ho * Wo * Cc or idx.dtype != torch.uint8:
+        raise ValueError("maxpool3x3s2_fwd_idx: bad out / idx buffer")
+    check(lib().hk_maxpool3x3s2_fwd_idx(ptr(x), ptr(out), ptr(idx), B, H, W, Cc, Ho, Wo, stream_ptr()), "hk_maxpool3x3s2_fwd_idx")
+    return out, idx
+
+
+def maxpool3x3s2_bwd_idx(dout: torch.Tensor, idx: torch.Tensor, H: int, W: int, dx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Backward of maxpool3x3s2_fwd_idx: dout (B,Ho,Wo,C) bf16 routed through the recorded indices -> dx (B,H,W,C) bf16."""
+    _need_cuda(dout, idx, dx)
+    B, Ho, Wo, Cc = dout.shape
+    if dx is None:
+        dx = torch.empty((B, H, W, Cc), device=dout.device, dtype=torch.bfloat16)
+    check(lib().hk_maxpool3x3s2_bwd_idx(ptr(dout), ptr(idx), ptr(dx), B, H, W, Cc, Ho, Wo, stream_ptr()), "hk_maxpool3x3s2_bwd_idx")
+    return dx
+
+
 def head_logits(feat: torch.Tensor, w_fc: torch.Tensor, b_fc: torch.Tensor, H: int, W: int, out: Optional[torch.Tensor] = None,
                 logits_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(B,h,w,C) features -> (B,K,H,W) fp32 upsampled LOGITS (no sigmoid): the training-side head."""

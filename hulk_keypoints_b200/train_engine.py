@@ -100,6 +100,8 @@ class TrainEngine:
         # ... and the forward statistics gathered in the conv epilogues (hk_conv_bn_stats_fwd): 36 launches and one read of every raw conv
         # output fewer.  HK_CONV_STATS=0: stand-alone hk_bn_stats_acc.
         self.fuse_conv_stats = os.environ.get("HK_CONV_STATS", "1") != "0"
+        # max-pool forward records the winning taps (one pass over the stem map instead of two); HK_MAXPOOL_IDX=0: argmax pass in the backward
+        self.maxpool_idx = os.environ.get("HK_MAXPOOL_IDX", "1") != "0"
         offs_acc, tot = [], 0
         for c in self.convs:
             offs_acc.append(tot)
@@ -325,7 +327,10 @@ class TrainEngine:
                                st.scale, st.shift, self.bn_ws)
             ops.bn_apply(st.y, st.scale, st.shift, relu=True, out=self.a0, relu_bits=st.relu_bits if self.use_relu_bits else None)
         st.relu_out = self.a0
-        ops.maxpool3x3s2(self.a0, out=self.p0)
+        if self.maxpool_idx:
+            ops.maxpool3x3s2_fwd_idx(self.a0, out=self.p0, idx=self.pool_idx)   # forward + the winning taps the backward routes through
+        else:
+            ops.maxpool3x3s2(self.a0, out=self.p0)
         self._join_wgrad_stream()               # packed weights ready
         n += 5
         x = self.p0
@@ -423,9 +428,13 @@ class TrainEngine:
             self._join_wgrad_stream()
             return n + 1
         da0 = self._buf("da0", self.a0.shape)
-        ops.maxpool3x3s2_bwd(d, self.a0, dx=da0, idx_ws=self.pool_idx)
+        if self.maxpool_idx:
+            ops.maxpool3x3s2_bwd_idx(d, self.pool_idx, self.a0.shape[1], self.a0.shape[2], dx=da0)
+        else:
+            ops.maxpool3x3s2_bwd(d, self.a0, dx=da0, idx_ws=self.pool_idx)
+            n += 1
         dy0 = self._dy_buf(st)
-        n += 2 + self._bn_bwd(st, da0, True, dy0)
+        n += 1 + self._bn_bwd(st, da0, True, dy0)
         self._on_wgrad_stream(lambda: ops.stem_wgrad(self.x, dy0, self._g(net.conv1.weight), ws=self.wgrad_ws))
         self._join_wgrad_stream()
         n += 2

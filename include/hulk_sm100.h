@@ -309,6 +309,13 @@ HK_API int hk_sigmoid_bwd(const float* heat, const float* grad_heat, float* grad
  * idx_ws: B*Ho*Wo*C bytes (the per-window argmax taps computed in a first pass). */
 HK_API int hk_maxpool3x3s2_bwd(const void* dout, const void* x, void* dx, int B, int H, int W, int C, int Ho, int Wo, void* idx_ws,
                                size_t idx_ws_bytes, void* stream);
+/* The training step's max-pool as forward-with-indices + gather: hk_maxpool3x3s2_fwd_idx writes y (B,Ho,Wo,C) bf16 AND idx (B*Ho*Wo*C bytes:
+ * the tap r*3+s of the first maximum of each window in scan order, ATen's max_pool2d_with_indices rule) in one pass over x;
+ * hk_maxpool3x3s2_bwd_idx routes dout through those indices (dx (B,H,W,C) bf16).  Same results as hk_maxpool3x3s2_fwd + hk_maxpool3x3s2_bwd,
+ * one pass over the stem map fewer. */
+HK_API int hk_maxpool3x3s2_fwd_idx(const void* x, void* y, void* idx, int B, int H, int W, int C, int Ho, int Wo, void* stream);
+HK_API int hk_maxpool3x3s2_bwd_idx(const void* dout, const void* idx, void* dx, int B, int H, int W, int C, int Ho, int Wo, void* stream);
+
 
 /* Head in training: K-row scoring conv + bilinear upsample WITHOUT the sigmoid (hk_bce_fwd_bwd takes logits), ATen's exact
  * operation order; and its backward: upsample-backward of g_up (B,K,H,W) to dlogits_ws (B,K,h,w), then

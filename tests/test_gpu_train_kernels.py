@@ -269,6 +269,10 @@ def test_maxpool_backward_matches_autograd_with_ties():
     # sums of up to 4 bf16 gradients are rounded to bf16 once
     assert torch.allclose(got, ref, atol=2e-2, rtol=1e-2)
     assert torch.equal(got != 0, bf(ref).float() != 0) or rel_err(got, ref) < 5e-3
+    # the training step's split form: forward with recorded indices (== the forward max-pool, bit for bit) + gather (== the call above)
+    y_idx, idx = ops.maxpool3x3s2_fwd_idx(x)
+    assert torch.equal(y_idx, ops.maxpool3x3s2(x))
+    assert torch.equal(ops.maxpool3x3s2_bwd_idx(dout, idx, H, W), dx)
 
 
 # ------------------------------------------------------------------ head (training): logits forward and backward
