@@ -39,6 +39,7 @@ constexpr int SP_PAIR_BYTES = 2 * SP_ROW_BYTES; // a ring slot holds an even/odd
 constexpr int SP_PAIRS = 8;
 constexpr int SP_RING_BYTES = SP_PAIRS * SP_PAIR_BYTES;      // 33792
 constexpr int SP_STAGES = 4;
+constexpr int SP_ACC = 2;                       // TMEM accumulators (64 columns each); 4 (the epilogue three rows behind the MMAs) measured no faster
 // TMA needs the box to START on a 16-byte boundary in global memory (an unaligned innermost coordinate raises an illegal-instruction
 // fault): the fp32 box starts 3 pixels left of ring pixel 0 (input column 252*strip - 8, a multiple of 4 floats), the uint8 box at the
 // 16-byte boundary below byte 3*(252*strip - 5); the converters skip the lead-in.
@@ -66,7 +67,8 @@ struct StemPoolArgs {
   int band_rows;     // stem rows per band (even)
   int nbands, nstrips, num_units;
 #ifdef HK_DIAG
-  int dbg_mode;   // HK_SP_DEBUG bit flags (diagnostics build): 1 = no TMA input loads, 2 = no MMAs, 4 = no epilogue TMEM loads
+  int dbg_mode;   // HK_SP_DEBUG bit flags (diagnostics build): 1 = no TMA input loads, 2 = no MMAs, 4 = no epilogue TMEM loads,
+                  // 8 = converters only pass their barriers on, 16 = epilogue stops after releasing the accumulator
 #endif
 };
 #ifdef HK_DIAG
@@ -130,10 +132,10 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   uint64_t* stage_empty = bars + 4;                 // [4]
   uint64_t* pair_full = bars + 8;                   // [8]
   uint64_t* pair_empty = bars + 16;                 // [8]
-  uint64_t* tmem_full = bars + 24;                  // [2]
-  uint64_t* tmem_empty = bars + 26;                 // [2]
-  uint64_t* w_bar = bars + 28;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 30);
+  uint64_t* tmem_full = bars + 24;                  // [SP_ACC]
+  uint64_t* tmem_empty = bars + 28;                 // [SP_ACC]
+  uint64_t* w_bar = bars + 32;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 34);
   float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
   float* s_bias = s_scale + 64;
 
@@ -151,7 +153,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       ptx::mbar_init(&pair_full[i], SP_CONV_THREADS);
       ptx::mbar_init(&pair_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < SP_ACC; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
       ptx::mbar_init(&tmem_empty[i], SP_EPI_THREADS);
     }
@@ -159,7 +161,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_ptr_smem, 128);
+    ptx::tmem_alloc(tmem_ptr_smem, SP_ACC * 64);
     ptx::tmem_relinquish();
   }
   if (tid >= 64 && tid < 128) {
@@ -218,7 +220,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       // pairs 0..2 of the unit must have landed before the first row; afterwards one new pair per row
       for (int j = 0; j < 3; ++j) ptx::mbar_wait(&pair_full[(n0 + j) & 7], ((n0 + j) >> 3) & 1, 43);
       for (int t = 0; t < un.rows; ++t, ++it) {
-        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        const uint32_t acc = it & (SP_ACC - 1), acc_phase = (it / SP_ACC) & 1;
         ptx::mbar_wait(&pair_full[(n0 + t + 3) & 7], ((n0 + t + 3) >> 3) & 1, 44);
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 45);
         ptx::tc_fence_after();
@@ -262,6 +264,11 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         ptx::mbar_wait(&pair_empty[slot], ((n >> 3) & 1) ^ 1, 47);
         const uint8_t* src = stages + st * SP_STAGE_BYTES;
         uint8_t* dst = ring + slot * SP_PAIR_BYTES;
+        if (SP_DBG(a) & 8) {
+          ptx::mbar_arrive(&pair_full[slot]);
+          ptx::mbar_arrive(&stage_empty[st]);
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < (2 * SP_PX + SP_CONV_THREADS - 1) / SP_CONV_THREADS; ++i) {
           const int p = ct + i * SP_CONV_THREADS;
@@ -297,9 +304,14 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int col = q * 32 + lane;             // column of the strip = TMEM lane
     const int et = tid - 256;
     const int c0 = half * 32;
-    float vmax[32];
+    // Pooling on the RAW accumulators: relu(scale*a + bias) is monotone in a (non-decreasing for scale >= 0, non-increasing for scale < 0)
+    // and so is the bf16 rounding, so the maximum over a pooling window of the activated values is the activation of the window's largest
+    // (smallest, for a negative scale) accumulator -- bit for bit.  The per-row work is two FMNMX per channel; affine + ReLU + bf16 pack and
+    // the scale/bias reads happen once per POOLED row.  (Applying them to every stem row cost ~350 instructions per thread and row and made
+    // this role the kernel's bound: 0.23 of its 0.31 ms, tools/diag_stem_pool_modes.py.)
+    float amax[32], amin[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) vmax[j] = 0.f;
+    for (int j = 0; j < 32; ++j) { amax[j] = -INFINITY; amin[j] = INFINITY; }
     uint32_t it = 0, emits = 0;
     for (int u = blockIdx.x; u < a.num_units; u += gridDim.x) {
       const SpUnit un = sp_unit(a, u);
@@ -307,7 +319,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const bool col_ok = stem_col >= 0 && stem_col < a.Wo;
       const int px0 = SP_POOL * un.strip;      // first pooled column of the strip
       for (int t = 0; t < un.rows; ++t, ++it) {
-        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        const uint32_t acc = it & (SP_ACC - 1), acc_phase = (it / SP_ACC) & 1;
         const int y = un.y_first + t;
         ptx::mbar_wait(&tmem_full[acc], acc_phase, 48);
         ptx::tc_fence_after();
@@ -321,36 +333,22 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tmem_empty[acc]);
-        float v[32];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 s4 = *reinterpret_cast<const float4*>(s_scale + c0 + g * 4);
-          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 4);
-          v[g * 4 + 0] = fmaxf(fmaf(__uint_as_float(r[g * 4 + 0]), s4.x, b4.x), 0.f);
-          v[g * 4 + 1] = fmaxf(fmaf(__uint_as_float(r[g * 4 + 1]), s4.y, b4.y), 0.f);
-          v[g * 4 + 2] = fmaxf(fmaf(__uint_as_float(r[g * 4 + 2]), s4.z, b4.z), 0.f);
-          v[g * 4 + 3] = fmaxf(fmaf(__uint_as_float(r[g * 4 + 3]), s4.w, b4.w), 0.f);
-        }
-        if (!col_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;   // outside the stem map: MaxPool's padding never wins (values are >= 0)
-        }
+        if (SP_DBG(a) & 16) continue;
         const bool carry_only = (t == 0 && un.y0 > 0);          // row y0-1: the first row of the band's first pooling window
         const bool emit = !carry_only && ((y & 1) || y == a.Ho - 1);
-        if (carry_only) {
+        if (carry_only || t == 0) {   // first row of a window sequence (band 0 has no row above)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) vmax[j] = v[j];
-          continue;
-        }
-        if (t == 0) {   // band 0: no row above
-#pragma unroll
-          for (int j = 0; j < 32; ++j) vmax[j] = v[j];
+          for (int j = 0; j < 32; ++j) { amax[j] = __uint_as_float(r[j]); amin[j] = __uint_as_float(r[j]); }
+          if (carry_only) continue;
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) vmax[j] = fmaxf(vmax[j], v[j]);
+          for (int j = 0; j < 32; ++j) {
+            amax[j] = fmaxf(amax[j], __uint_as_float(r[j]));
+            amin[j] = fminf(amin[j], __uint_as_float(r[j]));
+          }
         }
         if (!emit) continue;
-        // ---- pooled row py = y >> 1: vertical maxima -> swizzled smem row, horizontal 3-max, coalesced 16-byte stores ----
+        // ---- pooled row py = y >> 1: activation of the window extremes -> swizzled smem row, horizontal 3-max, coalesced 16-byte stores ----
         uint8_t* P = sP + (emits & 1) * SP_P_BYTES;
         ++emits;
         {
@@ -359,14 +357,30 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int cc = half * 4 + i;
+            float v[8];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const float4 s4 = *reinterpret_cast<const float4*>(s_scale + c0 + i * 8 + g * 4);
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + i * 8 + g * 4);
+              const float sc[4] = {s4.x, s4.y, s4.z, s4.w}, bi[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = i * 8 + g * 4 + e;
+                const float ext = sc[e] >= 0.f ? amax[j] : amin[j];
+                // outside the stem map: MaxPool's padding never wins (activated values are >= 0)
+                v[g * 4 + e] = col_ok ? fmaxf(fmaf(ext, sc[e], bi[e]), 0.f) : 0.f;
+              }
+            }
             *reinterpret_cast<uint4*>(my + ((cc ^ sw) << 4)) =
-                make_uint4(pack_bf16x2(vmax[i * 8 + 0], vmax[i * 8 + 1]), pack_bf16x2(vmax[i * 8 + 2], vmax[i * 8 + 3]),
-                           pack_bf16x2(vmax[i * 8 + 4], vmax[i * 8 + 5]), pack_bf16x2(vmax[i * 8 + 6], vmax[i * 8 + 7]));
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
           }
         }
         // the next window starts with this row when it is odd (row 2py+1 = row 2(py+1)-1)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) vmax[j] = (y & 1) ? v[j] : 0.f;
+        for (int j = 0; j < 32; ++j) {
+          amax[j] = (y & 1) ? __uint_as_float(r[j]) : -INFINITY;
+          amin[j] = (y & 1) ? __uint_as_float(r[j]) : INFINITY;
+        }
         ptx::named_bar_sync(1, SP_EPI_THREADS);
         const int py = y >> 1;
         __nv_bfloat16* out_row = a.y + ((size_t)(un.b * a.Hp + py) * a.Wp) * 64;
@@ -395,7 +409,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 128);
+    ptx::tmem_dealloc(tmem_base, SP_ACC * 64);
   }
 }
 
