@@ -290,13 +290,62 @@ constexpr int BN_ACC_MAX_C = 2048;
 // of them over DSMEM in rank order (fixed order: deterministic) and issues the atomics -- 1/8 of the atomic traffic of a per-CTA scheme
 // (at C = 512 and 592 blocks that was 1.2 M same-address L2 atomics per launch, ~8 us; now 74 clusters x 2 K).
 constexpr int BN_CLUSTER = 8;
-constexpr int BN_ACC_MAX_BLOCKS = 592;   // 74 clusters: four CTAs per SM, up to four 16-byte loads in flight per thread
+#ifndef BN_ACC_MAX_BLOCKS_V
+#define BN_ACC_MAX_BLOCKS_V 1184
+#endif
+constexpr int BN_ACC_MAX_BLOCKS = BN_ACC_MAX_BLOCKS_V;   // at most one resident wave of 8-CTA clusters (148 SMs x up to 8 blocks)
+
+// Tunables of the accumulator kernels (tools/diag_bn_kernels.py + tools/build_bn_variants.sh).  These kernels are pure streams:
+// their throughput is the bytes they keep in flight (resident threads x independent 16-byte loads per thread), not their arithmetic --
+// *_U = rows / vectors a thread has in flight, *_MINB = resident blocks per SM the register allocation is held to, *_CONTIG = 1: the
+// U pieces of a thread are neighbours (a block reads U contiguous 4 KB pieces of every operand per iteration), 0: one grid stride apart.
+#ifndef BN_STATS_U
+#define BN_STATS_U 4
+#endif
+#ifndef BN_BWDRED_U
+#define BN_BWDRED_U 2
+#endif
+#ifndef BN_RED_MINB
+#define BN_RED_MINB 4
+#endif
+#ifndef BN_RED_CONTIG
+#define BN_RED_CONTIG 1
+#endif
+#ifndef BN_APPLY_U
+#define BN_APPLY_U 4
+#endif
+#ifndef BN_APPLY_MINB
+#define BN_APPLY_MINB 3
+#endif
+#ifndef BN_APPLY_CONTIG
+#define BN_APPLY_CONTIG 1
+#endif
 
 // Shared-memory footprints are kept small on purpose (dynamic, sized by C): these kernels share the SMs with the weight-gradient
 // kernels of the second stream (one 198 KB CTA per SM), and a BatchNorm block that does not fit next to one simply waits for it.
+// Block sums of two per-thread 8-channel accumulators through ONE 8 KB buffer (a, then b): half the static shared memory of
+// block_reduce_2x8, so that more reduce blocks fit beside a weight-gradient CTA.  Same per-channel summation order (rows ascending).
+__device__ __forceinline__ void block_reduce_2x8_small(const float (&a)[8], const float (&b)[8], int C, float* __restrict__ s_tot) {
+  __shared__ float sh[BN_THREADS * 8];  // [rows][C] with rows*C = 256*8
+  const int CG = C >> 3, cg = threadIdx.x % CG, ty = threadIdx.x / CG, rows = BN_THREADS / CG;
+  float* s0 = sh + (ty * C + cg * 8);
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    if (which) __syncthreads();
+    *reinterpret_cast<float4*>(s0) = which ? make_float4(b[0], b[1], b[2], b[3]) : make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(s0 + 4) = which ? make_float4(b[4], b[5], b[6], b[7]) : make_float4(a[4], a[5], a[6], a[7]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+      float acc = 0.f;
+      for (int r = 0; r < rows; ++r) acc += sh[r * C + c];
+      s_tot[which * C + c] = acc;
+    }
+  }
+}
+
 __device__ __forceinline__ void bn_cluster_emit(const float (&a)[8], const float (&b)[8], int C, BnAcc* __restrict__ acc) {
   extern __shared__ float s_tot[];   // [2*C]
-  block_reduce_2x8_emit(a, b, C, [&](int c, float v) { s_tot[c] = v; });
+  block_reduce_2x8_small(a, b, C, s_tot);
   cg::cluster_group cluster = cg::this_cluster();
   cluster.sync();
   if (cluster.block_rank() == 0) {
@@ -310,33 +359,38 @@ __device__ __forceinline__ void bn_cluster_emit(const float (&a)[8], const float
   cluster.sync();   // the peers' shared memory stays alive until CTA 0 has read it
 }
 
-__global__ void __cluster_dims__(BN_CLUSTER, 1, 1) __launch_bounds__(BN_THREADS)
+__global__ void __cluster_dims__(BN_CLUSTER, 1, 1) __launch_bounds__(BN_THREADS, BN_RED_MINB)
 bn_stats_acc_kernel(const __nv_bfloat16* __restrict__ y, long long P, int C, BnAcc* __restrict__ acc) {
   const int CG = C >> 3, cg_ = threadIdx.x % CG, ty = threadIdx.x / CG, rows = BN_THREADS / CG;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const long long step = (long long)gridDim.x * rows;
-  long long r = (long long)blockIdx.x * rows + ty;
   const __nv_bfloat16* yp = y + cg_ * 8;
-  for (; r + 3 * step < P; r += 4 * step) {   // four independent 16-byte loads in flight per thread
-    Vec8 v[4];
+  const long long step = (long long)gridDim.x * rows;
+  const long long us = BN_RED_CONTIG ? rows : step, adv = BN_STATS_U * step;
+  for (long long r = (long long)blockIdx.x * (BN_RED_CONTIG ? BN_STATS_U * rows : rows) + ty; r < P; r += adv) {
+    if (r + (BN_STATS_U - 1) * us < P) {   // BN_STATS_U independent 16-byte loads in flight per thread
+      uint4 v[BN_STATS_U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = load8(yp + (r + u * step) * C);
+      for (int u = 0; u < BN_STATS_U; ++u) v[u] = *reinterpret_cast<const uint4*>(yp + (r + u * us) * C);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < BN_STATS_U; ++u) {
+        float f[8];
+        unpack_bf16x2(v[u].x, f[0], f[1]); unpack_bf16x2(v[u].y, f[2], f[3]); unpack_bf16x2(v[u].z, f[4], f[5]); unpack_bf16x2(v[u].w, f[6], f[7]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] += v[u].v[j]; q[j] = fmaf(v[u].v[j], v[u].v[j], q[j]); }
+        for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+      }
+    } else {
+      for (int u = 0; u < BN_STATS_U && r + u * us < P; ++u) {
+        const Vec8 v = load8(yp + (r + u * us) * C);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += v.v[j]; q[j] = fmaf(v.v[j], v.v[j], q[j]); }
+      }
     }
-  }
-  for (; r < P; r += step) {
-    const Vec8 v = load8(yp + r * C);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s[j] += v.v[j]; q[j] = fmaf(v.v[j], v.v[j], q[j]); }
   }
   bn_cluster_emit(s, q, C, acc);
 }
 
 // out = relu?(gamma*xhat + beta [+ residual]) with the batch statistics taken from the accumulators (sum y, sum y^2)
-__global__ void __launch_bounds__(BN_THREADS) bn_apply_fwd_acc_kernel(const __nv_bfloat16* __restrict__ y, const BnAcc* __restrict__ acc, long long P,
+__global__ void __launch_bounds__(BN_THREADS, BN_APPLY_MINB) bn_apply_fwd_acc_kernel(const __nv_bfloat16* __restrict__ y, const BnAcc* __restrict__ acc, long long P,
                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                      float* __restrict__ running_mean, float* __restrict__ running_var,
                                                                      float momentum, float eps, float* __restrict__ mean_out,
@@ -366,19 +420,21 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_fwd_acc_kernel(const __nv
     }
   }
   __syncthreads();
+  // the channel group of a thread is the same for every vector it touches: the grid stride is a multiple of 256, 256 of C/8
   const int cg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % (C >> 3));
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = s_sc[cg * 8 + j]; sh[j] = s_sh[cg * 8 + j]; }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    const Vec8 v = load8(y + i * 8);
-    float o[8];
+  auto finish = [&](long long i, const uint4& yu, const uint4& ru) {
+    float v[8], o[8];
+    unpack_bf16x2(yu.x, v[0], v[1]); unpack_bf16x2(yu.y, v[2], v[3]); unpack_bf16x2(yu.z, v[4], v[5]); unpack_bf16x2(yu.w, v[6], v[7]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(v.v[j], sc[j], sh[j]);
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], sc[j], sh[j]);
     if (residual) {
-      const Vec8 r = load8(residual + i * 8);
+      float r[8];
+      unpack_bf16x2(ru.x, r[0], r[1]); unpack_bf16x2(ru.y, r[2], r[3]); unpack_bf16x2(ru.z, r[4], r[5]); unpack_bf16x2(ru.w, r[6], r[7]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += r.v[j];
+      for (int j = 0; j < 8; ++j) o[j] += r[j];
     }
     if (relu) {
       if (relu_bits) {
@@ -391,71 +447,104 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_fwd_acc_kernel(const __nv
       for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
     }
     store8(out + i * 8, o);
+  };
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long us = BN_APPLY_CONTIG ? BN_THREADS : stride, adv = BN_APPLY_U * stride;
+  for (long long i = (long long)blockIdx.x * (BN_APPLY_CONTIG ? BN_APPLY_U * BN_THREADS : BN_THREADS) + threadIdx.x; i < nvec; i += adv) {
+    if (i + (BN_APPLY_U - 1) * us < nvec) {   // BN_APPLY_U vectors (x 1-2 loads) in flight per thread
+      uint4 yu[BN_APPLY_U], ru[BN_APPLY_U];
+#pragma unroll
+      for (int u = 0; u < BN_APPLY_U; ++u) {
+        yu[u] = *reinterpret_cast<const uint4*>(y + (i + u * us) * 8);
+        ru[u] = residual ? *reinterpret_cast<const uint4*>(residual + (i + u * us) * 8) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < BN_APPLY_U; ++u) finish(i + u * us, yu[u], ru[u]);
+    } else {
+      for (int u = 0; u < BN_APPLY_U && i + u * us < nvec; ++u) {
+        const uint4 yu = *reinterpret_cast<const uint4*>(y + (i + u * us) * 8);
+        const uint4 ru = residual ? *reinterpret_cast<const uint4*>(residual + (i + u * us) * 8) : make_uint4(0, 0, 0, 0);
+        finish(i + u * us, yu, ru);
+      }
+    }
   }
 }
 
+// sum d' and sum d'*xhat per channel (d' = dout masked by the ReLU that followed the BatchNorm).  The loop accumulates the RAW moment
+// sum d'*y; xhat = (y - mean)*invstd is applied to the thread's two sums once, after the loop (sum d'*xhat = invstd*(sum d'*y - mean*sum d')
+// over the <= 64 rows a thread owns): 16 fewer live registers and two fewer operations per element than normalising every element.
 template <bool BITS>
-__global__ void __cluster_dims__(BN_CLUSTER, 1, 1) __launch_bounds__(BN_THREADS)
+__global__ void __cluster_dims__(BN_CLUSTER, 1, 1) __launch_bounds__(BN_THREADS, BN_RED_MINB)
 bn_bwd_acc_kernel(const __nv_bfloat16* __restrict__ dout, const void* __restrict__ out_mask, const __nv_bfloat16* __restrict__ y,
                   const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C, BnAcc* __restrict__ acc) {
   const int CG = C >> 3, cg_ = threadIdx.x % CG, ty = threadIdx.x / CG, rows = BN_THREADS / CG;
-  float mu[8], is[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { mu[j] = mean[cg_ * 8 + j]; is[j] = invstd[cg_ * 8 + j]; }
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long step = (long long)gridDim.x * rows;
-  auto accumulate = [&](Vec8 d, const Vec8& v, uint32_t m, const Vec8& mv) {
+  const uint8_t* mbits = static_cast<const uint8_t*>(out_mask);
+  const __nv_bfloat16* mvals = static_cast<const __nv_bfloat16*>(out_mask);
+  auto accumulate = [&](const uint4& du, const uint4& vu, uint32_t m, const uint4& mu4) {
+    float d[8], v[8];
+    unpack_bf16x2(du.x, d[0], d[1]); unpack_bf16x2(du.y, d[2], d[3]); unpack_bf16x2(du.z, d[4], d[5]); unpack_bf16x2(du.w, d[6], d[7]);
+    unpack_bf16x2(vu.x, v[0], v[1]); unpack_bf16x2(vu.y, v[2], v[3]); unpack_bf16x2(vu.z, v[4], v[5]); unpack_bf16x2(vu.w, v[6], v[7]);
     if (out_mask) {
       if constexpr (BITS) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d.v[j] = (m >> j) & 1u ? d.v[j] : 0.f;
+        for (int j = 0; j < 8; ++j) d[j] = (m >> j) & 1u ? d[j] : 0.f;
       } else {
+        float mv[8];
+        unpack_bf16x2(mu4.x, mv[0], mv[1]); unpack_bf16x2(mu4.y, mv[2], mv[3]); unpack_bf16x2(mu4.z, mv[4], mv[5]); unpack_bf16x2(mu4.w, mv[6], mv[7]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d.v[j] = mv.v[j] > 0.f ? d.v[j] : 0.f;
+        for (int j = 0; j < 8; ++j) d[j] = mv[j] > 0.f ? d[j] : 0.f;
       }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      s1[j] += d.v[j];
-      s2[j] = fmaf(d.v[j], (v.v[j] - mu[j]) * is[j], s2[j]);
+      s1[j] += d[j];
+      s2[j] = fmaf(d[j], v[j], s2[j]);
     }
   };
-  long long r = (long long)blockIdx.x * rows + ty;
-  for (; r + step < P; r += 2 * step) {   // two rows = four to six independent 16-byte loads in flight per thread
-    const long long o0 = r * C + cg_ * 8, o1 = (r + step) * C + cg_ * 8;
-    const Vec8 d0 = load8(dout + o0), d1 = load8(dout + o1);
-    const Vec8 v0 = load8(y + o0), v1 = load8(y + o1);
-    uint32_t m0 = 0, m1 = 0;
-    Vec8 mv0 = {}, mv1 = {};
-    if (out_mask) {
-      if constexpr (BITS) {
-        m0 = static_cast<const uint8_t*>(out_mask)[o0 >> 3];
-        m1 = static_cast<const uint8_t*>(out_mask)[o1 >> 3];
-      } else {
-        mv0 = load8(static_cast<const __nv_bfloat16*>(out_mask) + o0);
-        mv1 = load8(static_cast<const __nv_bfloat16*>(out_mask) + o1);
+  const long long col = cg_ * 8;
+  const long long us = BN_RED_CONTIG ? rows : step, adv = BN_BWDRED_U * step;
+  for (long long r = (long long)blockIdx.x * (BN_RED_CONTIG ? BN_BWDRED_U * rows : rows) + ty; r < P; r += adv) {
+    if (r + (BN_BWDRED_U - 1) * us < P) {   // BN_BWDRED_U rows = 2-3 independent loads each, all issued before the first use
+      uint4 du[BN_BWDRED_U], vu[BN_BWDRED_U], mu4[BN_BWDRED_U];
+      uint32_t m[BN_BWDRED_U];
+#pragma unroll
+      for (int u = 0; u < BN_BWDRED_U; ++u) {
+        const long long o = (r + u * us) * C + col;
+        du[u] = *reinterpret_cast<const uint4*>(dout + o);
+        vu[u] = *reinterpret_cast<const uint4*>(y + o);
+        m[u] = 0;
+        mu4[u] = make_uint4(0, 0, 0, 0);
+        if (out_mask) {
+          if constexpr (BITS) m[u] = mbits[o >> 3];
+          else mu4[u] = *reinterpret_cast<const uint4*>(mvals + o);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < BN_BWDRED_U; ++u) accumulate(du[u], vu[u], m[u], mu4[u]);
+    } else {
+      for (int u = 0; u < BN_BWDRED_U && r + u * us < P; ++u) {
+        const long long o = (r + u * us) * C + col;
+        const uint4 du = *reinterpret_cast<const uint4*>(dout + o);
+        const uint4 vu = *reinterpret_cast<const uint4*>(y + o);
+        uint32_t m = 0;
+        uint4 mu4 = make_uint4(0, 0, 0, 0);
+        if (out_mask) {
+          if constexpr (BITS) m = mbits[o >> 3];
+          else mu4 = *reinterpret_cast<const uint4*>(mvals + o);
+        }
+        accumulate(du, vu, m, mu4);
       }
     }
-    accumulate(d0, v0, m0, mv0);
-    accumulate(d1, v1, m1, mv1);
   }
-  for (; r < P; r += step) {
-    const long long off = r * C + cg_ * 8;
-    const Vec8 d = load8(dout + off);
-    const Vec8 v = load8(y + off);
-    uint32_t m = 0;
-    Vec8 mv = {};
-    if (out_mask) {
-      if constexpr (BITS) m = static_cast<const uint8_t*>(out_mask)[off >> 3];
-      else mv = load8(static_cast<const __nv_bfloat16*>(out_mask) + off);
-    }
-    accumulate(d, v, m, mv);
-  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s2[j] = invstd[col + j] * fmaf(-mean[col + j], s1[j], s2[j]);
   bn_cluster_emit(s1, s2, C, acc);
 }
 
 template <bool BITS>
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_acc_kernel(const __nv_bfloat16* __restrict__ dout, const void* __restrict__ out_mask,
+__global__ void __launch_bounds__(BN_THREADS, BN_APPLY_MINB) bn_bwd_apply_acc_kernel(const __nv_bfloat16* __restrict__ dout, const void* __restrict__ out_mask,
                                                                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                                                                      const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                                      const BnAcc* __restrict__ acc, long long P, float* __restrict__ dgamma,
@@ -477,29 +566,74 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_acc_kernel(const __nv
     }
   }
   __syncthreads();
+  // The channel group of a thread is the same for every vector it touches (the grid stride is a multiple of 256, 256 of C/8).  Its 24
+  // coefficients stay in shared memory and are re-read (six 16-byte loads) once per batch of BN_APPLY_U vectors: held in registers they
+  // cost 24 of the registers that decide how many blocks are resident, and this kernel's throughput is the bytes it keeps in flight.
   const int c0 = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % (C >> 3)) * 8;
-  float k0[8], k1[8], k2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { k0[j] = s_k[0][c0 + j]; k1[j] = s_k[1][c0 + j]; k2[j] = s_k[2][c0 + j]; }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    Vec8 d = load8(dout + i * 8);
-    const Vec8 v = load8(y + i * 8);
+  const float4* kk0 = reinterpret_cast<const float4*>(s_k[0] + c0);
+  const float4* kk1 = reinterpret_cast<const float4*>(s_k[1] + c0);
+  const float4* kk2 = reinterpret_cast<const float4*>(s_k[2] + c0);
+  const uint8_t* mbits = static_cast<const uint8_t*>(out_mask);
+  const __nv_bfloat16* mvals = static_cast<const __nv_bfloat16*>(out_mask);
+  auto finish = [&](long long i, const uint4& du, const uint4& vu, uint32_t m, const uint4& mu4) {
+    float d[8], v[8];
+    unpack_bf16x2(du.x, d[0], d[1]); unpack_bf16x2(du.y, d[2], d[3]); unpack_bf16x2(du.z, d[4], d[5]); unpack_bf16x2(du.w, d[6], d[7]);
+    unpack_bf16x2(vu.x, v[0], v[1]); unpack_bf16x2(vu.y, v[2], v[3]); unpack_bf16x2(vu.z, v[4], v[5]); unpack_bf16x2(vu.w, v[6], v[7]);
     if (out_mask) {
       if constexpr (BITS) {
-        const uint32_t m = static_cast<const uint8_t*>(out_mask)[i];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d.v[j] = (m >> j) & 1u ? d.v[j] : 0.f;
+        for (int j = 0; j < 8; ++j) d[j] = (m >> j) & 1u ? d[j] : 0.f;
       } else {
-        const Vec8 m = load8(static_cast<const __nv_bfloat16*>(out_mask) + i * 8);
+        float mv[8];
+        unpack_bf16x2(mu4.x, mv[0], mv[1]); unpack_bf16x2(mu4.y, mv[2], mv[3]); unpack_bf16x2(mu4.z, mv[4], mv[5]); unpack_bf16x2(mu4.w, mv[6], mv[7]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d.v[j] = m.v[j] > 0.f ? d.v[j] : 0.f;
+        for (int j = 0; j < 8; ++j) d[j] = mv[j] > 0.f ? d[j] : 0.f;
       }
     }
-    if (dmasked) store8(dmasked + i * 8, d.v);
+    if (dmasked) store8(dmasked + i * 8, d);
+    const float4 a0 = kk0[0], a1 = kk0[1], b0 = kk1[0], b1 = kk1[1], g0 = kk2[0], g1 = kk2[1];
+    const float k0[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float k1[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float k2[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(k0[j], d.v[j], fmaf(k1[j], v.v[j], k2[j]));
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(k0[j], d[j], fmaf(k1[j], v[j], k2[j]));
     store8(dy + i * 8, o);
+  };
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long us = BN_APPLY_CONTIG ? BN_THREADS : stride, adv = BN_APPLY_U * stride;
+  for (long long i = (long long)blockIdx.x * (BN_APPLY_CONTIG ? BN_APPLY_U * BN_THREADS : BN_THREADS) + threadIdx.x; i < nvec; i += adv) {
+    if (i + (BN_APPLY_U - 1) * us < nvec) {
+      uint4 du[BN_APPLY_U], vu[BN_APPLY_U], mu4[BN_APPLY_U];
+      uint32_t m[BN_APPLY_U];
+#pragma unroll
+      for (int u = 0; u < BN_APPLY_U; ++u) {
+        const long long iu = i + u * us;
+        du[u] = *reinterpret_cast<const uint4*>(dout + iu * 8);
+        vu[u] = *reinterpret_cast<const uint4*>(y + iu * 8);
+        m[u] = 0;
+        mu4[u] = make_uint4(0, 0, 0, 0);
+        if (out_mask) {
+          if constexpr (BITS) m[u] = mbits[iu];
+          else mu4[u] = *reinterpret_cast<const uint4*>(mvals + iu * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < BN_APPLY_U; ++u) finish(i + u * us, du[u], vu[u], m[u], mu4[u]);
+    } else {
+      for (int u = 0; u < BN_APPLY_U && i + u * us < nvec; ++u) {
+        const long long iu = i + u * us;
+        const uint4 du = *reinterpret_cast<const uint4*>(dout + iu * 8);
+        const uint4 vu = *reinterpret_cast<const uint4*>(y + iu * 8);
+        uint32_t m = 0;
+        uint4 mu4 = make_uint4(0, 0, 0, 0);
+        if (out_mask) {
+          if constexpr (BITS) m = mbits[iu];
+          else mu4 = *reinterpret_cast<const uint4*>(mvals + iu * 8);
+        }
+        finish(iu, du, vu, m, mu4);
+      }
+    }
   }
 }
 
@@ -516,25 +650,58 @@ static int bn_grid_elems(long long nvec) {
   if (blocks > cap) blocks = cap;
   return (int)blocks;
 }
-// a whole number of 8-CTA clusters, at most one resident wave (and at most BN_ACC_MAX_BLOCKS CTAs)
-template <int TAG, class K>   // TAG: one cached occupancy per kernel instantiation (instantiations may share a function type)
-static int bn_grid_acc_rows(K kernel, long long P, int C, size_t smem) {
-  static int resident = 0;
+// Grid of the reduce kernels: a whole number of 8-CTA clusters, at most ONE resident wave.  "Resident" is asked of
+// cudaOccupancyMaxActiveClusters, not derived from blocks per SM x SMs: a cluster lives inside one GPC, so a grid that fills every
+// block slot of the GPU only fits if every GPC's slot count is a multiple of 8 -- otherwise the last clusters wait for a second wave and
+// the kernel takes up to twice as long (measured: the 592-block grid at exactly 4 blocks per SM ran 25 % slower than the same grid with
+// a fifth slot free).  One wave less one cluster per GPC's worth of slack keeps every cluster co-resident.
+template <int TAG, class K>   // TAG: one cached answer per kernel instantiation and channel count (instantiations may share a function type)
+static int bn_grid_acc_rows(K kernel, long long P, int C, size_t smem, int U) {
+  static int resident_by_c[12] = {0};   // index: log2(C)
+  int lg = 0;
+  while ((1 << lg) < C && lg < 11) ++lg;
+  int& resident = resident_by_c[lg];
   if (resident == 0) {
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BN_THREADS, smem) != cudaSuccess || occ < 1) occ = 2;
-    resident = occ * sm_count() / BN_CLUSTER * BN_CLUSTER;
+    int clusters = 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(BN_CLUSTER * (unsigned)sm_count(), 1, 1);
+    cfg.blockDim = dim3(BN_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = BN_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg) == cudaSuccess && clusters > 0) {
+      resident = clusters * BN_CLUSTER;
+    } else {
+      (void)cudaGetLastError();
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BN_THREADS, smem) != cudaSuccess || occ < 1) occ = 2;
+      resident = (occ * sm_count() / BN_CLUSTER - 8) * BN_CLUSTER;   // one cluster of slack per GPC
+    }
     if (resident > BN_ACC_MAX_BLOCKS) resident = BN_ACC_MAX_BLOCKS;
+    if (resident < BN_CLUSTER) resident = BN_CLUSTER;
   }
+  // equal shares: chunks of U x rows rows (U = the rows a thread has in flight), at least four per block, the same number (+-1) for every block
   const int rows = BN_THREADS / (C >> 3);
-  long long blocks = ceil_div_ll(P, (long long)rows * 16);
+  const long long chunks = ceil_div_ll(P, (long long)rows * U);
+  long long gmax = ceil_div_ll(chunks, 4);
+  if (gmax > resident) gmax = resident;
+  const long long iters = ceil_div_ll(chunks, gmax);
+  long long blocks = ceil_div_ll(ceil_div_ll(chunks, iters), BN_CLUSTER) * BN_CLUSTER;
   if (blocks > resident) blocks = resident;
-  blocks = ceil_div_ll(blocks, BN_CLUSTER) * BN_CLUSTER;
   return (int)blocks;
 }
-// Grid of the accumulator apply kernels.  Every block pays the coefficient prologue, so few fat blocks; and a grid-stride loop over equal
-// shares finishes in whole waves only if the grid is a multiple of what is resident at once (a 1184-block grid at 5 resident blocks per
-// SM ran a full wave plus a 3/5 one: 1.4x the time of the 16-blocks-per-SM grid it replaced).
+// Grid of the accumulator apply kernels.  Every block pays the coefficient prologue, so few fat blocks.  The work is split into chunks of
+// BN_APPLY_U x 256 vectors; the grid is the smallest one that gives every block the same number of chunks (+-1) within BN_APPLY_WAVES
+// resident waves -- a grid-stride loop over unequal shares waits for its slowest block (a 1184-block grid at 5 resident blocks per SM ran
+// a full wave plus a 3/5 one: 1.4x the time of the 16-blocks-per-SM grid it replaced).
+#ifndef BN_APPLY_WAVES
+#define BN_APPLY_WAVES 1
+#endif
 template <int TAG, class K>
 static int bn_grid_apply(K kernel, long long nvec, size_t smem) {
   static int resident = 0;   // per kernel instantiation
@@ -543,8 +710,10 @@ static int bn_grid_apply(K kernel, long long nvec, size_t smem) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BN_THREADS, smem) != cudaSuccess || occ < 1) occ = 4;
     resident = occ * sm_count();
   }
-  long long blocks = ceil_div_ll(nvec, (long long)BN_THREADS * 4);   // >= 4 vectors per thread
-  if (blocks >= resident) blocks = (blocks >= 2LL * resident) ? 2LL * resident : resident;
+  const long long chunks = ceil_div_ll(nvec, (long long)BN_THREADS * BN_APPLY_U);
+  const long long gmax = (long long)BN_APPLY_WAVES * resident;
+  const long long iters = ceil_div_ll(chunks, gmax);
+  long long blocks = ceil_div_ll(chunks, iters);
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
@@ -623,7 +792,7 @@ int hk_bn_stats_acc(const void* y, long long P, int C, void* acc, void* stream) 
   HK_REQUIRE(y && acc, "hk_bn_stats_acc: null pointer");
   HK_REQUIRE(P > 0 && bn_c_ok(C), "hk_bn_stats_acc: unsupported shape P=%lld C=%d (C must be a power-of-two multiple of 8 up to 2048)", P, C);
   HK_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(acc) & 31) == 0, "hk_bn_stats_acc: misaligned buffer");
-  bn_stats_acc_kernel<<<bn_grid_acc_rows<0>(bn_stats_acc_kernel, P, C, 2 * (size_t)C * 4), BN_THREADS, 2 * (size_t)C * 4, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y), P, C, static_cast<BnAcc*>(acc));
+  bn_stats_acc_kernel<<<bn_grid_acc_rows<0>(bn_stats_acc_kernel, P, C, 2 * (size_t)C * 4, BN_STATS_U), BN_THREADS, 2 * (size_t)C * 4, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y), P, C, static_cast<BnAcc*>(acc));
   return check_launch("bn_stats_acc_kernel");
 }
 
@@ -651,7 +820,7 @@ int hk_bn_bwd_acc(const void* dout, const void* out_mask_or_null, int mask_is_bi
   const __nv_bfloat16* d = static_cast<const __nv_bfloat16*>(dout);
   const __nv_bfloat16* yy = static_cast<const __nv_bfloat16*>(y);
   BnAcc* a = static_cast<BnAcc*>(acc);
-  const int blocks = mask_is_bits ? bn_grid_acc_rows<1>(bn_bwd_acc_kernel<true>, P, C, 2 * (size_t)C * 4) : bn_grid_acc_rows<2>(bn_bwd_acc_kernel<false>, P, C, 2 * (size_t)C * 4);
+  const int blocks = mask_is_bits ? bn_grid_acc_rows<1>(bn_bwd_acc_kernel<true>, P, C, 2 * (size_t)C * 4, BN_BWDRED_U) : bn_grid_acc_rows<2>(bn_bwd_acc_kernel<false>, P, C, 2 * (size_t)C * 4, BN_BWDRED_U);
   if (mask_is_bits) bn_bwd_acc_kernel<true><<<blocks, BN_THREADS, 2 * (size_t)C * 4, as_stream(stream)>>>(d, out_mask_or_null, yy, mean, invstd, P, C, a);
   else bn_bwd_acc_kernel<false><<<blocks, BN_THREADS, 2 * (size_t)C * 4, as_stream(stream)>>>(d, out_mask_or_null, yy, mean, invstd, P, C, a);
   int rc = check_launch("bn_bwd_acc_kernel");

@@ -65,39 +65,63 @@ __global__ void __launch_bounds__(256) maxpool_argmax_kernel(const __nv_bfloat16
     if (ymax) st8(ymax + i * 8, best);
   }
 }
+// One thread per 2x2 block of input pixels (rows 2a, 2a+1; columns 2q, 2q+1) and 8 channels: the four pixels lie in the same four windows
+// (oy in {a, a+1}, ox in {q, q+1}), so one index word and one gradient vector per window serve nine (pixel, window) pairs -- 1 window
+// read per pixel instead of 2.25 in the one-thread-per-pixel form -- and every pixel's sum still runs over its windows in (oy, ox) order.
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ idx,
                                                          __nv_bfloat16* __restrict__ dx, int B, int H, int W, int C, int Ho, int Wo) {
-  const int CG = C >> 3;
-  const long long total = (long long)B * H * W * CG;
+  const int CG = C >> 3, Hq = (H + 1) >> 1, Wq = (W + 1) >> 1;
+  const long long total = (long long)B * Hq * Wq * CG;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(i % CG);
     long long p = i / CG;
-    const int ix = (int)(p % W);
-    p /= W;
-    const int iy = (int)(p % H);
-    const int b = (int)(p / H);
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int oy_lo = max(0, iy / 2), oy_hi = min(Ho - 1, (iy + 1) / 2);   // windows with 2*oy-1 <= iy <= 2*oy+1
-    const int ox_lo = max(0, ix / 2), ox_hi = min(Wo - 1, (ix + 1) / 2);
-    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-        const long long o = (((long long)b * Ho + oy) * Wo + ox) * C + cg * 8;
-        const uint2 w8 = __ldg(reinterpret_cast<const uint2*>(idx + o));
-        const uint32_t me = (uint32_t)((iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1)));
-        const uint32_t me4 = me * 0x01010101u;
-        const uint32_t e0 = w8.x ^ me4, e1 = w8.y ^ me4;   // a zero byte = this window routes its gradient here
-        if (((e0 - 0x01010101u) & ~e0 & 0x80808080u) | ((e1 - 0x01010101u) & ~e1 & 0x80808080u)) {
-          float g[8];
-          ld8(dout + o, g);
+    const int q = (int)(p % Wq);
+    p /= Wq;
+    const int a = (int)(p % Hq);
+    const int b = (int)(p / Hq);
+    // window (a + wy, q + wx), wy, wx in {0, 1}
+    uint2 w8[2][2];
+    uint4 g4[2][2];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (((e0 >> (8 * j)) & 0xffu) == 0) acc[j] += g[j];
-            if (((e1 >> (8 * j)) & 0xffu) == 0) acc[4 + j] += g[4 + j];
-          }
-        }
+    for (int wy = 0; wy < 2; ++wy) {
+#pragma unroll
+      for (int wx = 0; wx < 2; ++wx) {
+        const bool live = a + wy < Ho && q + wx < Wo;
+        const long long o = (((long long)b * Ho + (a + wy)) * Wo + (q + wx)) * C + cg * 8;
+        w8[wy][wx] = live ? __ldg(reinterpret_cast<const uint2*>(idx + o)) : make_uint2(0xffffffffu, 0xffffffffu);   // tap 255: nobody's
+        g4[wy][wx] = live ? __ldg(reinterpret_cast<const uint4*>(dout + o)) : make_uint4(0, 0, 0, 0);
       }
     }
-    st8(dx + i * 8, acc);
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+      const int iy = 2 * a + py;
+      if (iy >= H) continue;
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const int ix = 2 * q + px;
+        if (ix >= W) continue;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        // an even row / column lies in one window row / column only (its centre), an odd one in two
+#pragma unroll
+        for (int wy = 0; wy <= py; ++wy) {
+#pragma unroll
+          for (int wx = 0; wx <= px; ++wx) {
+            const uint32_t me = (uint32_t)((py + 1 - 2 * wy) * 3 + (px + 1 - 2 * wx));   // iy - (2*oy - 1), ix - (2*ox - 1)
+            const uint32_t me4 = me * 0x01010101u;
+            const uint32_t e0 = w8[wy][wx].x ^ me4, e1 = w8[wy][wx].y ^ me4;   // a zero byte = this window routes its gradient here
+            float g[8];
+            unpack_bf16x2(g4[wy][wx].x, g[0], g[1]); unpack_bf16x2(g4[wy][wx].y, g[2], g[3]);
+            unpack_bf16x2(g4[wy][wx].z, g[4], g[5]); unpack_bf16x2(g4[wy][wx].w, g[6], g[7]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (((e0 >> (8 * j)) & 0xffu) == 0) acc[j] += g[j];
+              if (((e1 >> (8 * j)) & 0xffu) == 0) acc[4 + j] += g[4 + j];
+            }
+          }
+        }
+        st8(dx + ((((long long)b * H + iy) * W + ix) * CG + cg) * 8, acc);
+      }
+    }
   }
 }
 
@@ -352,7 +376,7 @@ int hk_maxpool3x3s2_bwd(const void* dout, const void* x, void* dx, int B, int H,
       static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(idx_ws), B, H, W, C, Ho, Wo);
   int rc = check_launch("maxpool_argmax_kernel");
   if (rc) return rc;
-  const long long total = (long long)B * H * W * (C >> 3);
+  const long long total = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C >> 3);
   maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dout),
                                                                          static_cast<const uint8_t*>(idx_ws),
                                                                          static_cast<__nv_bfloat16*>(dx), B, H, W, C, Ho, Wo);
@@ -376,7 +400,7 @@ int hk_maxpool3x3s2_bwd_idx(const void* dout, const void* idx, void* dx, int B, 
   HK_REQUIRE(dout && idx && dx, "hk_maxpool3x3s2_bwd_idx: null pointer");
   HK_REQUIRE(B > 0 && H > 0 && W > 0 && C >= 8 && (C & 7) == 0 && Ho == (H + 2 - 3) / 2 + 1 && Wo == (W + 2 - 3) / 2 + 1,
              "hk_maxpool3x3s2_bwd_idx: bad shape");
-  const long long total = (long long)B * H * W * (C >> 3);
+  const long long total = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C >> 3);
   maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dout), static_cast<const uint8_t*>(idx),
                                                                          static_cast<__nv_bfloat16*>(dx), B, H, W, C, Ho, Wo);
   return check_launch("maxpool_bwd_kernel");
