@@ -320,6 +320,12 @@ constexpr int BN_ACC_MAX_BLOCKS = BN_ACC_MAX_BLOCKS_V;   // at most one resident
 #ifndef BN_APPLY_CONTIG
 #define BN_APPLY_CONTIG 1
 #endif
+// least chunks (U rows x 256/(C/8) rows) per reduce block.  Small-batch launches want MANY blocks: fatter blocks (8 / 16 / 32 chunks, and
+// likewise 4 / 8 / 16 per apply block) made the batch-4 train step 3 % / 12 % / 31 % slower -- parallelism beats the per-block emit /
+// coefficient prologue
+#ifndef BN_RED_MIN_CHUNKS
+#define BN_RED_MIN_CHUNKS 4
+#endif
 
 // Shared-memory footprints are kept small on purpose (dynamic, sized by C): these kernels share the SMs with the weight-gradient
 // kernels of the second stream (one 198 KB CTA per SM), and a BatchNorm block that does not fit next to one simply waits for it.
@@ -688,7 +694,7 @@ static int bn_grid_acc_rows(K kernel, long long P, int C, size_t smem, int U) {
   // equal shares: chunks of U x rows rows (U = the rows a thread has in flight), at least four per block, the same number (+-1) for every block
   const int rows = BN_THREADS / (C >> 3);
   const long long chunks = ceil_div_ll(P, (long long)rows * U);
-  long long gmax = ceil_div_ll(chunks, 4);
+  long long gmax = ceil_div_ll(chunks, BN_RED_MIN_CHUNKS);
   if (gmax > resident) gmax = resident;
   const long long iters = ceil_div_ll(chunks, gmax);
   long long blocks = ceil_div_ll(ceil_div_ll(chunks, iters), BN_CLUSTER) * BN_CLUSTER;

@@ -14,14 +14,12 @@ build() {  # name, source, flags...
   nvcc -shared -o tools/bin/libhulk_bn$name.so /tmp/train_bn_$name.o $OTHERS -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -lcudart
   echo built tools/bin/libhulk_bn$name.so
 }
-git show HEAD:hulk_keypoints_b200/csrc/train_bn.cu > /tmp/train_bn_prev.cu
-build prev /tmp/train_bn_prev.cu &
 S=hulk_keypoints_b200/csrc/train_bn.cu
-build a $S -DBN_APPLY_U=4 -DBN_APPLY_MINB=3 -DBN_APPLY_CONTIG=1 &
-build b $S -DBN_APPLY_U=4 -DBN_APPLY_MINB=3 -DBN_APPLY_CONTIG=0 &
-build c $S -DBN_APPLY_U=2 -DBN_APPLY_MINB=4 -DBN_APPLY_CONTIG=0 &
+build m0 $S &
+build r1 $S -DBN_RED_MIN_CHUNKS=1 &
+build r2 $S -DBN_RED_MIN_CHUNKS=2 &
+build w2 $S -DBN_APPLY_WAVES=2 &
 wait
-build d $S -DBN_APPLY_U=8 -DBN_APPLY_MINB=2 -DBN_APPLY_CONTIG=1 &
-build e $S -DBN_APPLY_U=4 -DBN_APPLY_MINB=4 -DBN_APPLY_CONTIG=1 &
-build f $S -DBN_APPLY_U=3 -DBN_APPLY_MINB=3 -DBN_APPLY_CONTIG=0 -DBN_BWDRED_U=3 &
+build r1w2 $S -DBN_RED_MIN_CHUNKS=1 -DBN_APPLY_WAVES=2 &
+build u2 $S -DBN_RED_MIN_CHUNKS=2 -DBN_APPLY_U=2 -DBN_APPLY_MINB=4 -DBN_APPLY_CONTIG=0 &
 wait
