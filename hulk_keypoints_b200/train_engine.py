@@ -100,6 +100,9 @@ class TrainEngine:
         # ... and the forward statistics gathered in the conv epilogues (hk_conv_bn_stats_fwd): 36 launches and one read of every raw conv
         # output fewer.  HK_CONV_STATS=0: stand-alone hk_bn_stats_acc.
         self.fuse_conv_stats = os.environ.get("HK_CONV_STATS", "1") != "0"
+        # HK_CONV_STATS=all: every conv with a specialised tcgen05 kernel gathers its statistics in the epilogue (A/B switch; at small batch
+        # the stand-alone reduction is a latency-bound launch, at large batch the epilogue-bound 64/128-channel layers lose more than it costs)
+        self.fuse_conv_stats_all = os.environ.get("HK_CONV_STATS", "1") == "all"
         # max-pool forward records the winning taps (one pass over the stem map instead of two); HK_MAXPOOL_IDX=0: argmax pass in the backward
         self.maxpool_idx = os.environ.get("HK_MAXPOOL_IDX", "1") != "0"
         offs_acc, tot = [], 0
@@ -207,7 +210,7 @@ class TrainEngine:
     def _conv_bn(self, c: _ConvT, x, out, relu: bool, residual=None, ws=None) -> int:
         """raw conv -> batch statistics (+ running stats) -> fused normalise (+ shortcut) (+ ReLU)."""
         bn = c.bn
-        if self.use_bn_acc and self.fuse_conv_stats and c.k == 3 and c.cout >= 256:
+        if self.use_bn_acc and self.fuse_conv_stats and ((c.k == 3 and c.cout >= 256) or (self.fuse_conv_stats_all and c is not self.stem)):
             # the conv epilogue gathers sum y / sum y^2 of the tile it stores: no statistics pass over the activation.  Only where the
             # epilogue hides under a long mainloop (3x3 convs of layers 3-4: 36 / 72 K blocks per tile); the 64/128-channel layers and
             # the 1x1 downsample convs are epilogue-bound and lose more than the stand-alone reduction costs (measured per launch)
