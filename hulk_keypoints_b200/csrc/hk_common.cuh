@@ -63,6 +63,11 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // ---- device helpers ----
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t v) { return __uint_as_float(((uint32_t)v) << 16); }
 
+// ToTensor's uint8 / 255 (reference src/dataset.py:16) for operands that are rounded to bf16 right away: for every byte value b,
+// bf16_rn(float(b) / 255.0f) == bf16_rn(float(b) * kInv255) (the fp32 results differ by one ulp for 126 of the 256 values, never across
+// a bf16 rounding boundary; checked exhaustively, tests/test_host_api.py::test_u8_scale_by_reciprocal_is_exact_in_bf16), so the tensor-core
+// stems multiply instead of issuing three IEEE divisions per pixel.  The fp32 correctness mode keeps the division.
+constexpr float kInv255 = 1.0f / 255.0f;
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -276,12 +276,12 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const int row = p >= SP_PX ? 1 : 0, x = p - row * SP_PX;
             float f0, f1, f2;
             if constexpr (U8) {
-              // byte 3x+c of the row lives in box (3x+c)/208; ToTensor semantics (reference dataset.py:16): uint8 / 255 in fp32
+              // byte 3x+c of the row lives in box (3x+c)/208; ToTensor semantics (reference dataset.py:16): bf16_rn(uint8 / 255) == bf16_rn(uint8 * kInv255), see hk_common.cuh
               const int e = 3 * x + u8_lead;
               auto at = [&](int byte) { const int k = byte / SP_U8_BOX; return src[k * SP_U8_BOX_PITCH + row * SP_U8_BOX + (byte - k * SP_U8_BOX)]; };
-              f0 = __fdiv_rn((float)at(e), 255.0f);
-              f1 = __fdiv_rn((float)at(e + 1), 255.0f);
-              f2 = __fdiv_rn((float)at(e + 2), 255.0f);
+              f0 = (float)at(e) * kInv255;
+              f1 = (float)at(e + 1) * kInv255;
+              f2 = (float)at(e + 2) * kInv255;
             } else {
               const int xs = x + SP_F32_LEAD;
               const int k = xs >= SP_F32_BOX ? 1 : 0, xi = xs - k * SP_F32_BOX;

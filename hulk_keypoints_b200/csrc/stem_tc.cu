@@ -147,11 +147,11 @@ __device__ __forceinline__ void stem_store_patch(const StemPatch<U8>& p, __nv_bf
         if (t == 0 || lane < ST_PATCH_W - 32) {
           float f0, f1, f2;
           if constexpr (U8) {
-            // ToTensor semantics (reference dataset.py:16): uint8 / 255 in fp32, then the bf16 operand rounding
+            // ToTensor semantics (reference dataset.py:16): bf16_rn(uint8 / 255) == bf16_rn(uint8 * kInv255) for all 256 values (hk_common.cuh)
             const uint32_t v = p.v[j][t][0];
-            f0 = __fdiv_rn((float)(v & 0xffu), 255.0f);
-            f1 = __fdiv_rn((float)((v >> 8) & 0xffu), 255.0f);
-            f2 = __fdiv_rn((float)((v >> 16) & 0xffu), 255.0f);
+            f0 = (float)(v & 0xffu) * kInv255;
+            f1 = (float)((v >> 8) & 0xffu) * kInv255;
+            f2 = (float)((v >> 16) & 0xffu) * kInv255;
           } else {
             f0 = __uint_as_float(p.v[j][t][0]);
             f1 = __uint_as_float(p.v[j][t][1]);

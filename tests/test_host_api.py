@@ -125,6 +125,16 @@ def test_transform_matches_totensor():
     assert torch.equal(t, torch.from_numpy(img).permute(2, 0, 1).float().div(255))
 
 
+def test_u8_scale_by_reciprocal_is_exact_in_bf16():
+    """The tensor-core stems scale uint8 pixels by the fp32 constant 1/255 instead of dividing (csrc/hk_common.cuh kInv255): after the bf16
+    operand rounding the two agree for every byte value, so the uint8 path stays bit-identical to ToTensor (reference src/dataset.py:16)
+    followed by the bf16 rounding."""
+    b = np.arange(256, dtype=np.float32)
+    div = torch.from_numpy(b / np.float32(255.0)).to(torch.bfloat16)
+    mul = torch.from_numpy(b * (np.float32(1.0) / np.float32(255.0))).to(torch.bfloat16)
+    assert torch.equal(div, mul)
+
+
 def test_shard_range_partitions():
     for total in (0, 1, 7, 64, 4096, 4097):
         for world in (1, 2, 3, 4, 8):
