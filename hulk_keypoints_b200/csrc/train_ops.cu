@@ -19,7 +19,10 @@ __device__ __forceinline__ float gauss_value(float x, float y, float u, float v,
   return expf(__fdiv_rn(-d2, denom));
 }
 
-// grid: (ceil(W/4 * H / threads), B*K).  Each thread produces 4 consecutive x of one row.
+// grid: (ceil(W/4 * H / threads), B*K).  Each thread produces 4 values.  fp32 output: 4 consecutive x (one 16-byte store; a warp writes
+// 512 contiguous bytes).  fp64 output: two PAIRS 64 elements apart inside the warp's 128-element run, so that each of the two 16-byte
+// store instructions of a warp covers 512 contiguous bytes -- with 4 consecutive doubles per thread every store instruction filled only
+// half of each 32-byte sector it touched: 169 us = 3.7 TB/s at 64x4x480x640, now 127 us = 5.0 TB/s (tools/diag_decode.py).
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 gauss_targets_kernel(const float* __restrict__ uv, int H, int W, float denom, OutT* __restrict__ out) {
@@ -29,6 +32,26 @@ gauss_targets_kernel(const float* __restrict__ uv, int H, int W, float denom, Ou
   const unsigned total = (unsigned)wq * (unsigned)H;
   OutT* dst = out + (size_t)map * H * W;
   const bool vec = (W & 3) == 0;
+  if constexpr (sizeof(OutT) == 8) if ((W & 1) == 0) {
+    // element pairs; a warp owns 128 consecutive elements of the flattened map per iteration (pairs may fall into different rows)
+    const unsigned hw = (unsigned)H * (unsigned)W;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned base = (((blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * 128u; base < hw; base += warps * 128u) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const unsigned e = base + (unsigned)h * 64u + 2u * lane;
+        if (e < hw) {
+          const int y = (int)(e / (unsigned)W);
+          const int x = (int)(e - (unsigned)y * (unsigned)W);   // even, and x + 1 < W because W is even
+          const float g0 = gauss_value((float)x, (float)y, u, v, denom);
+          const float g1 = gauss_value((float)(x + 1), (float)y, u, v, denom);
+          __stcs(reinterpret_cast<double2*>(dst + e), make_double2((double)g0, (double)g1));
+        }
+      }
+    }
+    return;
+  }
   for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const int y = (int)(t / (unsigned)wq);
     const int x0 = (int)(t - (unsigned)y * (unsigned)wq) << 2;

@@ -83,6 +83,10 @@ def test_gauss_targets_batched_ragged_width():
     uv = torch.tensor([[[3.0, 2.0], [0.0, 0.0]], [[8.5, 4.25], [10.0, 6.0]]])
     g = ops.gauss_targets(uv.to(dev()), 7, 11, 2.0).cpu().numpy()   # W not a multiple of 4
     assert _ulp_close(g, O.gauss_targets(uv.numpy(), 7, 11, 2.0))
+    g = ops.gauss_targets(uv.to(dev()), 9, 10, 2.0).cpu().numpy()   # even W, not a multiple of 4, map smaller than one warp run of 128
+    assert _ulp_close(g, O.gauss_targets(uv.numpy(), 9, 10, 2.0))
+    g = ops.gauss_targets(uv.to(dev()), 33, 26, 2.0).cpu().numpy()  # pairs of one warp run fall into different rows
+    assert _ulp_close(g, O.gauss_targets(uv.numpy(), 33, 26, 2.0))
 
 
 def test_dropin_gauss_2d_batch(golden):
