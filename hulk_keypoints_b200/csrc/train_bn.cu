@@ -288,12 +288,9 @@ constexpr int BN_ACC_MAX_C = 2048;
 
 // Reduce kernels run as clusters of 8 CTAs: every CTA leaves its 2*C block sums in shared memory, CTA 0 of the cluster adds the eight
 // of them over DSMEM in rank order (fixed order: deterministic) and issues the atomics -- 1/8 of the atomic traffic of a per-CTA scheme
-// (at C = 512 and 592 blocks that was 1.2 M same-address L2 atomics per launch, ~8 us; now 74 clusters x 2 K).
+// (at C = 512 and 592 blocks that was 1.2 M same-address L2 atomics per launch, ~8 us; now ~71 clusters x 2 K).
 constexpr int BN_CLUSTER = 8;
-#ifndef BN_ACC_MAX_BLOCKS_V
-#define BN_ACC_MAX_BLOCKS_V 1184
-#endif
-constexpr int BN_ACC_MAX_BLOCKS = BN_ACC_MAX_BLOCKS_V;   // at most one resident wave of 8-CTA clusters (148 SMs x up to 8 blocks)
+constexpr int BN_ACC_MAX_BLOCKS = 1184;   // upper bound only (148 SMs x 8 blocks); the grid is one resident wave of clusters, see bn_grid_acc_rows
 
 // Tunables of the accumulator kernels (tools/diag_bn_kernels.py + tools/build_bn_variants.sh).  These kernels are pure streams:
 // their throughput is the bytes they keep in flight (resident threads x independent 16-byte loads per thread), not their arithmetic --
