@@ -8,6 +8,7 @@ including the 996 dead fc rows, which receive zero gradient but are still decaye
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Iterable
 
 import torch
@@ -26,6 +27,9 @@ class FusedAdam:
             raise RuntimeError("FusedAdam needs fp32 CUDA parameters on one device (no CPU fallback)")
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.step_count = 0
+        # data-parallel exchange of bf16-rounded gradients (half the bytes; see all_reduce_range_async); opt-in
+        self.bf16_exchange = os.environ.get("HK_DP_BF16_GRADS", "0") == "1"
+        self._bf16_buf = None
         # every tensor starts on a 16-byte boundary inside the flat buffers
         offs, total = [], 0
         for p in self.params:
@@ -85,6 +89,16 @@ class FusedAdam:
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or end <= begin:
             return None
         avg = self._avg_op()
+        if self.bf16_exchange and avg is not None:
+            # opt-in (HK_DP_BF16_GRADS=1): the range travels as bf16 (half the bytes of the exchange); every rank rounds its fp32 gradients
+            # once, NCCL averages in bf16, finish_all_reduce() widens the result back into the fp32 buffer Adam reads (fp32 master
+            # statistics and parameters are untouched).  Not bit-identical to the fp32 exchange -- off by default.
+            if self._bf16_buf is None or self._bf16_buf.numel() != self.numel:
+                self._bf16_buf = torch.empty(self.numel, device=self.flat_grad.device, dtype=torch.bfloat16)
+            half = self._bf16_buf[begin:end]
+            half.copy_(self.flat_grad[begin:end])
+            work = dist.all_reduce(half, op=avg, async_op=True)
+            return (work, begin, end, "bf16")
         work = dist.all_reduce(self.flat_grad[begin:end], op=avg if avg is not None else dist.ReduceOp.SUM, async_op=True)
         return (work, begin, end, avg is not None)
 
@@ -96,7 +110,9 @@ class FusedAdam:
                 continue
             work, begin, end, averaged = w
             work.wait()
-            if not averaged:
+            if averaged == "bf16":
+                self.flat_grad[begin:end].copy_(self._bf16_buf[begin:end])
+            elif not averaged:
                 self.flat_grad[begin:end].div_(dist.get_world_size())
 
     @torch.no_grad()
